@@ -580,6 +580,10 @@ def preworld4d_simple_test(sd, pc, inputs, temporal_ego_states, stages=None):
     res = {}
     first = 1 if pc.if_post_finetune else 2
     fn = occ_from_head if pc.if_post_finetune else occ_from_density
+    if stages is not None:
+        stages['voxel_feats'] = vf
+        if pc.if_post_finetune:
+            stages['logits'] = occ_from_head(sd, pc, vf, True)[2]
     occ, geo_occ = fn(sd, pc, vf)
     res['semantic_occ_0s'], res['geo_occ_0s'] = [occ], [geo_occ]
     for k in range(6):

@@ -125,19 +125,14 @@ def r50_model_cfg(model_cfg, input_size=(256, 704), depth=50):
     return cfg
 
 
-@torch.no_grad()
-def randomize_norm_stats_(module, seed=0):
-    """Make every BatchNorm a non-identity: running_mean
-    ~N(0,0.1), running_var~U(0.5,1.5), gamma~U(0.5,1.5), beta~N(0,0.1)."""
-    g = torch.Generator().manual_seed(seed)
-    for m in module.modules():
-        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
-            n = m.num_features
-            m.running_mean.copy_(torch.randn(n, generator=g) * 0.1)
-            m.running_var.copy_(torch.rand(n, generator=g) + 0.5)
-            m.weight.copy_(torch.rand(n, generator=g) + 0.5)
-            m.bias.copy_(torch.randn(n, generator=g) * 0.1)
-    return module
+def _key_generator(key, seed):
+    """Per-tensor generator seeded by (state_dict key, seed) so the synthetic
+    weights depend only on the key names -- the reference's modules and ours
+    get bit-identical values regardless of module construction order."""
+    import zlib
+    g = torch.Generator()
+    g.manual_seed((zlib.crc32(key.encode()) * 2654435761 + seed) % (2 ** 63))
+    return g
 
 
 _RESIDUAL_TAIL = ('bn3', 'bn2', 'conv2.bn')
@@ -145,25 +140,31 @@ _RESIDUAL_TAIL = ('bn3', 'bn2', 'conv2.bn')
 
 @torch.no_grad()
 def lively_init_(module, seed=0, residual_gain=0.25):
-    """Random init that keeps activations O(1) through the ReLU stacks so the
-    synthetic depth distributions and argmax grids are not degenerate:
-    He-normal conv/linear weights, N(0, 0.1) biases, non-identity norm
-    statistics, and a damped gamma on the last norm of every residual branch
-    (otherwise ~30 residual adds blow the scale up by 1e6 and every softmax
-    saturates)."""
-    g = torch.Generator().manual_seed(seed)
-    for m in module.modules():
+    """Deterministic, key-addressed random init that keeps activations O(1)
+    through the ReLU stacks so the synthetic depth distributions and argmax
+    grids are not degenerate: He-normal conv/linear weights, N(0, 0.1) biases,
+    non-identity norm statistics (running_mean~N(0,0.1),
+    running_var~U(0.5,1.5), gamma~U(0.5,1.5), beta~N(0,0.1)) and a damped gamma
+    on the last norm of every residual branch (otherwise ~30 residual adds blow
+    the scale up by 1e6 and every softmax saturates)."""
+    for name, m in module.named_modules():
         if isinstance(m, (torch.nn.modules.conv._ConvNd, torch.nn.Linear)):
             fan_in = m.weight[0].numel()
+            g = _key_generator(name + '.weight', seed)
             m.weight.copy_(torch.randn(m.weight.shape, generator=g)
                            * math.sqrt(2.0 / fan_in))
             if m.bias is not None:
+                g = _key_generator(name + '.bias', seed)
                 m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
-    randomize_norm_stats_(module, seed + 1)
-    for name, m in module.named_modules():
-        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and \
-                name.endswith(_RESIDUAL_TAIL):
-            m.weight.mul_(residual_gain)
-        if name.endswith('depth_net.depth_conv.4'):
-            m.weight.mul_(0.15)       # depth logits ~N(0,2): soft depth bins
+            if name.endswith('depth_net.depth_conv.4'):
+                m.weight.mul_(0.15)   # depth logits ~N(0,2): soft depth bins
+        elif isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            n = m.num_features
+            g = _key_generator(name + '.bn', seed)
+            m.running_mean.copy_(torch.randn(n, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(n, generator=g) + 0.5)
+            m.weight.copy_(torch.rand(n, generator=g) + 0.5)
+            m.bias.copy_(torch.randn(n, generator=g) * 0.1)
+            if name.endswith(_RESIDUAL_TAIL):
+                m.weight.mul_(residual_gain)
     return module
