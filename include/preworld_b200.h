@@ -1,0 +1,257 @@
+/*
+ * preworld_b200 -- C ABI of the B200 (sm_100a) camera->voxel occupancy path.
+ *
+ * Drop-in boundary for getterupper/PreWorld @ 0b0e021.  Every entry point
+ *   - takes raw DEVICE pointers + sizes, never allocates, never synchronises,
+ *   - launches on the caller's stream (`stream` is a cudaStream_t; pass
+ *     torch.cuda.current_stream().cuda_stream),
+ *   - returns 0 on success, a cudaError_t value (>0) on a CUDA failure or
+ *     PW_ERR_INVALID_ARGUMENT (-1) on a contract violation.
+ * The reference's own FFI has no error checking and uses the legacy default
+ * stream (mmdet3d/ops/bev_pool_v2/src/bev_pool_cuda.cu:125-140).
+ *
+ * Layout convention: all feature maps are CHANNELS-LAST fp32
+ * (images [N,H,W,C], volumes [B,Z,Y,X,C]) -- i.e. torch tensors of the
+ * reference's logical shapes [N,C,H,W] / [B,C,Z,Y,X] carrying
+ * torch.channels_last / channels_last_3d strides.  `*_ld` arguments are the
+ * element stride between consecutive pixels/voxels (>= channel count), which
+ * lets a kernel read or write a channel slice of a wider (concatenated)
+ * tensor in place.
+ *
+ * Each declaration cites the reference interface it replaces.
+ */
+#ifndef PREWORLD_B200_H_
+#define PREWORLD_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PW_ABI_VERSION 1
+int pw_abi_version(void);
+/* Number of kernel launches issued through this library since load (the
+ * `gpu_launches` figure of bench.py). */
+long long pw_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Convolution / linear (fp32, implicit GEMM, fused affine+residual+act).
+ * Replaces torch.nn.Conv2d/Conv3d/Linear (+BatchNorm, +ReLU/Softplus/Sigmoid)
+ * groups: mmdet ResNet; necks/fpn.py:154-203; necks/view_transformer.py:
+ * 473-638; backbones/resnet.py:88-184; necks/lss_fpn.py:120-148;
+ * detectors/preworld.py:72-105; heads/occupancy_head.py:81-177;
+ * detectors/preworld_temporal_traj.py:119-150.
+ *   y[m, co] = act( (sum_k x[..] * w[k, co]) * scale[co] + bias[co]
+ *                   + residual[m, co] )
+ * x: [n,d,h,w,in_ld] (first `cin` channels used); w: [kd*kh*kw*cin, w_ld]
+ * (k ordered tap-major then cin; w_ld >= cout padded with zeros, w_ld%4==0);
+ * scale/bias/residual may be NULL.  act: 0 none, 1 relu, 2 softplus
+ * (threshold 20), 3 sigmoid.  cin%4 == 0, in_ld%4 == 0, x and w 16-byte
+ * aligned.
+ * ---------------------------------------------------------------------- */
+typedef struct pw_conv_desc {
+  int n, d, h, w, cin, in_ld;
+  int od, oh, ow, cout, out_ld, res_ld, w_ld;
+  int kd, kh, kw;
+  int sd, sh, sw;
+  int pd, ph, pw;
+  int dd, dh, dw;
+  int act;
+  int act_channels; /* >0: only output channels [0, act_channels) get `act`
+                       (fuses a ReLU branch and a linear shortcut branch that
+                       read the same input into one launch); 0: all */
+} pw_conv_desc;
+
+int pw_conv_fwd(const pw_conv_desc* desc, const float* x, const float* w,
+                const float* scale, const float* bias, const float* residual,
+                float* y, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Image-side element-wise helpers (all channels-last).
+ * ---------------------------------------------------------------------- */
+/* imgs [n,c,h,w] (NCHW as delivered by the loader, loading.py:1124-1134;
+ * consecutive images `img_stride` elements apart, so one frame of the
+ * camera-major [B, N*T, 3, H, W] batch is read in place)
+ * -> [n,h,w,c_pad] with zero padding channels. */
+int pw_nchw_to_nhwc_pad(const float* x, long long img_stride, float* y, int n,
+                        int c, int h, int w, int c_pad, void* stream);
+/* channels-last -> NCHW copy: y[n,c,p] = x[n,p,c0+c]  (API edges only). */
+int pw_nhwc_to_nchw(const float* x, int x_ld, float* y, int n, int c,
+                    long long pixels, void* stream);
+/* mmdet ResNet stem nn.MaxPool2d(kernel_size=3, stride=2, padding=1). */
+int pw_maxpool3x3s2(const float* x, float* y, int n, int h, int w, int c,
+                    int oh, int ow, void* stream);
+/* necks/fpn.py:164-172: y[n,oh,ow,:] += x[n, floor(oh*h/OH), floor(ow*w/OW),:]
+ * (F.interpolate mode='nearest' to the finer map's size, added in place). */
+int pw_upsample_nearest_add(const float* x, float* y, int n, int h, int w,
+                            int oh, int ow, int c, void* stream);
+/* SELayer gate, view_transformer.py:440-470: y[n,p,c] = x[n,p,c]*gate[n,c]
+ * (gate already passed through the sigmoid). */
+int pw_scale_channels(const float* x, int x_ld, const float* gate, float* y,
+                      int y_ld, int n, long long pixels, int c, void* stream);
+/* nn.AdaptiveAvgPool2d((1,1)): y[n,c] = mean_p x[n,p,c]. */
+int pw_global_avgpool(const float* x, int x_ld, float* y, int n,
+                      long long pixels, int c, void* stream);
+/* ASPP image-pool branch, view_transformer.py:407-410: bilinear upsampling of
+ * a 1x1 map == broadcast.  y[n,p,c0:c0+c] = v[n,c]. */
+int pw_broadcast_channels(const float* v, float* y, int y_ld, int n,
+                          long long pixels, int c, void* stream);
+/* view_transformer.py:801: depth = softmax over the D logits of every pixel.
+ * logits [rows, in_ld] (first d channels) -> prob_cl [rows, d] (channels-last,
+ * may be NULL) and prob_planar [n, d, pixels] (the reference's [B*N,D,H,W]
+ * layout, rows = n*pixels; may be NULL). */
+int pw_softmax_depth(const float* logits, int in_ld, float* prob_cl,
+                     float* prob_planar, int n, long long pixels, int d,
+                     void* stream);
+
+/* ------------------------------------------------------------------------
+ * Stereo cost volume, view_transformer.py:546-604 (gen_grid +
+ * calculate_cost_volumn): for each (cam, depth bin, h4, w4) warp the previous
+ * frame's stereo feature with the plane-sweep homography, bilinear sample
+ * (zeros padding, align_corners=True), cost = sum_c |curr - warp|, + bias
+ * where the warped last-group channel 0 is exactly 0, negate, softmax over D.
+ *   curr/prev: [n,h,w,c] channels-last stereo features (c % 4 == 0);
+ *   cam: [n, PW_CV_CAM_FLOATS] per-camera constants built by the host
+ *   (inv(post_rot), post_tran, k2s_rot @ inv(K), k2s_tran, K, post_rot[:2,:2],
+ *   post_tran[:2]);  frustum x/y/depth values; out: [n,h,w,d] channels-last.
+ * ---------------------------------------------------------------------- */
+#define PW_CV_CAM_FLOATS 48
+int pw_cost_volume(const float* curr, const float* prev, const float* cam,
+                   const float* xs, const float* ys, const float* ds, float* out,
+                   int n, int h, int w, int c, int d, float bias, int img_h,
+                   int img_w, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Voxel lift.
+ * ---------------------------------------------------------------------- */
+/* Drop-in for the reference FFI  bev_pool_v2(c, n_intervals, depth, feat,
+ * ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths, out)
+ * (mmdet3d/ops/bev_pool_v2/src/bev_pool.cpp:7-14,30-57; kernel
+ * src/bev_pool_cuda.cu:21-48).  Same argument meaning; `out` must be
+ * zero-initialised by the caller exactly as bev_pool.py:27 does. */
+int pw_bev_pool_v2(int c, int n_intervals, const float* depth, const float* feat,
+                   const int* ranks_depth, const int* ranks_feat,
+                   const int* ranks_bev, const int* interval_starts,
+                   const int* interval_lengths, float* out, void* stream);
+
+/* Fused B200-native lift: geometry -> voxel rank -> per-voxel point lists ->
+ * dense pooled volume, replacing get_lidar_coor + voxel_pooling_prepare_v2 +
+ * bev_pool_v2 + the zero-fill and the permute copy (view_transformer.py:
+ * 114-153,176-261; bev_pool.py:27,91).
+ *   cam: [b*n, PW_LIFT_CAM_FLOATS] = inv(post_rot)[9], post_tran[3],
+ *        sensor2ego[:3,:3] @ inv(K) [9], sensor2ego[:3,3] [3]
+ *   bda: [b,9]; xs[w], ys[h], ds[d]: frustum coordinates (device)
+ *   lower[3], interval[3]: grid lower bound / voxel size -- HOST pointers
+ *   depth: [b*n, d, h, w] probabilities (planar, as the reference)
+ *   feat:  [b*n, h, w, feat_ld] channels-last context features (c used)
+ *   out:   [b, gz, gy, gx, c] channels-last, EVERY voxel written (no memset)
+ *   workspace: pw_lift_workspace_bytes(...) bytes of device scratch.
+ * Summation order inside a voxel is ascending frustum-point index -- the
+ * order a stable sort gives the reference (its argsort is unstable,
+ * view_transformer.py:246, so the reference's own order is unspecified). */
+#define PW_LIFT_CAM_FLOATS 24
+long long pw_lift_workspace_bytes(int b, int n, int d, int h, int w, int gx,
+                                  int gy, int gz);
+int pw_lift_fused(const float* depth, const float* feat, int feat_ld,
+                  const float* cam, const float* bda, const float* xs,
+                  const float* ys, const float* ds, const float* lower,
+                  const float* interval, int b, int n, int d, int h, int w,
+                  int c, int gx, int gy, int gz, float* out, void* workspace,
+                  void* stream);
+/* Per-camera constant tables (device in, device out, no host round trip):
+ * the torch.inverse/matmul prologues of get_lidar_coor
+ * (view_transformer.py:141-150) and DepthNet.gen_grid (:552-566).
+ * sensor2ego / k2s_sensor [n,4,4], intrin/post_rot [n,3,3], post_tran [n,3]
+ * -> cam [n, PW_LIFT_CAM_FLOATS] resp. [n, PW_CV_CAM_FLOATS]. */
+int pw_lift_camera_params(int n, const float* sensor2ego, const float* intrin,
+                          const float* post_rot, const float* post_tran,
+                          float* cam, void* stream);
+int pw_cv_camera_params(int n, const float* k2s_sensor, const float* intrin,
+                        const float* post_rot, const float* post_tran,
+                        float* cam, void* stream);
+/* Only the rank computation (voxel id or -1 per frustum point); exposed for
+ * parity tests against voxel_pooling_prepare_v2. */
+int pw_lift_ranks(const float* cam, const float* bda, const float* xs,
+                  const float* ys, const float* ds, const float* lower,
+                  const float* interval, int b, int n, int d, int h, int w,
+                  int gx, int gy, int gz, int* rank, void* stream);
+
+/* ------------------------------------------------------------------------
+ * 3-D encoder helpers.
+ * ---------------------------------------------------------------------- */
+/* necks/lss_fpn.py:139-146: F.interpolate(scale_factor=s, mode='trilinear',
+ * align_corners=True) of x [b,z,y,x,c] written into channel slice of
+ * y [b,oz,oy,ox,y_ld]. */
+int pw_upsample_trilinear(const float* x, int x_ld, float* y, int y_ld, int b,
+                          int z, int yy, int xx, int c, int oz, int oy, int ox,
+                          void* stream);
+/* Strided channel-slice copy y[p, 0:c] = x[p, 0:c] (concatenation). */
+int pw_copy_channels(const float* x, int x_ld, float* y, int y_ld,
+                     long long pixels, int c, void* stream);
+/* preworld.py:202-203 / occupancy argmax: logits [zyx voxels, ld] in the
+ * library's [Z,Y,X] voxel order -> uint8 grid in the reference's [X,Y,Z] order
+ * (first maximum wins, as torch.argmax). */
+int pw_argmax_zyx_to_xyz(const float* logits, int ld, int ncls, unsigned char* occ,
+                         int gx, int gy, int gz, void* stream);
+/* preworld.py:173-194 density path: occ = density>thr ? argmax(semantic) : 17;
+ * density [voxels] , semantic [voxels, ld]. */
+int pw_density_occ_zyx_to_xyz(const float* density, int density_ld,
+                              const float* semantic, int ld, int ncls, float thr,
+                              int empty_idx, unsigned char* occ, unsigned char* geo,
+                              int gx, int gy, int gz, void* stream);
+/* [b,z,y,x,c] (library order) -> [b,x,y,z,c] (the reference's voxel_feats
+ * order, preworld.py:169) for API edges. */
+int pw_zyx_to_xyz(const float* x, float* y, int b, int gz, int gy, int gx, int c,
+                  void* stream);
+
+/* ------------------------------------------------------------------------
+ * Volume rendering (nerf/nerf_head.py:32-55,165-269,332-353 + the CUDA ops
+ * nerf/cuda/render_utils_kernel.cu:431-443,577-651 and
+ * ub360_utils_kernel.cu:12-32), one warp per ray.
+ * The three drop-ins keep the reference extension signatures
+ * (render_utils.cpp:170-184, ub360_utils.cpp:20-22) on raw pointers.
+ * ---------------------------------------------------------------------- */
+int pw_raw2alpha(const float* density, float shift, float interval, long long n,
+                 float* exp_d, float* alpha, void* stream);
+int pw_alpha2weight(const float* alpha, const long long* ray_id, long long n_pts,
+                    int n_rays, float* weight, float* T, float* alphainv_last,
+                    long long* i_start, long long* i_end, void* stream);
+int pw_cumdist_thres(const float* dist, float thres, int n_rays, int n_pts,
+                     unsigned char* mask, void* stream);
+/* Fused ray march: rays [r,16] (datasets/ray.py:49-56), volumes density
+ * [voxels], semantic [voxels,17], color [voxels,3] with voxel strides given in
+ * the descriptor (either voxel order works without a copy) -> per ray
+ * render_depth, render_semantic[17], render_color[3], alphainv_last, and a
+ * valid flag (0 < gt depth <= 52).  Invalid rays get zeros.  t_vals[n_steps]
+ * are the ray parameters of sample_ray (nerf_head.py:36-44; 391 inner + 26
+ * outer mid-points), computed once by the host with the reference's own
+ * torch.linspace expressions. */
+typedef struct pw_render_desc {
+  float scene_center[3];
+  float scene_radius[3];
+  float xyz_min[3];
+  float xyz_max[3];
+  float bg_len;
+  float act_shift;
+  float interval;
+  float step_size;
+  float fast_color_thres;
+  float radius;
+  float max_depth;
+  int world_len;
+  int gx, gy, gz;
+  int n_sem;
+  long long vs_x, vs_y, vs_z; /* voxel strides (in voxels) of the volumes:
+                                 library order [Z,Y,X] -> (1, gx, gx*gy);
+                                 reference order [X,Y,Z] -> (gy*gz, gz, 1) */
+} pw_render_desc;
+int pw_render_rays(const pw_render_desc* desc, const float* rays, int n_rays,
+                   const float* t_vals, int n_steps, const float* bda,
+                   const float* density, int density_ld,
+                   const float* semantic, int sem_ld, const float* color,
+                   int col_ld, float* out_depth, float* out_sem, float* out_col,
+                   float* out_last, unsigned char* out_valid, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PREWORLD_B200_H_ */

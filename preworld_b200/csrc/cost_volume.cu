@@ -1,0 +1,143 @@
+// Stereo plane-sweep cost volume, fused: replaces DepthNet.gen_grid +
+// calculate_cost_volumn (necks/view_transformer.py:546-604), i.e. the 64
+// F.grid_sample launches over 4-channel groups, the [B*N,4,D*H,W] warped
+// intermediates (~6 GB of traffic per frame), the |.|-sum, the bias mask and
+// the softmax over D.  One warp per stereo pixel (cam, h4, w4): the current
+// feature vector stays in registers, the D warped samples are gathered from
+// the channels-last previous-frame feature (each bilinear corner is one
+// contiguous C*4-byte row), costs are reduced with warp shuffles.
+#include "common.cuh"
+#include "../../include/preworld_b200.h"
+
+namespace {
+
+__device__ __forceinline__ float dot3(const float* m, float x, float y, float z) {
+  float acc = m[0] * x;
+  acc = fmaf(m[1], y, acc);
+  return fmaf(m[2], z, acc);
+}
+
+template <int Q>   // float4 chunks per lane: C == 128*Q
+__global__ void __launch_bounds__(256)
+cost_volume_kernel(const float* __restrict__ curr, const float* __restrict__ prev,
+                   const float* __restrict__ cam, const float* __restrict__ xs,
+                   const float* __restrict__ ys, const float* __restrict__ ds,
+                   float* __restrict__ out, int n, int H, int W, int C, int D, float bias,
+                   float wi_m1, float hi_m1) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long total = (long long)n * H * W;
+  if (warp >= total) return;
+  const int w = (int)(warp % W);
+  const int h = (int)((warp / W) % H);
+  const int img = (int)(warp / ((long long)W * H));
+  const float* cm = cam + (long long)img * PW_CV_CAM_FLOATS;
+
+  float4 cur[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q)
+    cur[q] = pw_ldg4(curr + warp * C + q * 128 + lane * 4);
+
+  // frustum pixel (downsample-4 grid), image augmentation undone
+  const float fx = __ldg(xs + w) - cm[9], fy = __ldg(ys + h) - cm[10];
+  const int own_q = (C - 4) / 128, own_lane = ((C - 4) % 128) / 4;
+  const float* pimg = prev + (long long)img * H * W * C;
+
+  float my_cost[4] = {0.f, 0.f, 0.f, 0.f};   // bins lane, lane+32, lane+64, lane+96
+  for (int d = 0; d < D; ++d) {
+    float pz = __ldg(ds + d) - cm[11];
+    float qx = dot3(cm + 0, fx, fy, pz), qy = dot3(cm + 3, fx, fy, pz), qz = dot3(cm + 6, fx, fy, pz);
+    qx *= qz; qy *= qz;
+    float sx = dot3(cm + 12, qx, qy, qz) + cm[21];
+    float sy = dot3(cm + 15, qx, qy, qz) + cm[22];
+    float sz = dot3(cm + 18, qx, qy, qz) + cm[23];
+    bool neg = sz < 1e-3f;
+    float ux = dot3(cm + 24, sx, sy, sz), uy = dot3(cm + 27, sx, sy, sz), uz = dot3(cm + 30, sx, sy, sz);
+    ux = __fdiv_rn(ux, uz); uy = __fdiv_rn(uy, uz);
+    float vx = fmaf(cm[34], uy, cm[33] * ux) + cm[37];
+    float vy = fmaf(cm[36], uy, cm[35] * ux) + cm[38];
+    float gx = __fdiv_rn(vx, wi_m1) * 2.f - 1.f, gy = __fdiv_rn(vy, hi_m1) * 2.f - 1.f;
+    if (neg) { gx = -2.f; gy = -2.f; }
+    // grid_sample(align_corners=True, padding zeros) on the [H,W] feature
+    float ix = ((gx + 1.f) * 0.5f) * (float)(W - 1);
+    float iy = ((gy + 1.f) * 0.5f) * (float)(H - 1);
+    float x0f = floorf(ix), y0f = floorf(iy);
+    float wnw = (x0f + 1.f - ix) * (y0f + 1.f - iy);
+    float wne = (ix - x0f) * (y0f + 1.f - iy);
+    float wsw = (x0f + 1.f - ix) * (iy - y0f);
+    float wse = (ix - x0f) * (iy - y0f);
+    // clamp before the int cast so far-away samples cannot overflow
+    int x0 = (int)fminf(fmaxf(x0f, -2.f), (float)W + 1.f);
+    int y0 = (int)fminf(fmaxf(y0f, -2.f), (float)H + 1.f);
+    bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
+    bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
+    const float* r00 = pimg + ((long long)y0 * W + x0) * C;
+    float part = 0.f;
+    bool zero_flag = false;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int off = q * 128 + lane * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vy0 && vx0) { float4 v = pw_ldg4(r00 + off);
+        acc.x = v.x * wnw; acc.y = v.y * wnw; acc.z = v.z * wnw; acc.w = v.w * wnw; }
+      if (vy0 && vx1) { float4 v = pw_ldg4(r00 + C + off);
+        acc.x = fmaf(v.x, wne, acc.x); acc.y = fmaf(v.y, wne, acc.y);
+        acc.z = fmaf(v.z, wne, acc.z); acc.w = fmaf(v.w, wne, acc.w); }
+      if (vy1 && vx0) { float4 v = pw_ldg4(r00 + (long long)W * C + off);
+        acc.x = fmaf(v.x, wsw, acc.x); acc.y = fmaf(v.y, wsw, acc.y);
+        acc.z = fmaf(v.z, wsw, acc.z); acc.w = fmaf(v.w, wsw, acc.w); }
+      if (vy1 && vx1) { float4 v = pw_ldg4(r00 + (long long)W * C + C + off);
+        acc.x = fmaf(v.x, wse, acc.x); acc.y = fmaf(v.y, wse, acc.y);
+        acc.z = fmaf(v.z, wse, acc.z); acc.w = fmaf(v.w, wse, acc.w); }
+      part += ((fabsf(cur[q].x - acc.x) + fabsf(cur[q].y - acc.y)) + fabsf(cur[q].z - acc.z)) +
+              fabsf(cur[q].w - acc.w);
+      if (q == own_q && lane == own_lane) zero_flag = (acc.x == 0.f);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    zero_flag = __shfl_sync(0xffffffffu, (int)zero_flag, own_lane) != 0;
+    if (bias != 0.f && zero_flag) part += bias;
+    if ((d & 31) == lane) my_cost[d >> 5] = part;
+  }
+
+  // softmax over D of -cost
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k * 32 + lane < D) m = fmaxf(m, -my_cost[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float e[4], s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    e[k] = (k * 32 + lane < D) ? expf(-my_cost[k] - m) : 0.f;
+    s += e[k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k * 32 + lane < D) out[warp * D + k * 32 + lane] = e[k] / s;
+}
+
+}  // namespace
+
+PW_API int pw_cost_volume(const float* curr, const float* prev, const float* cam, const float* xs,
+                          const float* ys, const float* ds, float* out, int n, int h, int w, int c,
+                          int d, float bias, int img_h, int img_w, void* stream) {
+  PW_REQUIRE(curr && prev && cam && xs && ys && ds && out);
+  PW_REQUIRE(n > 0 && h > 0 && w > 0 && d > 0 && d <= 128);
+  PW_REQUIRE(c % 128 == 0 && c <= 512);
+  long long warps = (long long)n * h * w;
+  int blocks = pw_ceil_div(warps * 32, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  float wi_m1 = (float)img_w - 1.f, hi_m1 = (float)img_h - 1.f;
+  switch (c / 128) {
+    case 1: cost_volume_kernel<1><<<blocks, 256, 0, st>>>(curr, prev, cam, xs, ys, ds, out, n, h, w, c, d, bias, wi_m1, hi_m1); break;
+    case 2: cost_volume_kernel<2><<<blocks, 256, 0, st>>>(curr, prev, cam, xs, ys, ds, out, n, h, w, c, d, bias, wi_m1, hi_m1); break;
+    case 3: cost_volume_kernel<3><<<blocks, 256, 0, st>>>(curr, prev, cam, xs, ys, ds, out, n, h, w, c, d, bias, wi_m1, hi_m1); break;
+    default: cost_volume_kernel<4><<<blocks, 256, 0, st>>>(curr, prev, cam, xs, ys, ds, out, n, h, w, c, d, bias, wi_m1, hi_m1); break;
+  }
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}

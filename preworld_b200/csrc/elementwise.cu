@@ -1,0 +1,416 @@
+// Channels-last element-wise / reduction helpers of the image side and the
+// 3-D encoder.  All kernels are HBM/L2-bound streaming kernels: float4
+// accesses along the channel dimension, grid-stride loops.
+#include "common.cuh"
+#include "../../include/preworld_b200.h"
+
+namespace {
+
+constexpr int TPB = 256;
+
+inline int grid_for(long long work, int per_block = TPB, int max_blocks = 148 * 16) {
+  long long b = (work + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+// ---- NCHW -> NHWC (padded channels) --------------------------------------
+__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                        int n, int c, long long hw, int c_pad,
+                                        long long img_stride) {
+  long long total = (long long)n * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long img = i / hw, p = i - img * hw;
+    const float* src = x + img * img_stride + p;
+    float* dst = y + i * c_pad;
+    for (int ch = 0; ch < c_pad; ++ch) dst[ch] = ch < c ? __ldg(src + ch * hw) : 0.f;
+  }
+}
+
+// ---- NHWC slice -> NCHW ----------------------------------------------------
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int x_ld,
+                                    float* __restrict__ y, int n, int c, long long hw) {
+  __shared__ float tile[32][33];
+  // blockIdx.x: pixel tile, blockIdx.y: channel tile, blockIdx.z: image
+  long long p0 = (long long)blockIdx.x * 32;
+  int c0 = blockIdx.y * 32;
+  int img = blockIdx.z;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    long long p = p0 + r;
+    int ch = c0 + tx;
+    tile[r][tx] = (p < hw && ch < c) ? __ldg(x + ((long long)img * hw + p) * x_ld + ch) : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int ch = c0 + r;
+    long long p = p0 + tx;
+    if (p < hw && ch < c) y[((long long)img * c + ch) * hw + p] = tile[tx][r];
+  }
+}
+
+// ---- 3x3 stride-2 pad-1 max pool ------------------------------------------
+__global__ void maxpool3x3s2_kernel(const float* __restrict__ x, float* __restrict__ y, int n,
+                                    int h, int w, int c4, int oh, int ow) {
+  long long total = (long long)n * oh * ow * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % c4);
+    long long t = i / c4;
+    int ox = (int)(t % ow); t /= ow;
+    int oy = (int)(t % oh);
+    int img = (int)(t / oh);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int dy = 0; dy < 3; ++dy) {
+      int iy = oy * 2 - 1 + dy;
+      if ((unsigned)iy >= (unsigned)h) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        int ix = ox * 2 - 1 + dx;
+        if ((unsigned)ix >= (unsigned)w) continue;
+        float4 v = pw_ldg4(x + ((((long long)img * h + iy) * w + ix) * c4 + ch) * 4);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y);
+        m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    reinterpret_cast<float4*>(y)[i] = m;
+  }
+}
+
+// ---- nearest upsample + add -------------------------------------------------
+__global__ void upsample_nearest_add_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                            int n, int h, int w, int oh, int ow, int c4) {
+  long long total = (long long)n * oh * ow * c4;
+  // torch nearest: src = min(floor(dst * (in/out)), in-1), scale in float
+  const float sy = (float)h / (float)oh, sx = (float)w / (float)ow;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % c4);
+    long long t = i / c4;
+    int ox = (int)(t % ow); t /= ow;
+    int oy = (int)(t % oh);
+    int img = (int)(t / oh);
+    int iy = min((int)floorf(oy * sy), h - 1);
+    int ix = min((int)floorf(ox * sx), w - 1);
+    float4 v = pw_ldg4(x + ((((long long)img * h + iy) * w + ix) * c4 + ch) * 4);
+    float4 o = reinterpret_cast<float4*>(y)[i];
+    o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+    reinterpret_cast<float4*>(y)[i] = o;
+  }
+}
+
+// ---- per-(image, channel) gate ---------------------------------------------
+__global__ void scale_channels_kernel(const float* __restrict__ x, int x_ld,
+                                      const float* __restrict__ gate, float* __restrict__ y,
+                                      int y_ld, int n, long long pixels, int c4) {
+  long long total = (long long)n * pixels * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % c4);
+    long long row = i / c4;
+    int img = (int)(row / pixels);
+    float4 v = pw_ldg4(x + row * x_ld + ch * 4);
+    float4 g = pw_ldg4(gate + (long long)img * c4 * 4 + ch * 4);
+    v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+    *reinterpret_cast<float4*>(y + row * y_ld + ch * 4) = v;
+  }
+}
+
+// ---- global average pool ----------------------------------------------------
+// one block per (image, 32-channel group): 8 pixel lanes x 32 channels
+__global__ void global_avgpool_kernel(const float* __restrict__ x, int x_ld, float* __restrict__ y,
+                                      int n, long long pixels, int c) {
+  __shared__ float part[8][32];
+  int img = blockIdx.y;
+  int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+  int lane_p = threadIdx.x >> 5;
+  float s = 0.f;
+  if (ch < c)
+    for (long long p = lane_p; p < pixels; p += 8)
+      s += __ldg(x + ((long long)img * pixels + p) * x_ld + ch);
+  part[lane_p][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (lane_p == 0 && ch < c) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x & 31];
+    y[(long long)img * c + ch] = t / (float)pixels;
+  }
+}
+
+__global__ void broadcast_channels_kernel(const float* __restrict__ v, float* __restrict__ y,
+                                          int y_ld, int n, long long pixels, int c) {
+  long long total = (long long)n * pixels * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % c);
+    long long row = i / c;
+    int img = (int)(row / pixels);
+    y[row * y_ld + ch] = __ldg(v + (long long)img * c + ch);
+  }
+}
+
+// ---- softmax over depth bins ------------------------------------------------
+__global__ void softmax_depth_kernel(const float* __restrict__ logits, int in_ld,
+                                     float* __restrict__ prob_cl, float* __restrict__ prob_pl,
+                                     int n, long long pixels, int d) {
+  long long rows = (long long)n * pixels;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
+       r += (long long)gridDim.x * blockDim.x) {
+    const float* src = logits + r * in_ld;
+    float m = -INFINITY;
+    for (int k = 0; k < d; ++k) m = fmaxf(m, __ldg(src + k));
+    float s = 0.f;
+    for (int k = 0; k < d; ++k) s += expf(__ldg(src + k) - m);
+    long long img = r / pixels, p = r - img * pixels;
+    for (int k = 0; k < d; ++k) {
+      float v = expf(__ldg(src + k) - m) / s;
+      if (prob_cl) prob_cl[r * d + k] = v;
+      if (prob_pl) prob_pl[(img * d + k) * pixels + p] = v;
+    }
+  }
+}
+
+// ---- trilinear upsample (align_corners=True) into a channel slice ----------
+__global__ void upsample_trilinear_kernel(const float* __restrict__ x, int x_ld,
+                                          float* __restrict__ y, int y_ld, int b, int iz, int iy,
+                                          int ix, int c4, int oz, int oy, int ox) {
+  long long total = (long long)b * oz * oy * ox * c4;
+  // torch area_pixel_compute_scale(align_corners=True): (in-1)/(out-1)
+  const float sz = oz > 1 ? (float)(iz - 1) / (float)(oz - 1) : 0.f;
+  const float sy = oy > 1 ? (float)(iy - 1) / (float)(oy - 1) : 0.f;
+  const float sx = ox > 1 ? (float)(ix - 1) / (float)(ox - 1) : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % c4);
+    long long t = i / c4;
+    int x_o = (int)(t % ox); t /= ox;
+    int y_o = (int)(t % oy); t /= oy;
+    int z_o = (int)(t % oz);
+    int bb = (int)(t / oz);
+    float fz = sz * z_o, fy = sy * y_o, fx = sx * x_o;
+    int z0 = (int)fz, y0 = (int)fy, x0 = (int)fx;
+    int z1 = z0 + (z0 < iz - 1), y1 = y0 + (y0 < iy - 1), x1 = x0 + (x0 < ix - 1);
+    float lz1 = fz - z0, ly1 = fy - y0, lx1 = fx - x0;
+    float lz0 = 1.f - lz1, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    auto at = [&](int zz, int yy, int xx) {
+      return pw_ldg4(x + ((((long long)bb * iz + zz) * iy + yy) * ix + xx) * x_ld + ch * 4);
+    };
+    float4 v000 = at(z0, y0, x0), v001 = at(z0, y0, x1), v010 = at(z0, y1, x0),
+           v011 = at(z0, y1, x1), v100 = at(z1, y0, x0), v101 = at(z1, y0, x1),
+           v110 = at(z1, y1, x0), v111 = at(z1, y1, x1);
+    // same association as ATen's upsample_trilinear3d (t0*(h0*(w0*a+w1*b)+h1*(..))+t1*(..))
+#define TRI(f)                                                                       \
+    (lz0 * (ly0 * (lx0 * v000.f + lx1 * v001.f) + ly1 * (lx0 * v010.f + lx1 * v011.f)) + \
+     lz1 * (ly0 * (lx0 * v100.f + lx1 * v101.f) + ly1 * (lx0 * v110.f + lx1 * v111.f)))
+    float4 o = make_float4(TRI(x), TRI(y), TRI(z), TRI(w));
+#undef TRI
+    *reinterpret_cast<float4*>(
+        y + ((((long long)bb * oz + z_o) * oy + y_o) * ox + x_o) * y_ld + ch * 4) = o;
+  }
+}
+
+__global__ void copy_channels_kernel(const float* __restrict__ x, int x_ld, float* __restrict__ y,
+                                     int y_ld, long long pixels, int c4) {
+  long long total = pixels * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % c4);
+    long long row = i / c4;
+    *reinterpret_cast<float4*>(y + row * y_ld + ch * 4) = pw_ldg4(x + row * x_ld + ch * 4);
+  }
+}
+
+// ---- occupancy argmax, [Z,Y,X] voxel order -> [X,Y,Z] uint8 grid -----------
+__global__ void argmax_zyx_to_xyz_kernel(const float* __restrict__ logits, int ld, int ncls,
+                                         unsigned char* __restrict__ occ, int gx, int gy, int gz) {
+  long long total = (long long)gx * gy * gz;
+  // iterate in OUTPUT order (x,y,z with z fastest) so byte stores coalesce
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int z = (int)(i % gz);
+    long long t = i / gz;
+    int yv = (int)(t % gy);
+    int xv = (int)(t / gy);
+    const float* src = logits + (((long long)z * gy + yv) * gx + xv) * ld;
+    float best = __ldg(src);
+    int arg = 0;
+    for (int k = 1; k < ncls; ++k) {
+      float v = __ldg(src + k);
+      if (v > best) { best = v; arg = k; }
+    }
+    occ[i] = (unsigned char)arg;
+  }
+}
+
+__global__ void density_occ_kernel(const float* __restrict__ density, int dld,
+                                   const float* __restrict__ sem, int ld, int ncls, float thr,
+                                   int empty_idx, unsigned char* __restrict__ occ,
+                                   unsigned char* __restrict__ geo, int gx, int gy, int gz) {
+  long long total = (long long)gx * gy * gz;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int z = (int)(i % gz);
+    long long t = i / gz;
+    int yv = (int)(t % gy);
+    int xv = (int)(t / gy);
+    long long v = ((long long)z * gy + yv) * gx + xv;
+    bool nonempty = __ldg(density + v * dld) > thr;
+    int arg = empty_idx;
+    if (nonempty) {
+      const float* src = sem + v * ld;
+      float best = __ldg(src);
+      arg = 0;
+      for (int k = 1; k < ncls; ++k) {
+        float q = __ldg(src + k);
+        if (q > best) { best = q; arg = k; }
+      }
+    }
+    occ[i] = (unsigned char)arg;
+    if (geo) geo[i] = nonempty ? 0 : (unsigned char)empty_idx;
+  }
+}
+
+__global__ void zyx_to_xyz_kernel(const float* __restrict__ x, float* __restrict__ y, int b,
+                                  int gz, int gy, int gx, int c4) {
+  long long total = (long long)b * gz * gy * gx * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % c4);
+    long long t = i / c4;
+    int z = (int)(t % gz); t /= gz;
+    int yv = (int)(t % gy); t /= gy;
+    int xv = (int)(t % gx);
+    int bb = (int)(t / gx);
+    reinterpret_cast<float4*>(y)[i] =
+        pw_ldg4(x + (((((long long)bb * gz + z) * gy + yv) * gx + xv) * c4 + ch) * 4);
+  }
+}
+
+}  // namespace
+
+static long long g_launches = 0;
+void pw_count_launch(int k) { __atomic_add_fetch(&g_launches, k, __ATOMIC_RELAXED); }
+PW_API long long pw_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+PW_API int pw_abi_version(void) { return PW_ABI_VERSION; }
+
+#define ST ((cudaStream_t)stream)
+
+PW_API int pw_nchw_to_nhwc_pad(const float* x, long long img_stride, float* y, int n, int c,
+                               int h, int w, int c_pad, void* stream) {
+  PW_REQUIRE(x && y && n > 0 && c > 0 && c_pad >= c);
+  long long hw = (long long)h * w;
+  PW_REQUIRE(img_stride >= c * hw);
+  nchw_to_nhwc_pad_kernel<<<grid_for(n * hw), TPB, 0, ST>>>(x, y, n, c, hw, c_pad, img_stride);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+PW_API int pw_nhwc_to_nchw(const float* x, int x_ld, float* y, int n, int c, long long pixels,
+                           void* stream) {
+  PW_REQUIRE(x && y && n > 0 && c > 0 && pixels > 0 && x_ld >= c);
+  dim3 grid(pw_ceil_div(pixels, 32), pw_ceil_div(c, 32), n);
+  nhwc_to_nchw_kernel<<<grid, 256, 0, ST>>>(x, x_ld, y, n, c, pixels);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+PW_API int pw_maxpool3x3s2(const float* x, float* y, int n, int h, int w, int c, int oh, int ow,
+                           void* stream) {
+  PW_REQUIRE(x && y && (c & 3) == 0 && oh == (h + 2 - 3) / 2 + 1 && ow == (w + 2 - 3) / 2 + 1);
+  maxpool3x3s2_kernel<<<grid_for((long long)n * oh * ow * (c / 4)), TPB, 0, ST>>>(
+      x, y, n, h, w, c / 4, oh, ow);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+PW_API int pw_upsample_nearest_add(const float* x, float* y, int n, int h, int w, int oh, int ow,
+                                   int c, void* stream) {
+  PW_REQUIRE(x && y && (c & 3) == 0);
+  upsample_nearest_add_kernel<<<grid_for((long long)n * oh * ow * (c / 4)), TPB, 0, ST>>>(
+      x, y, n, h, w, oh, ow, c / 4);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+PW_API int pw_scale_channels(const float* x, int x_ld, const float* gate, float* y, int y_ld,
+                             int n, long long pixels, int c, void* stream) {
+  PW_REQUIRE(x && y && gate && (c & 3) == 0 && (x_ld & 3) == 0 && (y_ld & 3) == 0);
+  scale_channels_kernel<<<grid_for(n * pixels * (c / 4)), TPB, 0, ST>>>(x, x_ld, gate, y, y_ld, n,
+                                                                      pixels, c / 4);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+PW_API int pw_global_avgpool(const float* x, int x_ld, float* y, int n, long long pixels, int c,
+                             void* stream) {
+  PW_REQUIRE(x && y && n > 0 && pixels > 0);
+  dim3 grid(pw_ceil_div(c, 32), n);
+  global_avgpool_kernel<<<grid, 256, 0, ST>>>(x, x_ld, y, n, pixels, c);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+PW_API int pw_broadcast_channels(const float* v, float* y, int y_ld, int n, long long pixels,
+                                 int c, void* stream) {
+  PW_REQUIRE(v && y && y_ld >= c);
+  broadcast_channels_kernel<<<grid_for(n * pixels * c), TPB, 0, ST>>>(v, y, y_ld, n, pixels, c);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+PW_API int pw_softmax_depth(const float* logits, int in_ld, float* prob_cl, float* prob_planar,
+                            int n, long long pixels, int d, void* stream) {
+  PW_REQUIRE(logits && in_ld >= d && (prob_cl || prob_planar));
+  softmax_depth_kernel<<<grid_for(n * pixels, 128), 128, 0, ST>>>(logits, in_ld, prob_cl,
+                                                                   prob_planar, n, pixels, d);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+PW_API int pw_upsample_trilinear(const float* x, int x_ld, float* y, int y_ld, int b, int z,
+                                 int yy, int xx, int c, int oz, int oy, int ox, void* stream) {
+  PW_REQUIRE(x && y && (c & 3) == 0 && (x_ld & 3) == 0 && (y_ld & 3) == 0);
+  upsample_trilinear_kernel<<<grid_for((long long)b * oz * oy * ox * (c / 4)), TPB, 0, ST>>>(
+      x, x_ld, y, y_ld, b, z, yy, xx, c / 4, oz, oy, ox);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+PW_API int pw_copy_channels(const float* x, int x_ld, float* y, int y_ld, long long pixels, int c,
+                            void* stream) {
+  PW_REQUIRE(x && y && (c & 3) == 0 && (x_ld & 3) == 0 && (y_ld & 3) == 0);
+  copy_channels_kernel<<<grid_for(pixels * (c / 4)), TPB, 0, ST>>>(x, x_ld, y, y_ld, pixels,
+                                                                    c / 4);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+PW_API int pw_argmax_zyx_to_xyz(const float* logits, int ld, int ncls, unsigned char* occ, int gx,
+                                int gy, int gz, void* stream) {
+  PW_REQUIRE(logits && occ && ncls > 0 && ld >= ncls);
+  argmax_zyx_to_xyz_kernel<<<grid_for((long long)gx * gy * gz), TPB, 0, ST>>>(logits, ld, ncls,
+                                                                               occ, gx, gy, gz);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+PW_API int pw_density_occ_zyx_to_xyz(const float* density, int density_ld, const float* semantic,
+                                     int ld, int ncls, float thr, int empty_idx,
+                                     unsigned char* occ, unsigned char* geo, int gx, int gy,
+                                     int gz, void* stream) {
+  PW_REQUIRE(density && semantic && occ && ncls > 0 && ld >= ncls);
+  density_occ_kernel<<<grid_for((long long)gx * gy * gz), TPB, 0, ST>>>(
+      density, density_ld, semantic, ld, ncls, thr, empty_idx, occ, geo, gx, gy, gz);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+PW_API int pw_zyx_to_xyz(const float* x, float* y, int b, int gz, int gy, int gx, int c,
+                         void* stream) {
+  PW_REQUIRE(x && y && (c & 3) == 0);
+  zyx_to_xyz_kernel<<<grid_for((long long)b * gz * gy * gx * (c / 4)), TPB, 0, ST>>>(
+      x, y, b, gz, gy, gx, c / 4);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}

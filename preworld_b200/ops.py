@@ -1,0 +1,484 @@
+"""Torch-tensor front-end of the C-ABI kernels (include/preworld_b200.h).
+
+torch is used here only for device memory and streams: every function
+extracts raw device pointers, leading dimensions and the current stream and
+calls the C library.  There is no CPU or eager-PyTorch fallback -- CPU tensors
+raise.
+
+Layout: feature maps are handled as *channels-last arrays*
+``[N, H, W, C]`` / ``[B, Z, Y, X, C]`` ("cl" tensors: last dim stride 1, all
+other dims dense over a pixel pitch ``ld >= C``).  ``to_logical`` /
+``from_logical`` convert (zero-copy) to and from the reference's logical
+``[N,C,H,W]`` / ``[B,C,Z,Y,X]`` tensors with channels_last strides.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, RenderDesc, check
+
+ACT = {None: 0, 'none': 0, 'relu': 1, 'softplus': 2, 'sigmoid': 3}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                'preworld_b200 ops run on CUDA tensors only (no CPU fallback)')
+
+
+def cl_ld(t):
+    """Pixel pitch of a channels-last array [..., C]; validates density."""
+    assert t.dtype == torch.float32 and t.stride(-1) == 1, (t.dtype, t.stride())
+    ld = exp = None
+    for i in range(t.dim() - 2, -1, -1):
+        if t.shape[i] == 1:
+            continue                      # stride of a size-1 dim is arbitrary
+        if ld is None:
+            ld = exp = t.stride(i)
+        elif t.stride(i) != exp:
+            raise ValueError(f'not a dense channels-last array: shape '
+                             f'{tuple(t.shape)} strides {t.stride()}')
+        exp *= t.shape[i]
+    return t.shape[-1] if ld is None else ld
+
+
+def to_logical(t_cl):
+    """[N,H,W,C] -> [N,C,H,W] view (channels_last strides); 5-D alike."""
+    d = t_cl.dim()
+    return t_cl.permute(0, d - 1, *range(1, d - 1))
+
+
+def from_logical(t):
+    """[N,C,H,W] (channels_last strides) -> [N,H,W,C] view.  A tensor in the
+    default NCHW-contiguous format is rejected: callers convert images with
+    ``nchw_to_nhwc`` at the model boundary."""
+    d = t.dim()
+    v = t.permute(0, *range(2, d), 1)
+    if v.stride(-1) != 1:
+        raise ValueError('expected a channels-last feature map '
+                         f'(strides {t.stride()})')
+    return v
+
+
+# --------------------------------------------------------------------- conv
+class PackedConv:
+    """Weights of one conv/linear in the kernel's layout: w [K, w_ld] with
+    K = taps*cin_pad (tap-major), plus the folded per-channel affine."""
+    __slots__ = ('w', 'scale', 'bias', 'cin', 'cout', 'k', 'stride', 'pad',
+                 'dil', 'w_ld')
+
+    def __init__(self, weight, bias=None, bn=None, stride=1, padding=0,
+                 dilation=1, in_scale=None, in_shift=None, eps=None,
+                 spatial_perm=None):
+        """weight [Cout,Cin,*k] (or [Cout,Cin] for Linear).  bn = (gamma,
+        beta, mean, var, eps) folded as y = conv*s + (beta - mean*s + b*s).
+        in_scale/in_shift fold a per-input-channel affine applied BEFORE a
+        1x1 conv / linear (BatchNorm1d in front of DepthNet's Mlp).
+        spatial_perm re-orders the kernel's spatial axes (used to run the
+        reference's [X,Y,Z]-ordered OccHead on [Z,Y,X] volumes)."""
+        w = weight.detach().float()
+        if w.dim() == 2:
+            w = w[:, :, None, None, None]
+        elif w.dim() == 4:
+            w = w[:, :, None]
+        assert w.dim() == 5
+        if spatial_perm is not None:
+            w = w.permute(0, 1, *[2 + p for p in spatial_perm])
+        cout, cin = w.shape[:2]
+        k = tuple(w.shape[2:])
+        b = bias.detach().float() if bias is not None else None
+        if in_scale is not None:
+            assert k == (1, 1, 1)
+            shift_term = (w[:, :, 0, 0, 0] * in_shift[None, :]).sum(1)
+            b = shift_term if b is None else b + shift_term
+            w = w * in_scale[None, :, None, None, None]
+        cin_pad = (cin + 3) // 4 * 4
+        w_ld = (cout + 3) // 4 * 4
+        wk = torch.zeros(*k, cin_pad, w_ld, device=w.device)
+        wk[..., :cin, :cout] = w.permute(2, 3, 4, 1, 0)
+        self.w = wk.reshape(-1, w_ld).contiguous()
+        if bn is not None:
+            gamma, beta, mean, var, eps_ = bn
+            s = gamma.detach().float() / torch.sqrt(var.detach().float() + eps_)
+            sh = beta.detach().float() - mean.detach().float() * s
+            if b is not None:
+                sh = sh + b * s
+            self.scale, self.bias = s.contiguous(), sh.contiguous()
+        else:
+            self.scale = None
+            self.bias = b.contiguous() if b is not None else None
+        self.cin, self.cout, self.k, self.w_ld = cin_pad, cout, k, w_ld
+
+        def t3(v):
+            if isinstance(v, int):
+                v = (v,) * 3
+            v = tuple(v)
+            return (1,) * (3 - len(v)) + v if len(v) < 3 else v
+        self.stride, self.pad, self.dil = t3(stride), t3(padding), t3(dilation)
+        # a 2-D conv has kd == 1: depth stride/pad/dilation are neutral
+        if k[0] == 1 and len(tuple(weight.shape)) <= 4:
+            self.stride = (1,) + self.stride[1:]
+            self.pad = (0,) + self.pad[1:]
+            self.dil = (1,) + self.dil[1:]
+        if spatial_perm is not None:
+            self.stride = tuple(self.stride[p] for p in spatial_perm)
+            self.pad = tuple(self.pad[p] for p in spatial_perm)
+            self.dil = tuple(self.dil[p] for p in spatial_perm)
+
+
+def conv(x, pc, act=None, residual=None, out=None, act_channels=0):
+    """x: cl array [N,H,W,C] or [B,Z,Y,X,C] (C >= pc.cin, extra channels
+    ignored only if equal to the packed cin).  Returns / fills a cl array with
+    pc.cout channels; ``out`` may be a channel slice of a wider cl array."""
+    _require_cuda(x, residual, out)
+    spatial = x.shape[1:-1]
+    sp = (1,) * (3 - len(spatial)) + tuple(spatial)
+    n = x.shape[0]
+    assert x.shape[-1] == pc.cin, (x.shape, pc.cin)
+    o = tuple((sp[i] + 2 * pc.pad[i] - pc.dil[i] * (pc.k[i] - 1) - 1)
+              // pc.stride[i] + 1 for i in range(3))
+    if out is None:
+        out = torch.empty((n, *o[3 - len(spatial):], pc.cout), device=x.device,
+                          dtype=torch.float32)
+    else:
+        assert out.shape[0] == n and out.shape[-1] == pc.cout and \
+            tuple(out.shape[1:-1]) == o[3 - len(spatial):], (out.shape, o)
+    d = ConvDesc(n=n, d=sp[0], h=sp[1], w=sp[2], cin=pc.cin, in_ld=cl_ld(x),
+                 od=o[0], oh=o[1], ow=o[2], cout=pc.cout, out_ld=cl_ld(out),
+                 res_ld=cl_ld(residual) if residual is not None else 0,
+                 w_ld=pc.w_ld, kd=pc.k[0], kh=pc.k[1], kw=pc.k[2],
+                 sd=pc.stride[0], sh=pc.stride[1], sw=pc.stride[2],
+                 pd=pc.pad[0], ph=pc.pad[1], pw=pc.pad[2],
+                 dd=pc.dil[0], dh=pc.dil[1], dw=pc.dil[2], act=ACT[act],
+                 act_channels=act_channels)
+    if residual is not None:
+        assert residual.shape == out.shape
+    check(_lib.lib().pw_conv_fwd(ctypes.byref(d), _ptr(x), _ptr(pc.w),
+                                 _ptr(pc.scale), _ptr(pc.bias),
+                                 _ptr(residual), _ptr(out), _stream()),
+          'pw_conv_fwd')
+    return out
+
+
+def linear(x2d, pc, act=None, residual=None, out=None):
+    """x2d [rows, C] -> [rows, cout] through the conv kernel (1x1)."""
+    y = conv(x2d[:, None, :], pc, act,
+             residual[:, None, :] if residual is not None else None,
+             out[:, None, :] if out is not None else None)
+    return y[:, 0, :]
+
+
+# ---------------------------------------------------------------- image side
+def nchw_to_nhwc(x, c_pad=None):
+    """x [n,c,h,w]: each image dense NCHW; images may be strided (a frame
+    slice of the loader's camera-major batch)."""
+    _require_cuda(x)
+    n, c, h, w = x.shape
+    if x.stride()[1:] != (h * w, w, 1):
+        raise ValueError(f'images must be dense CHW planes, got {x.stride()}')
+    c_pad = c_pad or c
+    y = torch.empty((n, h, w, c_pad), device=x.device, dtype=torch.float32)
+    img_stride = x.stride(0) if n > 1 else c * h * w
+    check(_lib.lib().pw_nchw_to_nhwc_pad(_ptr(x), img_stride, _ptr(y), n, c,
+                                         h, w, c_pad, _stream()),
+          'pw_nchw_to_nhwc_pad')
+    return y
+
+
+def nhwc_to_nchw(x_cl):
+    """cl array [N,...,C] (may be a channel slice) -> contiguous [N,C,...]."""
+    _require_cuda(x_cl)
+    n, c = x_cl.shape[0], x_cl.shape[-1]
+    spatial = tuple(x_cl.shape[1:-1])
+    pixels = 1
+    for s in spatial:
+        pixels *= s
+    y = torch.empty((n, c, *spatial), device=x_cl.device, dtype=torch.float32)
+    check(_lib.lib().pw_nhwc_to_nchw(_ptr(x_cl), cl_ld(x_cl), _ptr(y), n, c,
+                                     pixels, _stream()), 'pw_nhwc_to_nchw')
+    return y
+
+
+def maxpool3x3s2(x):
+    n, h, w, c = x.shape
+    assert cl_ld(x) == c
+    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = torch.empty((n, oh, ow, c), device=x.device, dtype=torch.float32)
+    check(_lib.lib().pw_maxpool3x3s2(_ptr(x), _ptr(y), n, h, w, c, oh, ow,
+                                     _stream()), 'pw_maxpool3x3s2')
+    return y
+
+
+def upsample_nearest_add_(y, x):
+    """y += nearest-upsample(x) to y's size (in place)."""
+    n, oh, ow, c = y.shape
+    assert cl_ld(y) == c and cl_ld(x) == c and x.shape[-1] == c
+    check(_lib.lib().pw_upsample_nearest_add(_ptr(x), _ptr(y), n, x.shape[1],
+                                             x.shape[2], oh, ow, c, _stream()),
+          'pw_upsample_nearest_add')
+    return y
+
+
+def scale_channels(x, gate, out=None):
+    """x [N,H,W,C] * gate [N,C]."""
+    n, c = x.shape[0], x.shape[-1]
+    pixels = x[0, ..., 0].numel()
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    gate = gate.contiguous()
+    check(_lib.lib().pw_scale_channels(_ptr(x), cl_ld(x), _ptr(gate),
+                                       _ptr(out), cl_ld(out), n, pixels, c,
+                                       _stream()), 'pw_scale_channels')
+    return out
+
+
+def global_avgpool(x):
+    n, c = x.shape[0], x.shape[-1]
+    pixels = x[0, ..., 0].numel()
+    y = torch.empty((n, c), device=x.device, dtype=torch.float32)
+    check(_lib.lib().pw_global_avgpool(_ptr(x), cl_ld(x), _ptr(y), n, pixels,
+                                       c, _stream()), 'pw_global_avgpool')
+    return y
+
+
+def broadcast_channels_(out, v):
+    """out [N,H,W,C] (may be a slice) = v [N,C] broadcast over pixels."""
+    n, c = out.shape[0], out.shape[-1]
+    pixels = out[0, ..., 0].numel()
+    v = v.contiguous()
+    check(_lib.lib().pw_broadcast_channels(_ptr(v), _ptr(out), cl_ld(out), n,
+                                           pixels, c, _stream()),
+          'pw_broadcast_channels')
+    return out
+
+
+def softmax_depth(logits_cl, d):
+    """logits_cl [N,H,W,>=d] -> planar probabilities [N,d,H,W] (contiguous,
+    the reference's layout)."""
+    n, h, w = logits_cl.shape[:3]
+    y = torch.empty((n, d, h, w), device=logits_cl.device, dtype=torch.float32)
+    check(_lib.lib().pw_softmax_depth(_ptr(logits_cl), cl_ld(logits_cl), None,
+                                      _ptr(y), n, h * w, d, _stream()),
+          'pw_softmax_depth')
+    return y
+
+
+def cost_volume(curr, prev, cam, xs, ys, ds, bias, img_hw):
+    n, h, w, c = curr.shape
+    assert cl_ld(curr) == c and cl_ld(prev) == c and prev.shape == curr.shape
+    d = ds.numel()
+    out = torch.empty((n, h, w, d), device=curr.device, dtype=torch.float32)
+    check(_lib.lib().pw_cost_volume(_ptr(curr), _ptr(prev), _ptr(cam), _ptr(xs),
+                                    _ptr(ys), _ptr(ds), _ptr(out), n, h, w, c,
+                                    d, float(bias), int(img_hw[0]),
+                                    int(img_hw[1]), _stream()),
+          'pw_cost_volume')
+    return out
+
+
+# ----------------------------------------------------------------------- lift
+def bev_pool_v2_(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                 interval_starts, interval_lengths, out):
+    """In-place drop-in of bev_pool_v2_ext.bev_pool_v2_forward (note the
+    reference's pybind argument order is lengths-before-starts,
+    src/bev_pool.cpp:30-57; this wrapper takes keywords-by-name order)."""
+    _require_cuda(depth, feat, out)
+    c = feat.shape[-1]
+    check(_lib.lib().pw_bev_pool_v2(
+        c, int(interval_starts.numel()), _ptr(depth), _ptr(feat),
+        _ptr(ranks_depth), _ptr(ranks_feat), _ptr(ranks_bev),
+        _ptr(interval_starts), _ptr(interval_lengths), _ptr(out), _stream()),
+        'pw_bev_pool_v2')
+    return out
+
+
+def _cam_params(fn_name, floats, pose44, intrin, post_rot, post_tran):
+    _require_cuda(pose44, intrin, post_rot, post_tran)
+    n = pose44.numel() // 16
+    args = [t.contiguous().float() for t in (pose44, intrin, post_rot,
+                                             post_tran)]
+    cam = torch.empty((n, floats), device=pose44.device, dtype=torch.float32)
+    check(getattr(_lib.lib(), fn_name)(n, *[_ptr(a) for a in args], _ptr(cam),
+                                       _stream()), fn_name)
+    return cam
+
+
+def lift_camera_params(sensor2ego, intrin, post_rot, post_tran):
+    """[..,4,4],[..,3,3],[..,3,3],[..,3] -> cam [n, 24] (device)."""
+    return _cam_params('pw_lift_camera_params', 24, sensor2ego, intrin,
+                       post_rot, post_tran)
+
+
+def cv_camera_params(k2s_sensor, intrin, post_rot, post_tran):
+    return _cam_params('pw_cv_camera_params', 48, k2s_sensor, intrin, post_rot,
+                       post_tran)
+
+
+def _f3(v):
+    return (ctypes.c_float * 3)(*[float(x) for x in v])
+
+
+def lift_ranks(cam, bda, xs, ys, ds, lower, interval, b, n, grid):
+    d, h, w = ds.numel(), ys.numel(), xs.numel()
+    rank = torch.empty(b * n * d * h * w, device=cam.device, dtype=torch.int32)
+    check(_lib.lib().pw_lift_ranks(_ptr(cam), _ptr(bda), _ptr(xs), _ptr(ys),
+                                   _ptr(ds), _f3(lower), _f3(interval), b, n,
+                                   d, h, w, grid[0], grid[1], grid[2],
+                                   _ptr(rank), _stream()), 'pw_lift_ranks')
+    return rank
+
+
+_ws_cache = {}
+
+
+def lift_fused(depth, feat_cl, cam, bda, xs, ys, ds, lower, interval, b, n,
+               grid, out=None):
+    """depth [b*n,D,H,W] planar probabilities; feat_cl [b*n,H,W,C] (may be a
+    channel slice).  Returns the pooled volume as a cl array [b,Z,Y,X,C]."""
+    _require_cuda(depth, feat_cl)
+    d, h, w = ds.numel(), ys.numel(), xs.numel()
+    c = feat_cl.shape[-1]
+    gx, gy, gz = grid
+    assert depth.is_contiguous() and depth.shape == (b * n, d, h, w)
+    if out is None:
+        out = torch.empty((b, gz, gy, gx, c), device=depth.device,
+                          dtype=torch.float32)
+    nbytes = int(_lib.lib().pw_lift_workspace_bytes(b, n, d, h, w, gx, gy, gz))
+    key = (depth.device, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, device=depth.device, dtype=torch.uint8)
+        _ws_cache[key] = ws
+    check(_lib.lib().pw_lift_fused(
+        _ptr(depth), _ptr(feat_cl), cl_ld(feat_cl), _ptr(cam), _ptr(bda),
+        _ptr(xs), _ptr(ys), _ptr(ds), _f3(lower), _f3(interval), b, n, d, h, w,
+        c, gx, gy, gz, _ptr(out), _ptr(ws), _stream()), 'pw_lift_fused')
+    return out
+
+
+# ------------------------------------------------------------------ 3-D side
+def upsample_trilinear_(out, x):
+    """out [B,OZ,OY,OX,C] (may be a channel slice) = trilinear(x), align_corners."""
+    b, z, y, xx, c = x.shape
+    check(_lib.lib().pw_upsample_trilinear(
+        _ptr(x), cl_ld(x), _ptr(out), cl_ld(out), b, z, y, xx, c, out.shape[1],
+        out.shape[2], out.shape[3], _stream()), 'pw_upsample_trilinear')
+    return out
+
+
+def copy_channels_(out, x):
+    c = x.shape[-1]
+    pixels = x[..., 0].numel()
+    check(_lib.lib().pw_copy_channels(_ptr(x), cl_ld(x), _ptr(out), cl_ld(out),
+                                      pixels, c, _stream()),
+          'pw_copy_channels')
+    return out
+
+
+def argmax_zyx_to_xyz(logits_cl):
+    """logits [1,Z,Y,X,ncls] -> uint8 [X,Y,Z] (torch.argmax semantics)."""
+    _, gz, gy, gx, ncls = logits_cl.shape
+    occ = torch.empty((gx, gy, gz), device=logits_cl.device, dtype=torch.uint8)
+    check(_lib.lib().pw_argmax_zyx_to_xyz(_ptr(logits_cl), cl_ld(logits_cl),
+                                          ncls, _ptr(occ), gx, gy, gz,
+                                          _stream()), 'pw_argmax_zyx_to_xyz')
+    return occ
+
+
+def density_occ_zyx_to_xyz(density_cl, semantic_cl, thr, empty_idx):
+    """density [1,Z,Y,X,1+] (channel 0 used), semantic [1,Z,Y,X,ncls]."""
+    _, gz, gy, gx, ncls = semantic_cl.shape
+    occ = torch.empty((gx, gy, gz), device=semantic_cl.device,
+                      dtype=torch.uint8)
+    geo = torch.empty_like(occ)
+    check(_lib.lib().pw_density_occ_zyx_to_xyz(
+        _ptr(density_cl), cl_ld(density_cl), _ptr(semantic_cl),
+        cl_ld(semantic_cl), ncls, float(thr), int(empty_idx), _ptr(occ),
+        _ptr(geo), gx, gy, gz, _stream()), 'pw_density_occ_zyx_to_xyz')
+    return occ, geo
+
+
+def zyx_to_xyz(x_cl):
+    """[B,Z,Y,X,C] -> contiguous [B,X,Y,Z,C] (reference voxel_feats order)."""
+    b, gz, gy, gx, c = x_cl.shape
+    assert cl_ld(x_cl) == c
+    y = torch.empty((b, gx, gy, gz, c), device=x_cl.device,
+                    dtype=torch.float32)
+    check(_lib.lib().pw_zyx_to_xyz(_ptr(x_cl), _ptr(y), b, gz, gy, gx, c,
+                                   _stream()), 'pw_zyx_to_xyz')
+    return y
+
+
+# -------------------------------------------------------------------- render
+def raw2alpha(density, shift, interval):
+    _require_cuda(density)
+    density = density.contiguous()
+    exp_d = torch.empty_like(density)
+    alpha = torch.empty_like(density)
+    check(_lib.lib().pw_raw2alpha(_ptr(density), float(shift), float(interval),
+                                  density.numel(), _ptr(exp_d), _ptr(alpha),
+                                  _stream()), 'pw_raw2alpha')
+    return exp_d, alpha
+
+
+def alpha2weight(alpha, ray_id, n_rays):
+    _require_cuda(alpha, ray_id)
+    alpha = alpha.contiguous()
+    ray_id = ray_id.contiguous().long()
+    n = alpha.numel()
+    dev = alpha.device
+    weight = torch.empty(n, device=dev)
+    T = torch.empty(n, device=dev)
+    last = torch.empty(n_rays, device=dev)
+    i_s = torch.empty(n_rays, device=dev, dtype=torch.int64)
+    i_e = torch.empty(n_rays, device=dev, dtype=torch.int64)
+    check(_lib.lib().pw_alpha2weight(_ptr(alpha), _ptr(ray_id), n, n_rays,
+                                     _ptr(weight), _ptr(T), _ptr(last),
+                                     _ptr(i_s), _ptr(i_e), _stream()),
+          'pw_alpha2weight')
+    return weight, T, last, i_s, i_e
+
+
+def cumdist_thres(dist, thres):
+    _require_cuda(dist)
+    dist = dist.contiguous()
+    n_rays, n_pts = dist.shape
+    mask = torch.empty((n_rays, n_pts), device=dist.device, dtype=torch.bool)
+    check(_lib.lib().pw_cumdist_thres(_ptr(dist), float(thres), n_rays, n_pts,
+                                      _ptr(mask), _stream()),
+          'pw_cumdist_thres')
+    return mask
+
+
+def render_rays(desc, rays, t_vals, bda, density_cl, semantic_cl, color_cl):
+    """rays [R,16]; *_cl are cl arrays [Z,Y,X,c] (channel slices allowed).
+    Returns (depth [R], semantic [R,n_sem], color [R,3], alphainv_last [R],
+    valid [R] bool)."""
+    _require_cuda(rays, density_cl, semantic_cl, color_cl)
+    rays = rays.contiguous()
+    r = rays.shape[0]
+    dev = rays.device
+    ns = desc.n_sem
+    o_d = torch.empty(r, device=dev)
+    o_s = torch.empty((r, ns), device=dev)
+    o_c = torch.empty((r, 3), device=dev)
+    o_l = torch.empty(r, device=dev)
+    o_v = torch.empty(r, device=dev, dtype=torch.bool)
+    bda = bda.contiguous()
+    check(_lib.lib().pw_render_rays(
+        ctypes.byref(desc), _ptr(rays), r, _ptr(t_vals), t_vals.numel(),
+        _ptr(bda), _ptr(density_cl), cl_ld(density_cl), _ptr(semantic_cl),
+        cl_ld(semantic_cl), _ptr(color_cl), cl_ld(color_cl), _ptr(o_d),
+        _ptr(o_s), _ptr(o_c), _ptr(o_l), _ptr(o_v), _stream()),
+        'pw_render_rays')
+    return o_d, o_s, o_c, o_l, o_v

@@ -1,0 +1,477 @@
+"""Detectors: ``BEVStereo4DOCC``, ``PreWorld``, ``PreWorld4DTraj``.
+
+Host-side mirror of reference detectors/bevdet.py (BEVDet :25-58, BEVDet4D
+:274-290, BEVStereo4D :562-612), detectors/bevdet_occ.py (BEVStereo4DOCC
+:42-269), detectors/preworld.py (:22-226) and
+detectors/preworld_temporal_traj.py (:26-371): same registry names, ctor
+kwargs, state_dict keys, ``forward(return_loss=False, **data)`` dispatch
+(detectors/base.py:47-62) and ``simple_test`` outputs.  Only the forward
+(inference) path exists; ``forward_train`` raises.
+
+Everything between the image tensor and the uint8 occupancy grid runs in the
+C-ABI CUDA library; volumes stay channels-last in [B,Z,Y,X,C] voxel order end
+to end and the class argmax kernel writes the reference's [X,Y,Z] grid.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from . import builder
+from .base import BaseModule, ConvModule, pack_linear
+from .builder import DETECTORS
+from .heads import DownScaleModule3DCustom
+
+nusc_class_frequencies = np.array([
+    1163161, 2309034, 188743, 2997643, 20317180, 852476, 243808, 2457947,
+    497017, 2731022, 7224789, 214411435, 5565043, 63191967, 76098082,
+    128860031, 141625221, 2307405309])
+
+
+@DETECTORS.register_module()
+class BEVStereo4DOCC(BaseModule):
+    """Camera -> voxel-feature trunk (image encoder, view transformer,
+    pre-process net, BEV encoder) + ``final_conv``."""
+
+    _pack_children = ('final_conv', 'density_mlp', 'semantic_mlp', 'color_mlp',
+                      'plan_head', 'fusion_head')
+
+    def __init__(self, img_backbone=None, img_neck=None,
+                 img_view_transformer=None, img_bev_encoder_backbone=None,
+                 img_bev_encoder_neck=None, pre_process=None,
+                 align_after_view_transfromation=False, num_adj=1,
+                 with_prev=True, loss_occ=None, out_dim=32, num_classes=18,
+                 use_predicter=True, class_wise=False,
+                 balance_cls_weight=False, use_depth_gt=False,
+                 pts_bbox_head=None, train_cfg=None, test_cfg=None,
+                 pretrained=None, init_cfg=None, **kwargs):
+        super().__init__(init_cfg)
+        # mvx_two_stage.py:65-68
+        self.img_backbone = builder.build_backbone(img_backbone)
+        self.img_neck = builder.build_neck(img_neck) \
+            if img_neck is not None else None
+        # bevdet.py:25-31
+        self.img_view_transformer = builder.build_neck(img_view_transformer)
+        self.img_bev_encoder_backbone = builder.build_backbone(
+            img_bev_encoder_backbone)
+        self.img_bev_encoder_neck = builder.build_neck(img_bev_encoder_neck)
+        # bevdet.py:274-290, 562-568
+        self.pre_process = pre_process is not None
+        if self.pre_process:
+            self.pre_process_net = builder.build_backbone(pre_process)
+        self.num_frame = num_adj + 1
+        self.with_prev = with_prev
+        self.extra_ref_frames = 1
+        self.temporal_frame = self.num_frame
+        self.num_frame += self.extra_ref_frames
+        # bevdet_occ.py:42-86
+        self.out_dim = out_dim
+        self.num_classes = num_classes
+        self.use_predicter = use_predicter
+        out_channels = out_dim if use_predicter else num_classes
+        self.final_conv = ConvModule(
+            self.img_view_transformer.out_channels, out_channels,
+            kernel_size=3, stride=1, padding=1, bias=True,
+            conv_cfg=dict(type='Conv3d'))
+        if use_predicter:
+            self.predicter = nn.Sequential(
+                nn.Linear(out_dim, out_dim * 2), nn.Softplus(),
+                nn.Linear(out_dim * 2, num_classes))
+        self.pts_bbox_head = None
+        self.loss_occ = builder.build_loss(loss_occ) \
+            if loss_occ is not None else None
+        self.class_wise = class_wise
+        self.align_after_view_transfromation = False     # bevdet_occ.py:80
+        self.use_depth_gt = use_depth_gt
+        if use_depth_gt or not with_prev:
+            raise NotImplementedError(
+                'use_depth_gt / with_prev=False are not used by the PreWorld '
+                'configs')
+
+    @property
+    def with_img_neck(self):
+        return self.img_neck is not None
+
+    # -- forward dispatch (detectors/base.py:47-62, bevdet.py:139-175) -------
+    def forward(self, return_loss=True, **kwargs):
+        if return_loss:
+            return self.forward_train(**kwargs)
+        return self.forward_test(**kwargs)
+
+    def forward_train(self, *args, **kwargs):
+        raise NotImplementedError(
+            'preworld_b200 implements the forward-only (inference) path; '
+            'training is out of scope (SURVEY.md §8f)')
+
+    def forward_test(self, points=None, img_metas=None, img_inputs=None,
+                     **kwargs):
+        # bevdet.py:139-175: the loader wraps everything in a 1-element list
+        if isinstance(img_inputs, list) and isinstance(img_inputs[0],
+                                                       (list, tuple)):
+            img_inputs = img_inputs[0]
+            img_metas = img_metas[0] if img_metas else img_metas
+            points = points[0] if points else points
+        return self.simple_test(points, img_metas, img_inputs, **kwargs)
+
+    # -- bevdet_occ.py:88-139 -------------------------------------------------
+    def prepare_inputs(self, inputs, stereo=False):
+        """Split the loader's 7-tuple into per-frame lists and chain the poses
+        (fp64 4x4 inverse / matmul, as the reference).  The pose tensors are
+        tiny; they are processed wherever they live (CPU tensors straight from
+        the loader stay on the CPU and reach the device as 6xK tables)."""
+        B, N, C, H, W = inputs[0].shape
+        N = N // self.num_frame
+        imgs = inputs[0].view(B, N, self.num_frame, C, H, W)
+        imgs = [t.squeeze(2) for t in torch.split(imgs, 1, 2)]
+        sensor2egos, ego2globals, intrins, post_rots, post_trans, bda = \
+            inputs[1:7]
+        sensor2egos = sensor2egos.view(B, self.num_frame, N, 4, 4)
+        ego2globals = ego2globals.view(B, self.num_frame, N, 4, 4)
+        keyego2global = ego2globals[:, 0, 0, ...].unsqueeze(1).unsqueeze(1)
+        global2keyego = torch.inverse(keyego2global.double())
+        sensor2keyegos = (global2keyego @ ego2globals.double()
+                          @ sensor2egos.double()).float()
+        curr2adjsensor = None
+        if stereo:
+            tf = self.temporal_frame
+            curr2adjsensor = torch.inverse(
+                ego2globals[:, 1:tf + 1].double()
+                @ sensor2egos[:, 1:tf + 1].double()) \
+                @ ego2globals[:, :tf].double() @ sensor2egos[:, :tf].double()
+            curr2adjsensor = [p.squeeze(1) for p in
+                              torch.split(curr2adjsensor.float(), 1, 1)]
+            curr2adjsensor.extend([None] * self.extra_ref_frames)
+            assert len(curr2adjsensor) == self.num_frame
+        extra = [sensor2keyegos, ego2globals,
+                 intrins.view(B, self.num_frame, N, 3, 3),
+                 post_rots.view(B, self.num_frame, N, 3, 3),
+                 post_trans.view(B, self.num_frame, N, 3)]
+        extra = [[p.squeeze(1) for p in torch.split(t, 1, 1)] for t in extra]
+        sensor2keyegos, ego2globals, intrins, post_rots, post_trans = extra
+        return imgs, sensor2keyegos, ego2globals, intrins, post_rots, \
+            post_trans, bda, curr2adjsensor
+
+    # -- bevdet.py:34-50 ------------------------------------------------------
+    def image_encoder(self, img, stereo=False):
+        B, N, C, imH, imW = img.shape
+        x = self.img_backbone(img.reshape(B * N, C, imH, imW))
+        stereo_feat = None
+        if stereo:
+            stereo_feat = x[0]
+            x = x[1:]
+        if self.with_img_neck:
+            x = self.img_neck(x)
+            if type(x) in [list, tuple]:
+                x = x[0]
+        _, cdim, oh, ow = x.shape
+        return x.view(B, N, cdim, oh, ow), stereo_feat
+
+    # -- bevdet.py:573-588 (mmdet ResNet branch: stem + layer1 only) ---------
+    def extract_stereo_ref_feat(self, x):
+        B, N, C, imH, imW = x.shape
+        bb = self.img_backbone
+        y = bb.run_stem(x.reshape(B * N, C, imH, imW))
+        return ops.to_logical(bb.run_layer(0, y))
+
+    def bev_encoder(self, x):
+        x = self.img_bev_encoder_backbone(x)
+        x = self.img_bev_encoder_neck(x)
+        if type(x) in [list, tuple]:
+            x = x[0]
+        return x
+
+    # -- bevdet_occ.py:141-165 ------------------------------------------------
+    def prepare_bev_feat(self, img, sensor2keyego, ego2global, intrin,
+                         post_rot, post_tran, bda, mlp_input, feat_prev_iv,
+                         k2s_sensor, extra_ref_frame, depth_gt=None):
+        if extra_ref_frame:
+            return None, None, self.extract_stereo_ref_feat(img)
+        x, stereo_feat = self.image_encoder(img, stereo=True)
+        vt = self.img_view_transformer
+        metas = dict(k2s_sensor=k2s_sensor, intrins=intrin,
+                     post_rots=post_rot, post_trans=post_tran,
+                     frustum=vt.cv_frustum, cv_downsample=4,
+                     downsample=vt.downsample, grid_config=vt.grid_config,
+                     cv_feat_list=[feat_prev_iv, stereo_feat])
+        bev_feat, depth = vt(
+            [x, sensor2keyego, ego2global, intrin, post_rot, post_tran, bda,
+             mlp_input], metas, depth_gt)
+        if self.pre_process:
+            bev_feat = self.pre_process_net(bev_feat)[0]
+        return bev_feat, depth, stereo_feat
+
+    # -- bevdet_occ.py:167-269 ------------------------------------------------
+    def extract_img_feat(self, img_inputs, img_metas=None, **kwargs):
+        imgs, sensor2keyegos, ego2globals, intrins, post_rots, post_trans, \
+            bda, curr2adjsensor = img_inputs
+        dev = imgs[0].device
+        # pose tables travel to the device once (a few hundred floats each)
+        to_dev = lambda t: t.to(dev, non_blocking=True) if t is not None else t
+        sensor2keyegos = [to_dev(t) for t in sensor2keyegos]
+        ego2globals = [to_dev(t) for t in ego2globals]
+        intrins = [to_dev(t) for t in intrins]
+        post_rots = [to_dev(t) for t in post_rots]
+        post_trans = [to_dev(t) for t in post_trans]
+        curr2adjsensor = [to_dev(t) for t in curr2adjsensor]
+        bda = to_dev(bda)
+        bev_feat_list = []
+        depth_key_frame = None
+        feat_prev_iv = None
+        vt = self.img_view_transformer
+        for fid in range(self.num_frame - 1, -1, -1):
+            key_frame = fid == 0
+            extra_ref_frame = fid == self.num_frame - self.extra_ref_frames
+            mlp_input = vt.get_mlp_input(
+                sensor2keyegos[0], ego2globals[0], intrins[fid],
+                post_rots[fid], post_trans[fid], bda)
+            bev_feat, depth, feat_curr_iv = self.prepare_bev_feat(
+                imgs[fid], sensor2keyegos[fid], ego2globals[fid],
+                intrins[fid], post_rots[fid], post_trans[fid], bda, mlp_input,
+                feat_prev_iv, curr2adjsensor[fid], extra_ref_frame)
+            if key_frame:
+                depth_key_frame = depth
+            if not extra_ref_frame:
+                bev_feat_list.append(bev_feat)
+            feat_prev_iv = feat_curr_iv
+        # torch.cat(bev_feat_list, dim=1): [adjacent, key] order (:240,266)
+        parts = [ops.from_logical(f) for f in bev_feat_list]
+        ctot = sum(p.shape[-1] for p in parts)
+        cat = torch.empty((*parts[0].shape[:-1], ctot), device=dev,
+                          dtype=torch.float32)
+        c0 = 0
+        for p in parts:
+            ops.copy_channels_(cat[..., c0:c0 + p.shape[-1]], p)
+            c0 += p.shape[-1]
+        x = self.bev_encoder(ops.to_logical(cat))
+        return [x], depth_key_frame
+
+    def _build_packs(self):
+        return dict(final=self.final_conv.pack())
+
+    def voxel_features_cl(self, img, **kwargs):
+        """Trunk + final_conv (ReLU is ConvModule's default act) -> cl array
+        [B,Z,Y,X,C] in library voxel order."""
+        img_inputs = self.prepare_inputs(img, stereo=True)
+        img_feats, _ = self.extract_img_feat(img_inputs, None, **kwargs)
+        P = self.packs()
+        return ops.conv(ops.from_logical(img_feats[0]), P['final'], 'relu')
+
+
+def _pack_mlp(seq):
+    return [pack_linear(m) for m in seq if isinstance(m, nn.Linear)]
+
+
+@DETECTORS.register_module()
+class PreWorld(BEVStereo4DOCC):
+
+    def __init__(self, out_dim=32, dataset_type='Nuscenes', num_classes=18,
+                 dense_nerf_head=None, nerf_head=None, occupancy_head=None,
+                 test_threshold=8.5, use_lss_depth_loss=True,
+                 use_3d_loss=True, if_pretrain=False, if_render=True,
+                 if_post_finetune=False, weight_voxel_ce=0.0,
+                 weight_voxel_sem_scal=0.0, weight_voxel_geo_scal=0.0,
+                 weight_voxel_lovasz=0.0, empty_idx=17, use_focal_loss=True,
+                 balance_cls_weight=True, final_softplus=True, **kwargs):
+        super().__init__(use_predicter=False, out_dim=out_dim,
+                         num_classes=num_classes, **kwargs)
+        if dataset_type != 'Nuscenes':
+            raise NotImplementedError('only the nuScenes configs are shipped')
+        self.dataset_type = dataset_type
+        self.use_3d_loss = use_3d_loss
+        self.test_threshold = test_threshold
+        self.use_lss_depth_loss = use_lss_depth_loss
+        self.balance_cls_weight = balance_cls_weight
+        self.final_softplus = final_softplus
+        self.if_pretrain = if_pretrain
+        self.if_render = if_render
+        self.if_post_finetune = if_post_finetune
+        self.empty_idx = empty_idx
+        # nn.CrossEntropyLoss(weight=...) registers `semantic_loss.weight`
+        weights = torch.from_numpy(
+            1 / np.log(nusc_class_frequencies[:17] + 0.001)).float() \
+            if balance_cls_weight else None
+        self.semantic_loss = nn.CrossEntropyLoss(weight=weights,
+                                                 reduction='mean')
+        self.final_conv = ConvModule(
+            self.img_view_transformer.out_channels, self.out_dim,
+            kernel_size=3, stride=1, padding=1, bias=True,
+            conv_cfg=dict(type='Conv3d'))
+        dm = [nn.Linear(out_dim, out_dim * 2), nn.Softplus(),
+              nn.Linear(out_dim * 2, 2)]
+        if final_softplus:
+            dm.append(nn.Softplus())
+        self.density_mlp = nn.Sequential(*dm)
+        self.semantic_mlp = nn.Sequential(
+            nn.Linear(out_dim, out_dim * 2), nn.Softplus(),
+            nn.Linear(out_dim * 2, num_classes - 1))
+        self.color_mlp = nn.Sequential(
+            nn.Linear(out_dim, out_dim * 2), nn.Softplus(),
+            nn.Linear(out_dim * 2, 3))
+        self.nerf_head = builder.build_head(nerf_head)
+        self.occupancy_head = builder.build_head(occupancy_head)
+        self.use_focal_loss = use_focal_loss
+        if use_focal_loss:
+            self.focal_loss = builder.build_loss(dict(type='CustomFocalLoss'))
+
+    def _build_packs(self):
+        P = super()._build_packs()
+        P['density'] = _pack_mlp(self.density_mlp)
+        P['semantic'] = _pack_mlp(self.semantic_mlp)
+        P['color'] = _pack_mlp(self.color_mlp)
+        return P
+
+    # -- attribute projection (preworld.py:81-105,173-176,251-254) -----------
+    def attributes_cl(self, vf_cl, with_color=True):
+        """Per-voxel MLPs on a cl array [B,Z,Y,X,32] -> one attribute buffer
+        [B,Z,Y,X,24]: channel 0-1 density (after the final Softplus),
+        2-18 semantic, 19-21 colour."""
+        P = self.packs()
+        ns = self.num_classes - 1
+        rows = vf_cl.reshape(-1, vf_cl.shape[-1])
+        attr = torch.empty((rows.shape[0], 24), device=vf_cl.device,
+                           dtype=torch.float32)
+        h = ops.linear(rows, P['density'][0], 'softplus')
+        ops.linear(h, P['density'][1],
+                   'softplus' if self.final_softplus else None,
+                   out=attr[:, 0:2])
+        h = ops.linear(rows, P['semantic'][0], 'softplus')
+        ops.linear(h, P['semantic'][1], out=attr[:, 2:2 + ns])
+        if with_color:
+            h = ops.linear(rows, P['color'][0], 'softplus')
+            ops.linear(h, P['color'][1], out=attr[:, 2 + ns:5 + ns])
+        return attr.view(*vf_cl.shape[:-1], 24)
+
+    def _occ_from_density(self, vf_cl):
+        """preworld.py:173-194."""
+        ns = self.num_classes - 1
+        attr = self.attributes_cl(vf_cl, with_color=False)
+        occ, geo = ops.density_occ_zyx_to_xyz(
+            attr[:1, ..., 0:1], attr[:1, ..., 2:2 + ns], self.test_threshold,
+            self.num_classes - 1)
+        return occ, geo
+
+    def _occ_from_head(self, vf_cl):
+        """preworld.py:196-221 (nuScenes): OccHead logits -> argmax; geo_occ is
+        17 where the class is 17 else 0."""
+        logits = self.occupancy_head.logits_cl(vf_cl[:1], True)
+        occ = ops.argmax_zyx_to_xyz(logits)
+        return occ, logits
+
+    @staticmethod
+    def _to_numpy_pair(occ_dev, geo_dev=None, empty=17):
+        occ = occ_dev.cpu().numpy()
+        if geo_dev is None:
+            geo = np.where(occ != 17, 0, empty).astype(np.uint8)
+        else:
+            geo = geo_dev.cpu().numpy()
+        return occ, geo
+
+    def occupancy(self, vf_cl):
+        if self.if_post_finetune:
+            occ, _ = self._occ_from_head(vf_cl)
+            return self._to_numpy_pair(occ, None, self.num_classes - 1)
+        occ, geo = self._occ_from_density(vf_cl)
+        return self._to_numpy_pair(occ, geo)
+
+    def simple_test(self, points, img_metas, img=None, rescale=False,
+                    **kwargs):
+        vf = self.voxel_features_cl(img, **kwargs)
+        occ, geo_occ = self.occupancy(vf)
+        return {'semantic_occ': [occ], 'geo_occ': [geo_occ]}
+
+    # -- pre-training forward (preworld.py:229-256 + nerf_head.py:361-407) ---
+    def render_forward(self, img, rays, **kwargs):
+        """The forward part of ``forward_train`` with ``if_render=True``:
+        trunk -> attribute projection -> volume rendering of ``rays``
+        [B,R,16].  Returns the per-sample renderings (losses are training-only
+        and out of scope)."""
+        vf = self.voxel_features_cl(img, **kwargs)
+        ns = self.num_classes - 1
+        attr = self.attributes_cl(vf)
+        bda = img[6].to(vf.device)
+        rays = rays.to(vf.device)
+        return [self.nerf_head.render(
+            attr[b, ..., 0:1], attr[b, ..., 2:2 + ns],
+            attr[b, ..., 2 + ns:5 + ns], rays[b], bda[b], library_order=True)
+            for b in range(rays.shape[0])]
+
+
+@DETECTORS.register_module()
+class PreWorld4DTraj(PreWorld):
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        od = self.out_dim
+        self.velocity_dim = 3
+        self.past_frame = 5
+        self.plan_head = nn.Sequential(
+            nn.Linear(self.velocity_dim * (self.past_frame + 2), 256),
+            nn.ReLU(inplace=True), nn.Linear(256, 256), nn.ReLU(inplace=True),
+            nn.Linear(256, od))
+        self.fusion_head = nn.Sequential(
+            nn.Linear(od * 2, od * 4), nn.Softplus(), nn.Linear(od * 4, od))
+        self.downscale = DownScaleModule3DCustom(in_dim=od)
+        self.ego_fusion_head = nn.Sequential(
+            nn.Linear(od * 5, od * 8), nn.Softplus(),
+            nn.Linear(od * 8, od * 4), nn.Softplus(),
+            nn.Linear(od * 4, od * 2), nn.Softplus(), nn.Linear(od * 2, od))
+        self.traj_head = nn.Sequential(
+            nn.Linear(od, od * 2), nn.Softplus(), nn.Linear(od * 2, 2))
+        self.curr_epoch = 0
+
+    def set_epoch(self, epoch):
+        self.curr_epoch = epoch
+
+    def _build_packs(self):
+        P = super()._build_packs()
+        od = self.out_dim
+        P['plan'] = _pack_mlp(self.plan_head)
+        f0, f2 = self.fusion_head[0], self.fusion_head[2]
+        # fusion_head[0] on cat([voxel, ego]) = W[:, :od] voxel + (W[:, od:]
+        # ego + b): the ego half is a per-sample bias, so the [.., 64] concat
+        # the reference materialises (164 MB/step) never exists.
+        P['fuse_vox'] = ops.PackedConv(f0.weight[:, :od], None)
+        P['fuse_ego'] = ops.PackedConv(f0.weight[:, od:], f0.bias)
+        P['fuse_out'] = pack_linear(f2)
+        return P
+
+    def forecast_step(self, vf_cl, ego_states):
+        """preworld_temporal_traj.py:329-341,368: plan_head -> broadcast ->
+        cat -> fusion_head -> residual add."""
+        P = self.packs()
+        B = vf_cl.shape[0]
+        e = ego_states.reshape(B, -1).to(vf_cl.device).float()
+        e = torch.nn.functional.pad(e, (0, (-e.shape[1]) % 4)).contiguous()
+        e = ops.linear(e, P['plan'][0], 'relu')
+        e = ops.linear(e, P['plan'][1], 'relu')
+        e = ops.linear(e, P['plan'][2])
+        ego_bias = ops.linear(e, P['fuse_ego'])              # [B, 128]
+        out = torch.empty_like(vf_cl)
+        for b in range(B):
+            rows = vf_cl[b].reshape(-1, vf_cl.shape[-1])
+            pc = P['fuse_vox']
+            step = ops.PackedConv.__new__(ops.PackedConv)
+            for k in ops.PackedConv.__slots__:
+                setattr(step, k, getattr(pc, k))
+            step.bias = ego_bias[b].contiguous()
+            h = ops.linear(rows, step, 'softplus')
+            ops.linear(h, P['fuse_out'], residual=rows,
+                       out=out[b].reshape(-1, vf_cl.shape[-1]))
+        return out
+
+    def simple_test(self, points, img_metas, img=None, rescale=False,
+                    **kwargs):
+        """preworld_temporal_traj.py:213-371.  Every forecasting step feeds
+        ``temporal_ego_states[0]`` (:331), exactly as the reference does."""
+        vf = self.voxel_features_cl(img)
+        temporal_ego_states = kwargs['temporal_ego_states'][0]
+        res = {}
+        occ, geo = self.occupancy(vf)
+        res['semantic_occ_0s'], res['geo_occ_0s'] = [occ], [geo]
+        first = 1 if self.if_post_finetune else 2
+        for k in range(6):
+            vf = self.forecast_step(vf, temporal_ego_states[0])
+            occ, geo = self.occupancy(vf)
+            res[f'semantic_occ_{k + first}s'] = [occ]
+            res[f'geo_occ_{k + first}s'] = [geo]
+        return res

@@ -1,0 +1,213 @@
+"""Image side: ``ResNet`` backbone and ``CustomFPN`` neck.
+
+``ResNet`` mirrors mmdet 2.24.0 ``mmdet/models/backbones/resnet.py`` (pinned by
+the reference's requirements.txt:15; call sites detectors/bevdet.py:10,38,
+577-588) -- same constructor kwargs and parameter names (``conv1``, ``bn1``,
+``layer{i}.{j}.conv{1,2,3}`` / ``bn{1,2,3}`` / ``downsample.{0,1}``), which are
+also torchvision's.  ``CustomFPN`` mirrors reference necks/fpn.py:10-203.
+All arithmetic runs in the C-ABI conv kernel with BatchNorm, residual add and
+ReLU fused into its epilogue.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .base import BaseModule, ConvModule, pack_conv
+from .builder import BACKBONES, NECKS
+
+
+class _Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride, downsample, style):
+        super().__init__()
+        s1, s2 = (1, stride) if style == 'pytorch' else (stride, 1)
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, stride=s1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=s2, padding=1,
+                               bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.downsample = downsample
+
+    def pack(self):
+        p = [pack_conv(self.conv1, self.bn1), pack_conv(self.conv2, self.bn2),
+             pack_conv(self.conv3, self.bn3)]
+        if self.downsample is not None:
+            p.append(pack_conv(self.downsample[0], self.downsample[1]))
+        return p
+
+    @staticmethod
+    def run(p, x):
+        identity = ops.conv(x, p[3]) if len(p) == 4 else x
+        y = ops.conv(x, p[0], 'relu')
+        y = ops.conv(y, p[1], 'relu')
+        return ops.conv(y, p[2], 'relu', residual=identity)
+
+
+class _BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride, downsample, style):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride=stride, padding=1,
+                               bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = downsample
+
+    def pack(self):
+        p = [pack_conv(self.conv1, self.bn1), pack_conv(self.conv2, self.bn2)]
+        if self.downsample is not None:
+            p.append(pack_conv(self.downsample[0], self.downsample[1]))
+        return p
+
+    @staticmethod
+    def run(p, x):
+        identity = ops.conv(x, p[2]) if len(p) == 3 else x
+        y = ops.conv(x, p[0], 'relu')
+        return ops.conv(y, p[1], 'relu', residual=identity)
+
+
+@BACKBONES.register_module()
+class ResNet(BaseModule):
+    arch_settings = {18: (_BasicBlock, (2, 2, 2, 2)),
+                     34: (_BasicBlock, (3, 4, 6, 3)),
+                     50: (_Bottleneck, (3, 4, 6, 3)),
+                     101: (_Bottleneck, (3, 4, 23, 3)),
+                     152: (_Bottleneck, (3, 8, 36, 3))}
+
+    def __init__(self, depth, in_channels=3, stem_channels=None,
+                 base_channels=64, num_stages=4, strides=(1, 2, 2, 2),
+                 dilations=(1, 1, 1, 1), out_indices=(0, 1, 2, 3),
+                 style='pytorch', deep_stem=False, avg_down=False,
+                 frozen_stages=-1, conv_cfg=None,
+                 norm_cfg=dict(type='BN', requires_grad=True), norm_eval=True,
+                 dcn=None, stage_with_dcn=(False, False, False, False),
+                 plugins=None, with_cp=False, zero_init_residual=True,
+                 pretrained=None, init_cfg=None):
+        super().__init__(init_cfg)
+        if deep_stem or avg_down or dcn is not None or plugins is not None \
+                or tuple(dilations) != (1, 1, 1, 1):
+            raise NotImplementedError(
+                'ResNet variant not used by the PreWorld configs')
+        block, stage_blocks = self.arch_settings[depth]
+        self.depth = depth
+        self.deep_stem = deep_stem
+        self.out_indices = tuple(out_indices)
+        stem_channels = stem_channels or base_channels
+        self.conv1 = nn.Conv2d(in_channels, stem_channels, 7, 2, 3, bias=False)
+        self.norm1_name = 'bn1'
+        self.bn1 = nn.BatchNorm2d(stem_channels)
+        self.res_layers = []
+        inplanes = stem_channels
+        for i, nb in enumerate(stage_blocks[:num_stages]):
+            planes = base_channels * 2 ** i
+            blocks = []
+            for b in range(nb):
+                stride = strides[i] if b == 0 else 1
+                downsample = None
+                if b == 0 and (stride != 1
+                               or inplanes != planes * block.expansion):
+                    downsample = nn.Sequential(
+                        nn.Conv2d(inplanes, planes * block.expansion, 1,
+                                  stride=stride, bias=False),
+                        nn.BatchNorm2d(planes * block.expansion))
+                blocks.append(block(inplanes, planes, stride, downsample,
+                                    style))
+                inplanes = planes * block.expansion
+            name = f'layer{i + 1}'
+            self.add_module(name, nn.Sequential(*blocks))
+            self.res_layers.append(name)
+
+    @property
+    def norm1(self):
+        return self.bn1
+
+    def _build_packs(self):
+        return dict(stem=pack_conv(self.conv1, self.bn1),
+                    layers=[[blk.pack() for blk in getattr(self, n)]
+                            for n in self.res_layers])
+
+    # -- stage-level entry points (bevdet.py:577-588 runs stem + layer1 only
+    #    for the stereo reference frame) ------------------------------------
+    def run_stem(self, img_nchw):
+        """NCHW image batch -> cl array after conv1/bn1/relu/maxpool."""
+        p = self.packs()
+        x = ops.nchw_to_nhwc(img_nchw, p['stem'].cin)
+        x = ops.conv(x, p['stem'], 'relu')
+        return ops.maxpool3x3s2(x)
+
+    def run_layer(self, i, x):
+        p = self.packs()
+        blk = type(getattr(self, self.res_layers[i])[0])
+        for bp in p['layers'][i]:
+            x = blk.run(bp, x)
+        return x
+
+    def forward(self, x):
+        """[N,3,H,W] -> tuple of logical [N,C,h,w] feature maps
+        (channels_last strides) for ``out_indices``."""
+        x = self.run_stem(x)
+        outs = []
+        for i in range(len(self.res_layers)):
+            x = self.run_layer(i, x)
+            if i in self.out_indices:
+                outs.append(ops.to_logical(x))
+        return tuple(outs)
+
+
+@NECKS.register_module()
+class CustomFPN(BaseModule):
+    """necks/fpn.py:10-203 for the configuration the path uses: no norm, no
+    activation, nearest top-down upsampling to the finer map's size, outputs
+    selected by ``out_ids``."""
+
+    def __init__(self, in_channels, out_channels, num_outs, start_level=0,
+                 end_level=-1, out_ids=[], add_extra_convs=False,
+                 relu_before_extra_convs=False, no_norm_on_lateral=False,
+                 conv_cfg=None, norm_cfg=None, act_cfg=None,
+                 upsample_cfg=dict(mode='nearest'),
+                 init_cfg=dict(type='Xavier', layer='Conv2d',
+                               distribution='uniform')):
+        super().__init__(init_cfg)
+        assert isinstance(in_channels, list)
+        if norm_cfg is not None or act_cfg is not None or add_extra_convs \
+                or upsample_cfg.get('mode') != 'nearest' \
+                or 'scale_factor' in upsample_cfg:
+            raise NotImplementedError(
+                'CustomFPN variant not used by the PreWorld configs')
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.num_ins = len(in_channels)
+        self.num_outs = num_outs
+        self.out_ids = list(out_ids)
+        self.backbone_end_level = self.num_ins if end_level == -1 \
+            else end_level
+        self.start_level = start_level
+        assert num_outs <= len(self.out_ids) or num_outs == 1
+        self.lateral_convs = nn.ModuleList()
+        self.fpn_convs = nn.ModuleList()
+        for i in range(self.start_level, self.backbone_end_level):
+            self.lateral_convs.append(ConvModule(
+                in_channels[i], out_channels, 1, act_cfg=None))
+            if i in self.out_ids:
+                self.fpn_convs.append(ConvModule(
+                    out_channels, out_channels, 3, padding=1, act_cfg=None))
+
+    def _build_packs(self):
+        return dict(lat=[m.pack() for m in self.lateral_convs],
+                    fpn=[m.pack() for m in self.fpn_convs])
+
+    def forward(self, inputs):
+        assert len(inputs) == len(self.in_channels)
+        p = self.packs()
+        lat = [ops.conv(ops.from_logical(inputs[i + self.start_level]), pc)
+               for i, pc in enumerate(p['lat'])]
+        for i in range(len(lat) - 1, 0, -1):
+            ops.upsample_nearest_add_(lat[i - 1], lat[i])
+        outs = [ops.to_logical(ops.conv(lat[i], p['fpn'][k]))
+                for k, i in enumerate(self.out_ids)]
+        return outs[0]

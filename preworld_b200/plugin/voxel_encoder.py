@@ -1,0 +1,137 @@
+"""3-D occupancy encoder: ``CustomResNet3D`` and ``LSSFPN3D``.
+
+Mirrors reference backbones/resnet.py:88-184 (BasicBlock3D, CustomResNet3D)
+and necks/lss_fpn.py:103-148 (LSSFPN3D): same kwargs, same state_dict keys
+(``layers.{i}.{j}.conv{1,2}.{conv,bn}``, ``layers.{i}.0.downsample.{conv,bn}``,
+``conv.{conv,bn}``).  Volumes are channels-last [B,Z,Y,X,C]; the logical
+tensors exchanged with callers are [B,C,Z,Y,X] with channels_last_3d strides.
+
+Fusions relative to the reference graph:
+* conv1 (+BN+ReLU) and the 3^3 ``downsample`` shortcut (+BN) of the first
+  block of every stage read the same input with the same stride -> ONE launch
+  with 2*Cout output channels (ReLU on the first half only);
+* BN, the residual add and the final ReLU of a block live in the epilogue of
+  conv2;
+* LSSFPN3D: the x2 / x4 trilinear up-samplings write straight into channel
+  slices of the concatenation buffer read by the 1x1x1 conv.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .base import BaseModule, ConvModule
+from .builder import BACKBONES, NECKS
+
+_BN3D = dict(type='BN3d')
+_C3D = dict(type='Conv3d')
+
+
+class BasicBlock3D(nn.Module):
+    def __init__(self, channels_in, channels_out, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = ConvModule(channels_in, channels_out, 3, stride=stride,
+                                padding=1, bias=False, conv_cfg=_C3D,
+                                norm_cfg=_BN3D, act_cfg=dict(type='ReLU'))
+        self.conv2 = ConvModule(channels_out, channels_out, 3, stride=1,
+                                padding=1, bias=False, conv_cfg=_C3D,
+                                norm_cfg=_BN3D, act_cfg=None)
+        self.downsample = downsample
+        self.channels_out = channels_out
+
+    def pack(self):
+        c1, c2 = self.conv1.pack(), self.conv2.pack()
+        if self.downsample is None:
+            return dict(c1=c1, c2=c2, fused=False)
+        ds = self.downsample.pack()
+        # one conv with [conv1 | downsample] output channels
+        f = ops.PackedConv.__new__(ops.PackedConv)
+        f.w = torch.cat([c1.w[:, :c1.cout], ds.w[:, :ds.cout]], 1).contiguous()
+        f.scale = torch.cat([c1.scale, ds.scale]).contiguous()
+        f.bias = torch.cat([c1.bias, ds.bias]).contiguous()
+        f.cin, f.cout, f.k, f.w_ld = c1.cin, c1.cout + ds.cout, c1.k, \
+            c1.cout + ds.cout
+        f.stride, f.pad, f.dil = c1.stride, c1.pad, c1.dil
+        assert f.w_ld % 4 == 0 and c1.cout % 4 == 0
+        return dict(c1=f, c2=c2, fused=True, split=c1.cout)
+
+    @staticmethod
+    def run(p, x):
+        if p['fused']:
+            y = ops.conv(x, p['c1'], 'relu', act_channels=p['split'])
+            s = p['split']
+            return ops.conv(y[..., :s], p['c2'], 'relu', residual=y[..., s:])
+        y = ops.conv(x, p['c1'], 'relu')
+        return ops.conv(y, p['c2'], 'relu', residual=x)
+
+
+@BACKBONES.register_module()
+class CustomResNet3D(BaseModule):
+
+    def __init__(self, numC_input, num_layer=[2, 2, 2], num_channels=None,
+                 stride=[2, 2, 2], backbone_output_ids=None, with_cp=False):
+        super().__init__()
+        assert len(num_layer) == len(stride)
+        num_channels = [numC_input * 2 ** (i + 1)
+                        for i in range(len(num_layer))] \
+            if num_channels is None else num_channels
+        self.backbone_output_ids = range(len(num_layer)) \
+            if backbone_output_ids is None else backbone_output_ids
+        layers = []
+        curr = numC_input
+        for i in range(len(num_layer)):
+            layer = [BasicBlock3D(
+                curr, num_channels[i], stride=stride[i],
+                downsample=ConvModule(curr, num_channels[i], 3,
+                                      stride=stride[i], padding=1, bias=False,
+                                      conv_cfg=_C3D, norm_cfg=_BN3D,
+                                      act_cfg=None))]
+            curr = num_channels[i]
+            layer.extend([BasicBlock3D(curr, curr)
+                          for _ in range(num_layer[i] - 1)])
+            layers.append(nn.Sequential(*layer))
+        self.layers = nn.Sequential(*layers)
+        self.with_cp = with_cp
+
+    def _build_packs(self):
+        return [[blk.pack() for blk in layer] for layer in self.layers]
+
+    def forward(self, x):
+        """[B,C,Z,Y,X] (channels_last_3d) -> list of the same."""
+        x = ops.from_logical(x)
+        feats = []
+        for lid, layer in enumerate(self.packs()):
+            for bp in layer:
+                x = BasicBlock3D.run(bp, x)
+            if lid in self.backbone_output_ids:
+                feats.append(ops.to_logical(x))
+        return feats
+
+
+@NECKS.register_module()
+class LSSFPN3D(BaseModule):
+
+    def __init__(self, in_channels, out_channels, levels=3, with_cp=False):
+        super().__init__()
+        if levels != 3:
+            raise NotImplementedError('PreWorld configs use levels=3')
+        self.levels = levels
+        self.conv = ConvModule(in_channels, out_channels, 1, stride=1,
+                               padding=0, bias=False, conv_cfg=_C3D,
+                               norm_cfg=_BN3D, act_cfg=dict(type='ReLU'))
+        self.with_cp = with_cp
+
+    def _build_packs(self):
+        return self.conv.pack()
+
+    def forward(self, feats):
+        x8, x16, x32 = [ops.from_logical(f) for f in feats]
+        pc = self.packs()
+        b, z, y, x, c8 = x8.shape
+        c16, c32 = x16.shape[-1], x32.shape[-1]
+        assert c8 + c16 + c32 == pc.cin
+        cat = torch.empty((b, z, y, x, pc.cin), device=x8.device,
+                          dtype=torch.float32)
+        ops.copy_channels_(cat[..., :c8], x8)
+        ops.upsample_trilinear_(cat[..., c8:c8 + c16], x16)
+        ops.upsample_trilinear_(cat[..., c8 + c16:], x32)
+        return ops.to_logical(ops.conv(cat, pc, 'relu'))
