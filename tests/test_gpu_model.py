@@ -1,0 +1,226 @@
+"""End-to-end parity of the plugin detectors (all arithmetic in the C-ABI CUDA
+library) against (a) the golden fixtures produced by the verbatim reference
+and (b) the CPU oracle run on the same seeded inputs.
+
+Bars (BASELINE.json north_star): class logits within 1e-3 relative fp32;
+argmax occupancy identical -- except voxels whose top-2 logit margin in the
+oracle is below the float tolerance (near ties flip between ANY two fp32
+evaluation orders: the reference's own unstable argsort makes its GPU result
+non-deterministic at that level, and the CPU oracle itself differs from the
+verbatim reference in 1 voxel of 640 000, see tests/golden/REPORT.json)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import torch_ref                                   # noqa: E402
+from oracle.cases import (CASES, build_case_inputs, model_cfg_for,   # noqa
+                          stage_sample)
+from preworld_b200 import build_model, ops                     # noqa: E402
+from preworld_b200 import synthetic as S                       # noqa: E402
+
+REL_TOL = 1e-3
+
+
+def _model(case):
+    m = build_model(model_cfg_for(case)).eval()
+    S.lively_init_(m, case['seed'])
+    return m
+
+
+def _run_stages(model, inputs):
+    """Run the trunk capturing the same stages oracle/make_golden.py hooks."""
+    st = {}
+    calls = {'n': 0}
+
+    def vt_hook(mod, inp, out):
+        fid = 1 - calls['n']
+        st[f'lifted_{fid}'], st[f'depth_{fid}'] = out[0], out[1]
+        calls['n'] += 1
+    hs = [model.img_view_transformer.register_forward_hook(vt_hook),
+          model.img_bev_encoder_neck.register_forward_hook(
+              lambda m, i, o: st.__setitem__('encoded', o))]
+    vf = model.voxel_features_cl(inputs)
+    for h in hs:
+        h.remove()
+    st['voxel_feats'] = vf.permute(0, 3, 2, 1, 4)            # [B,X,Y,Z,C]
+    if model.if_post_finetune:
+        lg = model.occupancy_head.logits_cl(vf[:1], True)
+        st['logits'] = lg.permute(0, 4, 3, 2, 1)             # [1,18,X,Y,Z]
+    return vf, st
+
+
+def _check_samples(fx, st, name):
+    worst = {}
+    for key in fx.files:
+        kind, k = key.split('/', 1)
+        if kind != 'sample':
+            continue
+        got = stage_sample(st[k]).numpy()
+        scale = max(float(fx['stats/' + k][2]), 1e-6)       # max |ref|
+        err = float(np.abs(got - fx[key]).max()) / scale
+        worst[k] = err
+        assert err < REL_TOL, (name, k, err)
+    return worst
+
+
+def _margin_ok(occ, want, logits_ref):
+    """Every argmax mismatch must sit on a near tie of the oracle logits."""
+    bad = np.argwhere(occ != want)
+    lg = logits_ref[0].permute(1, 2, 3, 0).numpy()          # [X,Y,Z,18]
+    scale = np.abs(lg).max()
+    for x, y, z in bad:
+        top2 = np.sort(lg[x, y, z])[-2:]
+        assert top2[1] - top2[0] < REL_TOL * scale, \
+            ((x, y, z), top2, occ[x, y, z], want[x, y, z])
+    return len(bad)
+
+
+@pytest.mark.parametrize('name', ['tiny_finetune', 'tiny_pretrain'])
+def test_preworld_matches_reference_and_oracle(name, golden_dir):
+    case = CASES[name]
+    fx = np.load(os.path.join(golden_dir, name + '.npz'))
+    model = _model(case)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    inputs, _ = build_case_inputs(case)
+    dev_inputs = tuple(t.cuda() for t in inputs)
+    with torch.no_grad():
+        vf, st = _run_stages(model, dev_inputs)
+        out = model.simple_test(None, None, img=dev_inputs)
+    worst = _check_samples(fx, {k: v.cpu() for k, v in st.items()}, name)
+    print(name, 'worst relative stage errors', worst)
+    # oracle on the CPU for full tensors
+    pc = torch_ref.PathConfig(model_cfg_for(case))
+    ost = {}
+    want = torch_ref.preworld_simple_test(sd, pc, inputs, ost)
+    for k in ('lifted_0', 'lifted_1', 'encoded', 'voxel_feats'):
+        ref = ost[k]
+        err = (st[k].cpu() - ref).abs().max().item() / ref.abs().max().item()
+        assert err < REL_TOL, (k, err)
+    assert out['semantic_occ'][0].dtype == np.uint8
+    assert out['semantic_occ'][0].shape == fx['out/semantic_occ'].shape
+    if model.if_post_finetune:
+        err = (st['logits'].cpu() - ost['logits']).abs().max().item() \
+            / ost['logits'].abs().max().item()
+        assert err < REL_TOL, err
+        n_bad = _margin_ok(out['semantic_occ'][0], want['semantic_occ'][0],
+                           ost['logits'])
+        assert n_bad <= 0.001 * want['semantic_occ'][0].size
+        n_fx = int((out['semantic_occ'][0] != fx['out/semantic_occ']).sum())
+        assert n_fx <= 0.001 * fx['out/semantic_occ'].size + 2
+        geo = out['geo_occ'][0]
+        assert ((geo == 0) == (out['semantic_occ'][0] != 17)).all()
+    else:
+        # density path: thresholded argmax over the semantic MLP
+        for k in ('semantic_occ', 'geo_occ'):
+            mism = int((out[k][0] != fx['out/' + k]).sum())
+            assert mism <= 0.001 * fx['out/' + k].size + 2, (k, mism)
+
+
+@pytest.mark.parametrize('name', ['tiny_traj', 'tiny_pretrain_traj'])
+def test_preworld4d_forecasting_matches_reference(name, golden_dir):
+    case = CASES[name]
+    fx = np.load(os.path.join(golden_dir, name + '.npz'))
+    model = _model(case).cuda()
+    inputs, extra = build_case_inputs(case)
+    dev_inputs = tuple(t.cuda() for t in inputs)
+    with torch.no_grad():
+        out = model(return_loss=False, img_inputs=[dev_inputs],
+                    img_metas=[None], **extra)
+    keys = [k for k in fx.files if k.startswith('out/')]
+    assert len(keys) == 14                      # 7 grids x (semantic, geo)
+    for key in keys:
+        k = key.split('/', 1)[1]
+        mism = int((out[k][0] != fx[key]).sum())
+        # six recursive steps amplify fp32 reordering; near ties only
+        assert mism <= 0.002 * fx[key].size + 2, (k, mism)
+    with torch.no_grad():
+        vf, st = _run_stages(model, dev_inputs)
+    _check_samples(fx, {k: v.cpu() for k, v in st.items()}, name)
+
+
+def test_forecast_step_matches_oracle():
+    case = CASES['tiny_traj']
+    model = _model(case)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    g = torch.Generator().manual_seed(0)
+    vf = torch.randn(2, 40, 40, 16, 32, generator=g)         # [B,X,Y,Z,C]
+    ego = torch.randn(2, 1, 21, generator=g)
+    want = torch_ref.forecast_step(sd, vf, ego)
+    vf_cl = vf.permute(0, 3, 2, 1, 4).contiguous().cuda()
+    with torch.no_grad():
+        got = model.forecast_step(vf_cl, ego.cuda())
+    got = got.permute(0, 3, 2, 1, 4).cpu()
+    assert (got - want).abs().max().item() / want.abs().max().item() < 1e-5
+
+
+def test_attribute_projection_matches_oracle():
+    case = CASES['tiny_pretrain']
+    model = _model(case)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    g = torch.Generator().manual_seed(1)
+    vf = torch.randn(1, 40, 40, 16, 32, generator=g) * 2
+    d, s, c = torch_ref.attribute_projection(sd, vf)
+    with torch.no_grad():
+        attr = model.attributes_cl(vf.permute(0, 3, 2, 1, 4).contiguous().cuda())
+    attr = attr.permute(0, 3, 2, 1, 4).cpu()
+    for got, want in ((attr[..., 0], d), (attr[..., 2:19], s),
+                      (attr[..., 19:22], c)):
+        assert (got - want).abs().max().item() / want.abs().max().item() < 1e-5
+
+
+def test_render_forward_runs_end_to_end():
+    """Config 3 plumbing: trunk -> attribute projection -> ray march."""
+    case = CASES['tiny_pretrain']
+    # NerfHead hard-codes a 200x200x16 world (nerf_head.py:150): use the full
+    # grid with the tiny image size
+    from preworld_b200 import model_cfg
+    cfg = model_cfg('pretrain', 'r50', (64, 176))
+    model = build_model(cfg).eval()
+    S.lively_init_(model, 3)
+    model = model.cuda()
+    inputs = S.make_img_inputs(1, (64, 176), seed=4)
+    rays = S.make_rays(inputs, 512, seed=5)
+    with torch.no_grad():
+        res = model.render_forward(tuple(t.cuda() for t in inputs), rays.cuda())
+    r = res[0]
+    assert r['render_semantic'].shape == (512, 17)
+    assert torch.isfinite(r['render_depth']).all()
+    assert r['ray_mask'].all()
+
+
+@pytest.mark.timeout(900)
+def test_full_size_finetune_matches_reference(golden_dir):
+    """BASELINE.json configs[0]/[1]: 6x3x256x704 -> 200x200x16, R50."""
+    case = CASES['full_finetune']
+    fx = np.load(os.path.join(golden_dir, 'full_finetune.npz'))
+    model = _model(case)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    inputs, _ = build_case_inputs(case)
+    dev_inputs = tuple(t.cuda() for t in inputs)
+    with torch.no_grad():
+        vf, st = _run_stages(model, dev_inputs)
+        out = model.simple_test(None, None, img=dev_inputs)
+    worst = _check_samples(fx, {k: v.cpu() for k, v in st.items()}, 'full')
+    print('full_finetune worst relative stage errors', worst)
+    occ, want = out['semantic_occ'][0], fx['out/semantic_occ']
+    assert occ.shape == (200, 200, 16)
+    n_bad = int((occ != want).sum())
+    print('full_finetune argmax mismatches vs reference fixture:', n_bad)
+    assert n_bad <= 64                        # 1e-4 of 640 000 voxels
+    # size-independent properties
+    assert ((out['geo_occ'][0] == 0) == (occ != 17)).all()
+    with torch.no_grad():
+        out2 = model.simple_test(None, None, img=dev_inputs)
+    assert (out2['semantic_occ'][0] == occ).all()      # deterministic
+    lifted = st['lifted_0'].cpu()
+    assert lifted.shape == (1, 32, 16, 200, 200)
+    nz = (lifted.abs().sum(1) > 0).float().mean().item()
+    assert 0.15 < nz < 0.35                   # ~142k of 640k voxels non-empty
