@@ -172,8 +172,12 @@ conv_igemm_kernel(const pw_conv_desc p, const float* __restrict__ x,
     bi[j] = (bias != nullptr && c < p.cout) ? __ldg(bias + c) : 0.f;
   }
   const int act_end = p.act_channels > 0 ? p.act_channels : p.cout;
+  // float4 epilogue only when the (possibly channel-sliced) output and
+  // residual rows are 16-byte aligned
   const bool vec_ok = ((p.out_ld & 3) == 0) && (col0 + TN <= p.cout) &&
-                      (res == nullptr || (p.res_ld & 3) == 0);
+                      ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
+                      (res == nullptr || ((p.res_ld & 3) == 0 &&
+                                          (reinterpret_cast<uintptr_t>(res) & 15) == 0));
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     int m = m0 + ty * TM + i;
