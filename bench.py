@@ -114,7 +114,7 @@ class LaunchProfiler:
         from preworld_b200 import _lib
         for name in _lib.SIGNATURES:
             if name in ('pw_abi_version', 'pw_launch_count',
-                        'pw_lift_workspace_bytes'):
+                        'pw_lift_workspace_bytes', 'pw_conv_umma_supported'):
                 continue
             fn = getattr(self.L, name)
             self.orig[name] = fn
@@ -128,18 +128,28 @@ class LaunchProfiler:
             e0.record()
             rc = fn(*args)
             e1.record()
-            self.records.append((name, e0, e1, self._work(name, args)))
+            self.records.append((name, e0, e1, self._work(name, args),
+                                 self._shape(name, args)))
             return rc
         return call
 
     @staticmethod
+    def _shape(name, a):
+        if name in ('pw_conv_fwd', 'pw_conv_umma_fwd'):
+            d = a[0]._obj
+            return (f'{d.n}x{d.d}x{d.h}x{d.w}x{d.cin}->{d.cout} '
+                    f'k{d.kd}{d.kh}{d.kw} s{d.sw} d{d.dw}')
+        return ''
+
+    @staticmethod
     def _work(name, a):
         """(algorithmic flops, algorithmic bytes) of one call."""
-        if name == 'pw_conv_fwd':
+        if name in ('pw_conv_fwd', 'pw_conv_umma_fwd'):
             d = a[0]._obj
             m = d.n * d.od * d.oh * d.ow
             k = d.kd * d.kh * d.kw * d.cin
-            res = 4 * m * d.cout if a[5] is not None and a[5].value else 0
+            r = a[5] if name == 'pw_conv_fwd' else a[6]
+            res = 4 * m * d.cout if r is not None and r.value else 0
             return (2.0 * m * k * d.cout,
                     4.0 * (d.n * d.d * d.h * d.w * d.cin + m * d.cout
                            + k * d.cout) + res)
@@ -162,9 +172,18 @@ class LaunchProfiler:
     def summary(self, steps):
         torch.cuda.synchronize()
         agg = {}
-        for name, e0, e1, (fl, by) in self.records:
+        layers = {}
+        for name, e0, e1, (fl, by), shape in self.records:
+            ms = e0.elapsed_time(e1)
             a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
-            a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += fl; a[3] += by
+            a[0] += 1; a[1] += ms; a[2] += fl; a[3] += by
+            if shape:
+                b = layers.setdefault(name[3:-4] + ' ' + shape, [0, 0.0, 0.0])
+                b[0] += 1; b[1] += ms; b[2] += fl
+        self.layers = {
+            k: dict(launches_per_step=v[0] / steps, ms_per_step=v[1] / steps,
+                    tflops=v[2] / (v[1] * 1e-3) / 1e12 if v[1] else 0.0)
+            for k, v in sorted(layers.items(), key=lambda kv: -kv[1][1])}
         out = {}
         for name, (cnt, ms, fl, by) in agg.items():
             out[name] = dict(launches_per_step=cnt / steps,
@@ -348,9 +367,24 @@ def main():
             for i in range(psteps):
                 step_resident(i)
         kernels = prof.summary(psteps)
+        if os.environ.get('PW_BENCH_LAYERS'):
+            with open(os.environ['PW_BENCH_LAYERS'], 'w') as f:
+                json.dump(prof.layers, f, indent=1)
         top = max(kernels, key=lambda k: kernels[k]['ms_per_step'])
         k = kernels[top]
-        if top == 'pw_conv_fwd':
+        if top == 'pw_conv_umma_fwd':
+            roof = {'kernel': 'conv_umma_kernel (pw_conv_umma_fwd: tcgen05 '
+                              'kind::tf32 implicit GEMM, 3xTF32 split, TMA)',
+                    'bound': 'tensor', 'achieved': k['tflops'],
+                    'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                    'frac': k['tflops'] / peaks['bf16_tflops_sustained'],
+                    'traffic': None, 'peak_source': peak_src,
+                    'share_of_step': k['ms_per_step'] / (ms / args.steps),
+                    'note': 'achieved = ALGORITHMIC fp32 conv FLOPs / time; '
+                            'the kernel executes 3 tf32 MMAs per algorithmic '
+                            'MMA (tf32 dense peak is half the bf16 peak), so '
+                            'the executed-tensor-work fraction is 6x this'}
+        elif top == 'pw_conv_fwd':
             roof = {'kernel': 'conv_igemm_kernel (pw_conv_fwd, fp32 SIMT '
                               'implicit GEMM; all conv/linear layers)',
                     'bound': 'tensor', 'achieved': k['tflops'],

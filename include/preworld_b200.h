@@ -65,6 +65,19 @@ int pw_conv_fwd(const pw_conv_desc* desc, const float* x, const float* w,
                 const float* scale, const float* bias, const float* residual,
                 float* y, void* stream);
 
+/* Same contract on the tcgen05 tensor cores (conv_umma.cu): TMA-staged
+ * 128-pixel x 32-channel tiles, tcgen05.mma kind::tf32 with a 3-term hi/lo
+ * split (fp32-level accuracy), accumulator in TMEM.  Requires cin % 32 == 0;
+ * weights are passed TRANSPOSED and pre-split: wt_hi / wt_lo [cout, K]
+ * (K-major, K = taps*cin tap-major), wt_hi = w with the low 13 mantissa bits
+ * cleared, wt_lo = w - wt_hi.  pw_conv_umma_supported() returns 1 when this
+ * descriptor can run on that path. */
+int pw_conv_umma_supported(const pw_conv_desc* desc);
+int pw_conv_umma_fwd(const pw_conv_desc* desc, const float* x,
+                     const float* wt_hi, const float* wt_lo, const float* scale,
+                     const float* bias, const float* residual, float* y,
+                     void* stream);
+
 /* ------------------------------------------------------------------------
  * Image-side element-wise helpers (all channels-last).
  * ---------------------------------------------------------------------- */

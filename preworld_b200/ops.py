@@ -75,7 +75,7 @@ class PackedConv:
     """Weights of one conv/linear in the kernel's layout: w [K, w_ld] with
     K = taps*cin_pad (tap-major), plus the folded per-channel affine."""
     __slots__ = ('w', 'scale', 'bias', 'cin', 'cout', 'k', 'stride', 'pad',
-                 'dil', 'w_ld')
+                 'dil', 'w_ld', 'wt_hi', 'wt_lo')
 
     def __init__(self, weight, bias=None, bn=None, stride=1, padding=0,
                  dilation=1, in_scale=None, in_shift=None, eps=None,
@@ -107,6 +107,9 @@ class PackedConv:
         wk = torch.zeros(*k, cin_pad, w_ld, device=w.device)
         wk[..., :cin, :cout] = w.permute(2, 3, 4, 1, 0)
         self.w = wk.reshape(-1, w_ld).contiguous()
+        self.wt_hi = self.wt_lo = None
+        if cin % 32 == 0:
+            self.set_umma_weights(w.permute(0, 2, 3, 4, 1).reshape(cout, -1))
         if bn is not None:
             gamma, beta, mean, var, eps_ = bn
             s = gamma.detach().float() / torch.sqrt(var.detach().float() + eps_)
@@ -136,6 +139,20 @@ class PackedConv:
             self.dil = tuple(self.dil[p] for p in spatial_perm)
 
 
+    def set_umma_weights(self, wt):
+        """wt [cout, K] (K-major, tap-major then cin): pre-split for the
+        3xTF32 tensor-core path (pw_conv_umma_fwd)."""
+        wt = wt.contiguous().float()
+        hi = (wt.view(torch.int32) & -8192).view(torch.float32)   # 0xFFFFE000
+        self.wt_hi = hi.contiguous()
+        self.wt_lo = (wt - hi).contiguous()
+
+
+# The tensor-core path is used whenever the layer qualifies; set to False to
+# force the fp32 SIMT kernel (tests compare the two).
+USE_UMMA = True
+
+
 def conv(x, pc, act=None, residual=None, out=None, act_channels=0):
     """x: cl array [N,H,W,C] or [B,Z,Y,X,C] (C >= pc.cin, extra channels
     ignored only if equal to the packed cin).  Returns / fills a cl array with
@@ -163,6 +180,14 @@ def conv(x, pc, act=None, residual=None, out=None, act_channels=0):
                  act_channels=act_channels)
     if residual is not None:
         assert residual.shape == out.shape
+    L = _lib.lib()
+    if USE_UMMA and pc.wt_hi is not None and \
+            L.pw_conv_umma_supported(ctypes.byref(d)):
+        check(L.pw_conv_umma_fwd(ctypes.byref(d), _ptr(x), _ptr(pc.wt_hi),
+                                 _ptr(pc.wt_lo), _ptr(pc.scale), _ptr(pc.bias),
+                                 _ptr(residual), _ptr(out), _stream()),
+              'pw_conv_umma_fwd')
+        return out
     check(_lib.lib().pw_conv_fwd(ctypes.byref(d), _ptr(x), _ptr(pc.w),
                                  _ptr(pc.scale), _ptr(pc.bias),
                                  _ptr(residual), _ptr(out), _stream()),

@@ -51,6 +51,10 @@ class BasicBlock3D(nn.Module):
         f.cin, f.cout, f.k, f.w_ld = c1.cin, c1.cout + ds.cout, c1.k, \
             c1.cout + ds.cout
         f.stride, f.pad, f.dil = c1.stride, c1.pad, c1.dil
+        f.wt_hi = f.wt_lo = None
+        if c1.wt_hi is not None and ds.wt_hi is not None:
+            f.wt_hi = torch.cat([c1.wt_hi, ds.wt_hi], 0).contiguous()
+            f.wt_lo = torch.cat([c1.wt_lo, ds.wt_lo], 0).contiguous()
         assert f.w_ld % 4 == 0 and c1.cout % 4 == 0
         return dict(c1=f, c2=c2, fused=True, split=c1.cout)
 

@@ -41,9 +41,21 @@ CONV_CASES = [
 ]
 
 
+@pytest.fixture(params=['simt', 'umma'])
+def conv_path(request):
+    """Run a test on the fp32 SIMT kernel and on the tcgen05 3xTF32 kernel
+    (the latter is taken whenever cin % 32 == 0)."""
+    old = ops.USE_UMMA
+    ops.USE_UMMA = request.param == 'umma'
+    yield request.param
+    ops.USE_UMMA = old
+
+
 @pytest.mark.parametrize('case', CONV_CASES)
-def test_conv_matches_torch_fp32(case):
+def test_conv_matches_torch_fp32(case, conv_path):
     dims, n, cin, cout, sp, k, stride, pad, dil, bias, bn, act, res = case
+    if conv_path == 'umma' and cin % 32:
+        pytest.skip('tensor-core path needs cin % 32 == 0')
     g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
     x = torch.randn(n, cin, *sp, generator=g)
     w = torch.randn(cout, cin, *([k] * dims), generator=g) / (cin * k ** dims) ** .5
@@ -75,7 +87,7 @@ def test_conv_matches_torch_fp32(case):
     assert _rel(got, want) < 2e-5, _rel(got, want)
 
 
-def test_conv_channel_slices_and_split_activation():
+def test_conv_channel_slices_and_split_activation(conv_path):
     """Input / output / residual as channel slices of wider buffers, and the
     fused [relu | linear] double-branch launch used by BasicBlock3D."""
     g = torch.Generator().manual_seed(5)

@@ -1,0 +1,197 @@
+"""Host-side logic of the plugin surface (runs without a GPU): registry,
+config loading, state_dict contract, pose chain, frustum / geometry constants,
+weight packing, and that the product refuses to run without CUDA."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_ref
+from oracle.cases import CASES, build_case_inputs, model_cfg_for
+from preworld_b200 import (Config, ConfigDict, build_model, model_cfg, ops)
+from preworld_b200 import plugin
+from preworld_b200 import synthetic as S
+
+
+def test_registry_surface():
+    # one registry under five names (mmdet3d/models/builder.py:16-28)
+    assert plugin.BACKBONES is plugin.MODELS is plugin.NECKS is plugin.HEADS \
+        is plugin.DETECTORS
+    for name in ('ResNet', 'CustomFPN', 'LSSViewTransformerBEVStereo',
+                 'CustomResNet3D', 'LSSFPN3D', 'OccHead', 'NerfHead',
+                 'BEVStereo4DOCC', 'PreWorld', 'PreWorld4DTraj',
+                 'CrossEntropyLoss', 'CustomFocalLoss'):
+        assert name in plugin.MODELS, name
+    with pytest.raises(KeyError):
+        plugin.build_backbone(dict(type='SwinTransformer'))
+    with pytest.raises(TypeError):
+        plugin.build_neck(dict(out_channels=3))
+    m = plugin.build_neck(dict(type='LSSFPN3D', in_channels=224,
+                               out_channels=32))
+    assert sorted(m.state_dict())[0] == 'conv.bn.bias'
+
+
+def test_reference_config_files_load_unchanged(reference_root):
+    """configs/preworld/** parse with our loader and equal model_cfg()."""
+    def norm(o):
+        if isinstance(o, dict):
+            return {k: norm(v) for k, v in o.items()}
+        if isinstance(o, (list, tuple)):
+            return [norm(v) for v in o]
+        return o
+    files = {
+        'finetune': 'nuscenes/preworld-7frame-finetune.py',
+        'pretrain': 'nuscenes/preworld-7frame-pretrain.py',
+        'finetune-traj': 'nuscenes-temporal/preworld-7frame-finetune-traj.py',
+        'pretrain-traj': 'nuscenes-temporal/preworld-7frame-pretrain-traj.py'}
+    for variant, f in files.items():
+        cfg = Config.fromfile(os.path.join(reference_root, 'configs',
+                                           'preworld', f))
+        assert norm(cfg['model']) == norm(model_cfg(variant, 'swin')), variant
+        assert cfg.model.type in plugin.DETECTORS
+
+
+@pytest.mark.parametrize('variant', ['finetune', 'pretrain', 'finetune-traj'])
+def test_state_dict_keys_equal_the_reference(variant, reference_root):
+    """Reference checkpoints must load by key: same keys, same shapes."""
+    import warnings
+    warnings.filterwarnings('ignore')
+    from oracle import ref_shim
+    builder = ref_shim.load_all()
+    cfg = model_cfg(variant, 'r50', (64, 176))
+    ref = builder.build_model(ConfigDict(cfg)).state_dict()
+    mine = build_model(cfg).state_dict()
+    assert set(mine) == set(ref)
+    assert all(mine[k].shape == ref[k].shape for k in ref)
+    # and a reference state_dict loads strictly
+    build_model(cfg).load_state_dict(ref, strict=True)
+
+
+def test_key_addressed_init_is_construction_order_independent():
+    cfg = model_cfg('finetune', 'r50', (64, 176))
+    a = S.lively_init_(build_model(cfg), 3).state_dict()
+    b = S.lively_init_(build_model(cfg), 3).state_dict()
+    c = S.lively_init_(build_model(cfg), 4).state_dict()
+    k = 'img_bev_encoder_backbone.layers.1.0.conv1.conv.weight'
+    assert torch.equal(a[k], b[k]) and not torch.equal(a[k], c[k])
+
+
+def test_prepare_inputs_matches_oracle():
+    """bevdet_occ.py:88-139 -- fp64 pose chain, frame split."""
+    case = CASES['tiny_finetune']
+    model = build_model(model_cfg_for(case)).eval()
+    inputs, _ = build_case_inputs(case, batch=2)
+    got = model.prepare_inputs(inputs, stereo=True)
+    want = torch_ref.prepare_inputs(inputs)
+    assert len(got) == len(want) == 8
+    for g, w in zip(got, want):
+        if isinstance(w, list):
+            assert len(g) == len(w)
+            for gi, wi in zip(g, w):
+                assert (gi is None) == (wi is None)
+                if wi is not None:
+                    assert torch.equal(gi, wi)
+        else:
+            assert torch.equal(g, w)
+    assert got[7][-1] is None and len(got[0]) == 3
+
+
+def test_view_transformer_constants_match_oracle():
+    case = CASES['full_finetune']
+    cfg = model_cfg_for(case)
+    vt = plugin.build_neck(cfg['img_view_transformer'])
+    geo = torch_ref.LiftGeometry(cfg['img_view_transformer']['grid_config'],
+                                 (256, 704), 16, 32)
+    assert vt.D == geo.D == 88
+    assert torch.equal(vt.frustum, geo.frustum)
+    assert torch.equal(vt.cv_frustum, geo.cv_frustum)
+    assert torch.equal(vt.grid_lower_bound, geo.lower)
+    assert torch.equal(vt.grid_interval, geo.interval)
+    assert [int(v) for v in vt.grid_size] == [200, 200, 16]
+    inputs, _ = build_case_inputs(case)
+    pi = torch_ref.prepare_inputs(inputs)
+    got = vt.get_mlp_input(pi[1][0], pi[2][0], pi[3][0], pi[4][0], pi[5][0],
+                           pi[6])
+    want = torch_ref.get_mlp_input(pi[1][0], pi[3][0], pi[4][0], pi[5][0],
+                                   pi[6])
+    assert got.shape == (1, 6, 27) and torch.equal(got, want)
+
+
+def test_nerf_head_buffers_and_ray_parameters():
+    from preworld_b200.plugin.heads import NerfHead
+    h = NerfHead([-40., -40., -1., 40., 40., 5.4], 0.4, scene_center=[0, 0, 2.2])
+    ng = torch_ref.NerfGeometry([-40., -40., -1., 40., 40., 5.4])
+    assert torch.equal(h.scene_center, ng.scene_center)
+    assert torch.equal(h.xyz_min, ng.xyz_min) and torch.equal(h.xyz_max, ng.xyz_max)
+    assert abs(float(h.act_shift) - ng.act_shift) < 1e-7
+    t = h.ray_parameters(torch.device('cpu'))
+    assert t.numel() == 417                       # 391 inner + 26 outer
+    rays = torch.zeros(4, 16)
+    rays[:, 7] = 1.0
+    _, _, t_ref = torch_ref.sample_ray(ng, rays[:, 4:7], rays[:, 7:10],
+                                       torch.eye(3))
+    assert torch.equal(t, t_ref)
+
+
+def test_weight_packing():
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(18, 8, 1, 1, 1, generator=g)
+    pc = ops.PackedConv(w)
+    assert pc.w.shape == (8, 20) and pc.cout == 18 and pc.wt_hi is None
+    assert torch.equal(pc.w[:, :18], w[:, :, 0, 0, 0].t())
+    assert (pc.w[:, 18:] == 0).all()
+    w = torch.randn(16, 32, 3, 3, 3, generator=g)
+    gamma, beta = torch.rand(16, generator=g) + .5, torch.randn(16, generator=g)
+    mean, var = torch.randn(16, generator=g), torch.rand(16, generator=g) + .5
+    pc = ops.PackedConv(w, None, (gamma, beta, mean, var, 1e-5), padding=1)
+    assert pc.w.shape == (27 * 32, 16) and pc.pad == (1, 1, 1)
+    s = gamma / torch.sqrt(var + 1e-5)
+    assert torch.allclose(pc.scale, s) and torch.allclose(pc.bias, beta - mean * s)
+    # tap-major then cin; tensor-core copy is the transpose, split hi + lo
+    assert torch.equal(pc.w[(1 * 9 + 2 * 3 + 0) * 32 + 5], w[:, 5, 1, 2, 0])
+    assert pc.wt_hi.shape == (16, 27 * 32)
+    assert torch.equal(pc.wt_hi + pc.wt_lo, pc.w.t())
+    assert (pc.wt_hi.view(torch.int32) & 0x1FFF == 0).all()
+    assert (pc.wt_lo.abs() <= pc.wt_hi.abs() * 2 ** -10 + 1e-30).all()
+    # spatial permutation used by OccHead on [Z,Y,X] memory
+    pr = ops.PackedConv(w, padding=1, spatial_perm=(2, 1, 0))
+    assert torch.equal(pr.w[(0 * 9 + 2 * 3 + 1) * 32 + 5], w[:, 5, 1, 2, 0])
+    # 2-D conv: depth stride/pad neutral; BN1d folded into a linear
+    p2 = ops.PackedConv(torch.randn(8, 4, 3, 3, generator=g), stride=2,
+                        padding=1, dilation=1)
+    assert p2.k == (1, 3, 3) and p2.stride == (1, 2, 2) and p2.pad == (0, 1, 1)
+    lw, lb = torch.randn(6, 27, generator=g), torch.randn(6, generator=g)
+    sc, sh = torch.rand(27, generator=g), torch.randn(27, generator=g)
+    pl = ops.PackedConv(lw, lb, in_scale=sc, in_shift=sh)
+    x = torch.randn(5, 27, generator=g)
+    want = torch.nn.functional.linear(x * sc + sh, lw, lb)
+    got = torch.nn.functional.pad(x, (0, 1)) @ pl.w[:, :6] + pl.bias
+    assert torch.allclose(got, want, atol=1e-5)
+
+
+def test_cl_layout_helpers():
+    x = torch.zeros(2, 5, 7, 16)
+    assert ops.cl_ld(x) == 16 and ops.cl_ld(x[..., 4:12]) == 16
+    assert ops.cl_ld(x[:, :, :, None, :].squeeze(3)[:, None][:, 0]) == 16
+    assert ops.cl_ld(torch.zeros(10, 24)[:, None, 2:19]) == 24
+    with pytest.raises(ValueError):
+        ops.cl_ld(x[:, ::2])
+    lg = ops.to_logical(x)
+    assert lg.shape == (2, 16, 5, 7) and ops.from_logical(lg).shape == x.shape
+    with pytest.raises(ValueError):
+        ops.from_logical(torch.zeros(2, 16, 5, 7))      # NCHW-contiguous
+
+
+def test_no_cpu_fallback():
+    """The product path fails loudly without CUDA tensors / in train mode."""
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.conv(torch.zeros(1, 4, 4, 32), ops.PackedConv(torch.zeros(8, 32)))
+    m = plugin.build_neck(dict(type='LSSFPN3D', in_channels=224,
+                               out_channels=32))
+    m.train()
+    with pytest.raises(RuntimeError, match='forward-only'):
+        m.packs()
+    det = build_model(model_cfg('finetune', 'r50', (64, 176)))
+    with pytest.raises(NotImplementedError):
+        det(return_loss=True)
