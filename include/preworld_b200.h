@@ -78,6 +78,18 @@ int pw_conv_umma_fwd(const pw_conv_desc* desc, const float* x,
                      const float* bias, const float* residual, float* y,
                      void* stream);
 
+/* Second-generation tensor-core conv (conv_halo.cu), same contract and weight
+ * format as pw_conv_umma_fwd: the CTA's input box incl. halo is TMA-loaded once
+ * per 32-channel chunk, the A operand is split to tf32 hi/lo in registers and
+ * fed to tcgen05.mma from TENSOR MEMORY, hi|lo weights form one 2N-wide MMA.
+ * pw_conv_halo_supported() returns 1 when the halo box fits shared memory
+ * (all stride-1 convs of the path; 1x1 convs are flattened to a GEMM). */
+int pw_conv_halo_supported(const pw_conv_desc* desc);
+int pw_conv_halo_fwd(const pw_conv_desc* desc, const float* x,
+                     const float* wt_hi, const float* wt_lo, const float* scale,
+                     const float* bias, const float* residual, float* y,
+                     void* stream);
+
 /* ------------------------------------------------------------------------
  * Image-side element-wise helpers (all channels-last).
  * ---------------------------------------------------------------------- */

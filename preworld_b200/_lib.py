@@ -46,6 +46,9 @@ SIGNATURES = {
     'pw_conv_umma_supported': [ctypes.POINTER(ConvDesc)],
     'pw_conv_umma_fwd': [ctypes.POINTER(ConvDesc), c_p, c_p, c_p, c_p, c_p,
                          c_p, c_p, c_p],
+    'pw_conv_halo_supported': [ctypes.POINTER(ConvDesc)],
+    'pw_conv_halo_fwd': [ctypes.POINTER(ConvDesc), c_p, c_p, c_p, c_p, c_p,
+                         c_p, c_p, c_p],
     'pw_nchw_to_nhwc_pad': [c_p, c_ll, c_p, c_int, c_int, c_int, c_int, c_int,
                             c_p],
     'pw_nhwc_to_nchw': [c_p, c_int, c_p, c_int, c_int, c_ll, c_p],

@@ -1,0 +1,653 @@
+// Halo-resident tcgen05 implicit-GEMM convolution (channels-last fp32 in/out,
+// 3xTF32 split for fp32-level accuracy) -- the second-generation tensor-core
+// conv of this library.  Differences from conv_umma.cu, each aimed at the
+// shared-memory / L2 bandwidth wall that kernel hits on the 3-D encoder
+// (Cout 32..64, 27 taps):
+//   * the input box of the CTA *including its halo* is loaded ONCE per
+//     32-channel chunk (one 5-D TMA, padding = TMA zero fill) instead of once
+//     per tap: 27x -> ~2.3x L2->smem traffic for a 3x3x3 conv;
+//   * the A operand is fed to the tensor core from TENSOR MEMORY: the split
+//     warps read their pixel row of the shifted view straight out of the halo
+//     tile, split it into tf32 hi/lo in registers and tcgen05.st it -- no
+//     shared-memory write-back, and the MMA reads no A bytes from smem;
+//   * hi and lo weights sit back to back in smem, so  Ah*[Bh;Bl]  is ONE MMA
+//     of width 2N (main | correction accumulator side by side in TMEM) and
+//     Al*Bh a second one: 2 instructions per k-step instead of 3;
+//   * a CTA owns up to two 128-pixel M tiles that share every weight stage;
+//   * the epilogue transposes through (swizzled) smem so that global stores
+//     and residual loads are full 128-byte rows.
+//
+// Warp roles: 0 halo TMA, 1 weight TMA, 2 MMA issue + TMEM owner, 3..10 two
+// sets of four split/epilogue warps (warp%4 = TMEM lane quadrant).
+//
+// Replaces the cuDNN convolutions of the reference path (mmdet ResNet,
+// necks/fpn.py, necks/view_transformer.py:473-638, backbones/resnet.py:88-184,
+// necks/lss_fpn.py:120-148, detectors/preworld.py:72-105,
+// heads/occupancy_head.py:81-177).
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "../../include/preworld_b200.h"
+
+namespace {
+
+using namespace pwtc;
+
+constexpr int BLOCK_K = 32;                  // floats = one 128-byte swizzle row
+constexpr int ROW_BYTES = 128;
+constexpr int SPLIT_SETS = 2;
+constexpr int FIRST_SPLIT_WARP = 3;
+constexpr int NUM_WARPS = FIRST_SPLIT_WARP + 4 * SPLIT_SETS;
+constexpr int NUM_THREADS = NUM_WARPS * 32;  // 352
+constexpr int A_SLOT_COLS = 2 * BLOCK_K;     // hi | lo
+constexpr int STAGE_BYTES_PER_WARP = 32 * ROW_BYTES;
+constexpr int MAX_RING = 8;
+
+struct HaloParams {
+  int od, oh, ow, cout;
+  int kh, kw, n_taps, chunks;
+  int sd, sh, sw, pd, ph, pw, dd, dh, dw;
+  int lbx, lby;                // log2 of the M-tile box (bx * by * bz == 128)
+  int bx, by, bz;
+  int mt, mt_axis;             // M tiles per CTA, stacked along axis 0:x 1:y 2:z
+  int cbx, cby, cbz;           // CTA output box
+  int hx, hy, hz;              // halo box (input pixels)
+  int mt_halo_off;             // halo-row offset of M tile 1
+  int halo_stride;             // bytes per halo slot (multiple of 1024)
+  int halo_region;             // bytes reserved for the halo ring (>= staging)
+  int tiles_x, tiles_y, tiles_z;
+  int n_tile;
+  int nh, nb;                  // ring depths: halo slots; (weight stage + A slots) entries
+  int nacc;                    // accumulator copies per M tile (k-step k -> copy k % nacc):
+                               // independent MMA chains hide the accumulate latency at small N
+  int tmem_cols;
+  int dbg;                     // PW_HALO_DBG knock-out bits (timing experiments only)
+  long long* ts;               // PW_HALO_TS: per-CTA clock64 milestones (debug)
+  int out_ld, res_ld, act, act_channels;
+  const float* scale;
+  const float* bias;
+  const float* res;
+  float* y;
+};
+
+#define PW_TS(k) do { if (p.ts) p.ts[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (k)] = clock64(); } while (0)
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
+                 const __grid_constant__ CUtensorMap map_bh,
+                 const __grid_constant__ CUtensorMap map_bl, const HaloParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int b_stage = 2 * p.n_tile * ROW_BYTES;
+  uint8_t* b_ring = smem + p.halo_region;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.nb * b_stage);
+  // bars: halo_full[nh] halo_empty[nh] b_full[nb] empty[nb] a_full[nb*mt] accum
+  // Ring entry r = (chunk,tap) % nb owns weight stage r and A slots r*mt + m; ONE
+  // tcgen05.commit per entry frees both (a commit costs ~400 issue cycles).
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t halo_full = bar0, halo_empty = halo_full + 8 * p.nh;
+  const uint32_t b_full = halo_empty + 8 * p.nh, ring_empty = b_full + 8 * p.nb;
+  const uint32_t a_full = ring_empty + 8 * p.nb;
+  const uint32_t accum_bar = a_full + 8 * p.nb * p.mt;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * p.nh + p.nb * (2 + p.mt) + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) PW_TS(0);
+
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nh; ++s) {
+      mbar_init(halo_full + 8 * s, 1);
+      mbar_init(halo_empty + 8 * s, 4 * SPLIT_SETS);     // one arrive per split warp
+    }
+    for (int s = 0; s < p.nb; ++s) {
+      mbar_init(b_full + 8 * s, 1);
+      mbar_init(ring_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < p.nb * p.mt; ++s) mbar_init(a_full + 8 * s, 4);   // four warps of a set
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_holder), (uint32_t)p.tmem_cols);
+  if (warp == 0 && lane == 0) prefetch_tensormap(&map_a);
+  if (warp == 1 && lane == 0) { prefetch_tensormap(&map_bh); prefetch_tensormap(&map_bl); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  if (threadIdx.x == 0) PW_TS(1);
+  const int tile_cols = p.nacc * 2 * p.n_tile;          // TMEM columns of one M tile's accumulators
+  const uint32_t a_ring_col = (uint32_t)(p.mt * tile_cols);
+
+  // ---- tile coordinates ------------------------------------------------------
+  int tt = blockIdx.x;
+  const int tx = tt % p.tiles_x; tt /= p.tiles_x;
+  const int ty = tt % p.tiles_y; tt /= p.tiles_y;
+  const int tz = tt % p.tiles_z;
+  const int img = tt / p.tiles_z;
+  const int x0 = tx * p.cbx, y0 = ty * p.cby, z0 = tz * p.cbz;
+  const int n0 = blockIdx.y * p.n_tile;
+  const int T = p.n_taps;
+  const int total_ct = p.chunks * T;            // (chunk, tap) pairs
+
+  // Warps 0..2 run their loops warp-CONVERGED; only the TMA / MMA / commit
+  // instruction itself is issued by one elected lane.  (A whole loop under
+  // `if (lane == 0)` makes every uniform-register operand a waterfall loop:
+  // measured ~65 issue cycles per tcgen05.mma.)
+  if (warp == 0) {
+    // ===================== halo producer ======================================
+    const bool leader = elect_one();
+    const uint32_t bytes = (uint32_t)(p.hx * p.hy * p.hz) * ROW_BYTES;
+    const int cx = x0 * p.sw - p.pw, cy = y0 * p.sh - p.ph, cz = z0 * p.sd - p.pd;
+    int s = 0;
+    uint32_t ph = 1;
+    for (int c = 0; c < p.chunks; ++c) {
+      mbar_wait(halo_empty + 8 * s, ph);
+      if (leader) {
+        mbar_expect_tx(halo_full + 8 * s, bytes);
+        tma_load_5d(smem_u32(smem + (size_t)s * p.halo_stride), &map_a, halo_full + 8 * s,
+                    c * BLOCK_K, cx, cy, cz, img);
+      }
+      __syncwarp();
+      if (++s == p.nh) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ===================== weight producer ====================================
+    const bool leader = elect_one();
+    const uint32_t b_ring_u32 = smem_u32(b_ring);
+    int s = 0;
+    uint32_t ph = 1;
+    for (int c = 0; c < p.chunks; ++c) {
+      for (int t = 0; t < T; ++t) {
+        mbar_wait(ring_empty + 8 * s, ph);
+        if (leader) {
+          mbar_expect_tx(b_full + 8 * s, (uint32_t)b_stage);
+          const uint32_t dst = b_ring_u32 + (uint32_t)(s * b_stage);
+          const int k0 = (t * p.chunks + c) * BLOCK_K;   // weights are tap-major in K
+          tma_load_2d(dst, &map_bh, b_full + 8 * s, k0, n0);
+          tma_load_2d(dst + p.n_tile * ROW_BYTES, &map_bl, b_full + 8 * s, k0, n0);
+        }
+        __syncwarp();
+        if (++s == p.nb) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== MMA issuer ==========================================
+    const bool leader = elect_one();
+    const uint32_t idesc_2n = umma_idesc_tf32_m128(2 * p.n_tile);
+    const uint32_t idesc_n = umma_idesc_tf32_m128(p.n_tile);
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t desc0 = umma_desc_sw128(smem_u32(b_ring));
+    const uint32_t desc_stage = (uint32_t)(b_stage >> 4);      // descriptor address units
+    const uint32_t acc_stride = (uint32_t)(2 * p.n_tile);
+    int r = 0;
+    uint32_t ph = 0;
+    uint32_t accumulate = 0;                                   // first k-steps overwrite
+    for (int ct = 0; ct < total_ct; ++ct) {
+      mbar_wait(b_full + 8 * r, ph);
+      const uint64_t bdesc = desc0 + (uint64_t)(desc_stage * (uint32_t)r);
+      for (int m = 0; m < p.mt; ++m) {
+        mbar_wait(a_full + 8 * (r * p.mt + m), ph);
+        tc_fence_after();
+        const uint32_t a_hi = tbase + a_ring_col + (uint32_t)((r * p.mt + m) * A_SLOT_COLS);
+        const uint32_t acc = tbase + (uint32_t)(m * tile_cols);
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 8; ++k) {
+            const uint64_t bd = bdesc + (uint64_t)(k * 2);     // +32 bytes inside the swizzle row
+            const uint32_t acc_k = acc + (uint32_t)(k & (p.nacc - 1)) * acc_stride;
+            // [main | corr] (+)= Ah * [Bh ; Bl]
+            umma_tf32_ts(acc_k, a_hi + k * 8, bd, idesc_2n,
+                         (k < p.nacc) ? accumulate : 1u);
+            // corr += Al * Bh
+            umma_tf32_ts(acc_k + p.n_tile, a_hi + BLOCK_K + k * 8, bd, idesc_n, 1u);
+          }
+        }
+        __syncwarp();
+      }
+      accumulate = 1;
+      if (leader) umma_commit(ring_empty + 8 * r);   // weight stage + A slots free on retire
+      __syncwarp();
+      if (++r == p.nb) { r = 0; ph ^= 1; }
+    }
+    if (leader) umma_commit(accum_bar);
+    __syncwarp();
+  } else {
+    // ===================== split warps, then epilogue ==========================
+    const int sw_id = warp - FIRST_SPLIT_WARP;
+    const int set = sw_id >> 2;
+    const int q = warp & 3;                              // TMEM lane quadrant of this warp
+    const uint32_t lane_field = (uint32_t)(q * 32) << 16;
+    const int R = q * 32 + lane;                         // row of the M tile
+    const int rx = R & (p.bx - 1);
+    const int ry = (R >> p.lbx) & (p.by - 1);
+    const int rz = R >> (p.lbx + p.lby);
+    const int row_base = ((rz * p.sd) * p.hy + ry * p.sh) * p.hx + rx * p.sw;
+    const uint32_t a_ring = tmem_base + lane_field + a_ring_col;
+
+    // Iteration state, advanced incrementally (no divisions in the loop):
+    // it = (c*T + t)*mt + m; this set takes it = set, set+SETS, ...
+    struct It { int c, kx, ky, kz, m, r, hs; uint32_t eph, hph; };
+    auto advance = [&](It& s, int steps) {
+      for (int i = 0; i < steps; ++i) {
+        if (++s.m < p.mt) continue;
+        s.m = 0;
+        if (++s.r == p.nb) { s.r = 0; s.eph ^= 1; }
+        if (++s.kx < p.kw) continue;
+        s.kx = 0;
+        if (++s.ky < p.kh) continue;
+        s.ky = 0;
+        if (++s.kz * p.kh * p.kw < T) continue;
+        s.kz = 0;
+        ++s.c;
+        if (++s.hs == p.nh) { s.hs = 0; s.hph ^= 1; }
+      }
+    };
+    auto load_row = [&](const It& s, float4 (&raw)[8]) {
+      const int hrow = row_base + s.m * p.mt_halo_off +
+                       ((s.kz * p.dd) * p.hy + s.ky * p.dh) * p.hx + s.kx * p.dw;
+      const uint8_t* src = smem + (size_t)s.hs * p.halo_stride + (size_t)hrow * ROW_BYTES;
+      const int swz = hrow & 7;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        raw[j] = *reinterpret_cast<const float4*>(src + ((j ^ swz) << 4));
+    };
+
+    It cur{0, 0, 0, 0, 0, 0, 0, 1u, 0u};               // eph = parity to wait on ring_empty
+    advance(cur, set);
+    int released = 0;                                    // halo chunks this warp has released
+    float4 raw[8];
+    if (cur.c < p.chunks) {
+      mbar_wait(halo_full + 8 * cur.hs, cur.hph);
+      if (sw_id == 0 && lane == 0) PW_TS(3);
+      load_row(cur, raw);
+    }
+    bool first_it = true;
+    while (cur.c < p.chunks) {
+      const int slot = cur.r * p.mt + cur.m;
+      const uint32_t a_col = a_ring + (uint32_t)(slot * A_SLOT_COLS);
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = raw[half * 4 + j];
+          const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;
+            hi[j * 4 + e] = h;
+            lo[j * 4 + e] = __float_as_uint(f[e] - __uint_as_float(h));
+          }
+        }
+        if (half == 0) {
+          mbar_wait(ring_empty + 8 * cur.r, cur.eph);    // MMAs reading this slot retired
+          tc_fence_after();
+        }
+        tmem_st16(a_col + half * 16, hi);
+        tmem_st16(a_col + BLOCK_K + half * 16, lo);
+      }
+      // raw[] is consumed: prefetch the next row of this set while the stores drain
+      It nxt = cur;
+      advance(nxt, SPLIT_SETS);
+      const int upto = nxt.c < p.chunks ? nxt.c : p.chunks;
+      while (released < upto) {                          // chunks this warp is done reading
+        __syncwarp();
+        if (lane == 0) mbar_arrive(halo_empty + 8 * (released % p.nh));
+        ++released;
+      }
+      if (nxt.c < p.chunks) {
+        mbar_wait(halo_full + 8 * nxt.hs, nxt.hph);
+        load_row(nxt, raw);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full + 8 * slot);
+      if (first_it && sw_id == 0 && lane == 0) PW_TS(4);
+      first_it = false;
+      cur = nxt;
+    }
+    while (released < p.chunks) {                        // a set with no work in the last chunks
+      __syncwarp();
+      if (lane == 0) mbar_arrive(halo_empty + 8 * (released % p.nh));
+      ++released;
+    }
+
+    // ---- epilogue: TMEM -> regs (main + corr, affine) -> swizzled smem ->
+    //      coalesced residual / activation / store ----------------------------
+    if (sw_id == 0 && lane == 0) PW_TS(11);
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    if (sw_id == 0 && lane == 0) PW_TS(7);
+    float4* stage = reinterpret_cast<float4*>(smem + (size_t)sw_id * STAGE_BYTES_PER_WARP);
+    const int ncg = (p.n_tile + 31) >> 5;
+    const int items = p.mt * ncg;
+    const int act_end = p.act_channels > 0 ? p.act_channels : p.cout;
+    const bool vec_ok = ((p.out_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
+                        (p.res == nullptr || ((p.res_ld & 3) == 0 &&
+                                              (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
+    for (int item = set; item < items; item += SPLIT_SETS) {
+      const int m = item / ncg;
+      const int col0 = (item - m * ncg) * 32;
+      const int ncol = min(32, p.n_tile - col0);         // 16 or 32 (warp-uniform)
+      float acc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+      for (int copy = 0; copy < p.nacc; ++copy) {
+        uint32_t a[32], b[32];
+        const uint32_t taddr = tmem_base + lane_field +
+                               (uint32_t)(m * tile_cols + copy * 2 * p.n_tile + col0);
+        tmem_ld16_nowait(taddr, a);
+        tmem_ld16_nowait(taddr + p.n_tile, b);
+        if (ncol > 16) {
+          tmem_ld16_nowait(taddr + 16, a + 16);
+          tmem_ld16_nowait(taddr + p.n_tile + 16, b + 16);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < 16 || ncol > 16) acc[j] += __uint_as_float(a[j]) + __uint_as_float(b[j]);
+      }
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        if (j4 * 4 < ncol) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = j4 * 4 + e;
+            const int ch = n0 + col0 + j;
+            float x = acc[j];
+            if (ch < p.cout) {
+              const float sc = p.scale ? __ldg(p.scale + ch) : 1.f;
+              const float bi = p.bias ? __ldg(p.bias + ch) : 0.f;
+              x = fmaf(x, sc, bi);
+            }
+            v[e] = x;
+          }
+          stage[lane * 8 + (j4 ^ (lane & 7))] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+      __syncwarp();
+      const int ch4 = lane & 7;
+      const int cbase = n0 + col0 + ch4 * 4;
+      if (ch4 * 4 < ncol && cbase < p.cout) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3);
+          const int Rr = q * 32 + r;
+          int ox = x0 + (Rr & (p.bx - 1));
+          int oy = y0 + ((Rr >> p.lbx) & (p.by - 1));
+          int oz = z0 + (Rr >> (p.lbx + p.lby));
+          if (p.mt_axis == 0) ox += m * p.bx;
+          else if (p.mt_axis == 1) oy += m * p.by;
+          else oz += m * p.bz;
+          if (ox >= p.ow || oy >= p.oh || oz >= p.od) continue;
+          const float4 v4 = stage[r * 8 + (ch4 ^ (r & 7))];
+          float v[4] = {v4.x, v4.y, v4.z, v4.w};
+          const size_t pix = (((size_t)img * p.od + oz) * p.oh + oy) * p.ow + ox;
+          float* yrow = p.y + pix * p.out_ld + cbase;
+          const float* rrow = p.res ? p.res + pix * p.res_ld + cbase : nullptr;
+          const int a_ = (cbase < act_end) ? p.act : PW_ACT_NONE;   // act_end % 4 == 0
+          if (vec_ok && cbase + 4 <= p.cout) {
+            if (rrow) {
+              const float4 rr = pw_ldg4(rrow);
+              v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+            }
+            *reinterpret_cast<float4*>(yrow) =
+                make_float4(pw_activate(v[0], a_), pw_activate(v[1], a_),
+                            pw_activate(v[2], a_), pw_activate(v[3], a_));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (cbase + e < p.cout) {
+                float tv = v[e];
+                if (rrow) tv += __ldg(rrow + e);
+                yrow[e] = pw_activate(tv, a_);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  if (warp == FIRST_SPLIT_WARP && lane == 0) PW_TS(8);
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) PW_TS(9);
+  if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---- host side -----------------------------------------------------------------
+inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int SMEM_SLACK = 1024 /*align*/ + (6 * MAX_RING + 1) * 8 + 16;   // barriers: 2nh + nb(2+mt) + 1
+
+struct HaloPlan {
+  bool ok = false;
+  pw_conv_desc c;              // possibly flattened (1x1 convs)
+  HaloParams p;
+  size_t smem = 0;
+  dim3 grid;
+};
+
+// Picks box / M-tile count / ring depths with a small cycle model:
+// waves * (per-CTA mainloop + halo load).
+HaloPlan make_plan(const pw_conv_desc& in) {
+  HaloPlan plan;
+  pw_conv_desc c = in;
+  if (c.cin % BLOCK_K != 0 || c.in_ld % 4 != 0 || c.cout < 1) return plan;
+  if (c.n < 1 || c.od < 1 || c.oh < 1 || c.ow < 1) return plan;
+  const bool pointwise = c.kd == 1 && c.kh == 1 && c.kw == 1 && c.sd == 1 && c.sh == 1 &&
+                         c.sw == 1 && c.pd == 0 && c.ph == 0 && c.pw == 0;
+  if (pointwise) {
+    // a 1x1 conv is a plain [pixels, cin] x [cin, cout] GEMM: flatten to one row
+    const long long px = (long long)c.n * c.d * c.h * c.w;
+    if (px >= (1ll << 31)) return plan;
+    c.w = c.ow = (int)px;
+    c.n = c.d = c.h = c.od = c.oh = 1;
+  }
+  const int chunks = c.cin / BLOCK_K;
+  const int T = c.kd * c.kh * c.kw;
+  static const int boxes3[][3] = {{8, 4, 4}, {8, 8, 2}, {16, 4, 2}, {16, 8, 1}, {8, 16, 1},
+                                  {32, 4, 1}, {16, 2, 4}, {32, 2, 2}, {8, 2, 8}};
+  static const int boxes2[][3] = {{16, 8, 1}, {8, 16, 1}, {32, 4, 1}, {64, 2, 1}, {128, 1, 1}};
+  static const int boxes1[][3] = {{128, 1, 1}};
+  const int (*boxes)[3] = pointwise ? boxes1 : (c.od > 1 ? boxes3 : boxes2);
+  const int nboxes = pointwise ? 1 : (c.od > 1 ? 9 : 5);
+  const int n_full = min(round_up(c.cout, 16), 128);
+
+  double best = -1;
+  for (int ntry = 0; ntry < 3; ++ntry) {
+    const int n_tile = ntry == 0 ? n_full : (ntry == 1 ? 64 : 32);
+    if (ntry > 0 && n_tile >= n_full) continue;
+    const int slabs = pw_ceil_div(c.cout, n_tile);
+    const int b_stage = 2 * n_tile * ROW_BYTES;
+    for (int bi = 0; bi < nboxes; ++bi) {
+      for (int mt = 1; mt <= 2; ++mt) {
+        for (int axis = 0; axis < (mt == 1 ? 1 : 3); ++axis) {
+          int b[3] = {boxes[bi][0], boxes[bi][1], boxes[bi][2]};
+          int cb[3] = {b[0], b[1], b[2]};
+          if (mt == 2) cb[axis] *= 2;
+          if (pointwise && axis != 0) continue;
+          const int ext[3] = {c.ow, c.oh, c.od};
+          if (mt == 2 && ext[axis] <= b[axis]) continue;       // second tile would be empty
+          const int st[3] = {c.sw, c.sh, c.sd}, dl[3] = {c.dw, c.dh, c.dd};
+          const int kk[3] = {c.kw, c.kh, c.kd};
+          int h[3];
+          bool fit = true;
+          for (int a = 0; a < 3; ++a) {
+            h[a] = (cb[a] - 1) * st[a] + (kk[a] - 1) * dl[a] + 1;
+            if (h[a] > 256) fit = false;
+          }
+          if (!fit) continue;
+          const int hrows = h[0] * h[1] * h[2];
+          const int halo_stride = round_up(hrows * ROW_BYTES, 1024);
+          // TMEM: accumulators (mt * nacc * 2n) + A ring (nb * mt * 64 columns)
+          int nacc = 1;
+          if (const char* e = getenv("PW_HALO_NACC")) nacc = atoi(e) == 2 ? 2 : 1;
+          if (mt * nacc * 2 * n_tile + 2 * mt * A_SLOT_COLS > 512) nacc = 1;
+          const int acc_cols = mt * nacc * 2 * n_tile;
+          int nb = min(T * chunks, min(4, (512 - acc_cols) / (mt * A_SLOT_COLS)));
+          if (const char* e = getenv("PW_HALO_NB")) nb = min(nb, max(1, atoi(e)));
+          if (nb < 1 || (nb < 2 && T * chunks > 1)) continue;
+          if (const char* e = getenv("PW_HALO_MT")) { if (atoi(e) != mt) continue; }
+          // halo ring
+          int nh = min(chunks, 2);
+          auto smem_need = [&](int nh_, int nb_) {
+            return (long long)max(nh_ * halo_stride, 8 * STAGE_BYTES_PER_WARP) +
+                   (long long)nb_ * b_stage + SMEM_SLACK;
+          };
+          while (nb > 2 && smem_need(nh, nb) > SMEM_LIMIT) --nb;
+          // a multi-chunk conv needs two halo slots (load of chunk c+1 under the
+          // taps of chunk c); if that does not fit, conv_umma.cu takes the layer
+          if (smem_need(nh, nb) > SMEM_LIMIT) continue;
+          while (nh < min(chunks, MAX_RING) && nh * halo_stride < 64 * 1024 &&
+                 smem_need(nh + 1, nb) <= SMEM_LIMIT)
+            ++nh;
+          const long long tiles = (long long)pw_ceil_div(c.ow, cb[0]) * pw_ceil_div(c.oh, cb[1]) *
+                                  pw_ceil_div(c.od, cb[2]) * c.n * slabs;
+          if (tiles > 0x7fffffffLL) continue;
+          // cycle model
+          // measured: ~430 cycles per tcgen05.commit, >= ~50 per MMA
+          const double kstep = 1.5 * n_tile > 100.0 ? 1.5 * n_tile : 100.0;
+          const double per_ct = 430.0 + mt * 4.0 * kstep;
+          double cta = chunks * (T * per_ct + (nh > 1 ? 0.25 : 1.0) * hrows * 2.0) + 3000.0 +
+                       mt * n_tile * 40.0;
+          const double waves = (double)((tiles + 147) / 148);
+          const double cost = waves * cta;
+          if (best < 0 || cost < best) {
+            best = cost;
+            HaloParams& p = plan.p;
+            p = HaloParams{};
+            p.bx = b[0]; p.by = b[1]; p.bz = b[2];
+            p.lbx = ilog2(b[0]); p.lby = ilog2(b[1]);
+            p.mt = mt; p.mt_axis = axis;
+            p.cbx = cb[0]; p.cby = cb[1]; p.cbz = cb[2];
+            p.hx = h[0]; p.hy = h[1]; p.hz = h[2];
+            const int hstr[3] = {1, h[0], h[0] * h[1]};
+            p.mt_halo_off = mt == 2 ? b[axis] * st[axis] * hstr[axis] : 0;
+            p.halo_stride = halo_stride;
+            p.halo_region = max(nh * halo_stride, 8 * STAGE_BYTES_PER_WARP);
+            p.tiles_x = pw_ceil_div(c.ow, cb[0]); p.tiles_y = pw_ceil_div(c.oh, cb[1]);
+            p.tiles_z = pw_ceil_div(c.od, cb[2]);
+            p.n_tile = n_tile; p.nh = nh; p.nb = nb; p.nacc = nacc;
+            int cols = acc_cols + nb * mt * A_SLOT_COLS, pw2 = 32;
+            while (pw2 < cols) pw2 <<= 1;
+            p.tmem_cols = pw2;
+            plan.smem = (size_t)p.halo_region + (size_t)nb * b_stage + SMEM_SLACK;
+            plan.grid = dim3((unsigned)(tiles / slabs), (unsigned)slabs);
+            plan.ok = true;
+          }
+        }
+      }
+    }
+  }
+  if (!plan.ok) return plan;
+  HaloParams& p = plan.p;
+  p.od = c.od; p.oh = c.oh; p.ow = c.ow; p.cout = c.cout;
+  p.kh = c.kh; p.kw = c.kw; p.n_taps = T; p.chunks = chunks;
+  p.sd = c.sd; p.sh = c.sh; p.sw = c.sw; p.pd = c.pd; p.ph = c.ph; p.pw = c.pw;
+  p.dd = c.dd; p.dh = c.dh; p.dw = c.dw;
+  p.out_ld = c.out_ld; p.res_ld = c.res_ld; p.act = c.act; p.act_channels = c.act_channels;
+  plan.c = c;
+  return plan;
+}
+
+}  // namespace
+
+PW_API int pw_conv_halo_supported(const pw_conv_desc* d) {
+  if (!d) return 0;
+  if (d->sd < 1 || d->sh < 1 || d->sw < 1) return 0;
+  if (encode_tiled_fn() == nullptr) return 0;
+  return make_plan(*d).ok ? 1 : 0;
+}
+
+PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* wt_hi,
+                            const float* wt_lo, const float* scale, const float* bias,
+                            const float* residual, float* y, void* stream) {
+  PW_REQUIRE(d && x && wt_hi && wt_lo && y);
+  PW_REQUIRE(d->sd >= 1 && d->sh >= 1 && d->sw >= 1);
+  PW_REQUIRE(d->out_ld >= d->cout);
+  PW_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wt_hi & 15) == 0 &&
+             ((uintptr_t)wt_lo & 15) == 0);
+  PW_REQUIRE(residual == nullptr || d->res_ld >= d->cout);
+  PW_REQUIRE(d->act_channels >= 0 && (d->act_channels & 3) == 0);
+  EncodeTiledFn enc = encode_tiled_fn();
+  PW_REQUIRE(enc != nullptr);
+  HaloPlan plan = make_plan(*d);
+  PW_REQUIRE(plan.ok);
+  const pw_conv_desc& c = plan.c;
+  HaloParams& p = plan.p;
+  p.scale = scale; p.bias = bias; p.res = residual; p.y = y;
+  if (const char* e = getenv("PW_HALO_DBG")) p.dbg = atoi(e);
+  cudaStream_t st = (cudaStream_t)stream;
+
+  CUtensorMap ma, mbh, mbl;
+  {
+    cuuint64_t gdim[5] = {(cuuint64_t)c.cin, (cuuint64_t)c.w, (cuuint64_t)c.h, (cuuint64_t)c.d,
+                          (cuuint64_t)c.n};
+    cuuint64_t gstr[4] = {(cuuint64_t)c.in_ld * 4, (cuuint64_t)c.w * c.in_ld * 4,
+                          (cuuint64_t)c.h * c.w * c.in_ld * 4,
+                          (cuuint64_t)c.d * c.h * c.w * c.in_ld * 4};
+    cuuint32_t box[5] = {BLOCK_K, (cuuint32_t)p.hx, (cuuint32_t)p.hy, (cuuint32_t)p.hz, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(x), gdim, gstr,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 1000 + (int)r;
+  }
+  const long long K = (long long)p.n_taps * c.cin;
+  for (int i = 0; i < 2; ++i) {
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)c.cout};
+    cuuint64_t gstr[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)p.n_tile};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(i == 0 ? &mbh : &mbl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<float*>(i == 0 ? wt_hi : wt_lo), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 1000 + (int)r;
+  }
+
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const bool want_ts = getenv("PW_HALO_TS") != nullptr;
+  const size_t n_cta = (size_t)plan.grid.x * plan.grid.y;
+  if (want_ts) {
+    cudaMalloc(&p.ts, n_cta * 16 * sizeof(long long));
+    cudaMemset(p.ts, 0, n_cta * 16 * sizeof(long long));
+  }
+  conv_halo_kernel<<<plan.grid, NUM_THREADS, plan.smem, st>>>(ma, mbh, mbl, p);
+  PW_LAUNCH_CHECK();
+  if (want_ts) {
+    cudaStreamSynchronize(st);
+    long long* h = (long long*)malloc(n_cta * 16 * sizeof(long long));
+    cudaMemcpy(h, p.ts, n_cta * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+    double sum[16] = {0};
+    for (size_t i = 0; i < n_cta; ++i)
+      for (int k = 0; k < 16; ++k) sum[k] += (double)(h[i * 16 + k] - h[i * 16]);
+    fprintf(stderr, "[halo ts] grid %u x %u mt %d n_tile %d nh %d nb %d nacc %d box %dx%dx%d halo %dx%dx%d smem %zu tmem %d:",
+            plan.grid.x, plan.grid.y, p.mt, p.n_tile, p.nh, p.nb, p.nacc, p.cbx, p.cby, p.cbz,
+            p.hx, p.hy, p.hz, plan.smem, p.tmem_cols);
+    for (int k = 0; k < 15; ++k) fprintf(stderr, " t%d=%.0f", k, sum[k] / n_cta);
+    fprintf(stderr, "\n");
+    free(h);
+    cudaFree(p.ts);
+  }
+  pw_count_launch(1);
+  return 0;
+}

@@ -151,6 +151,9 @@ class PackedConv:
 # The tensor-core path is used whenever the layer qualifies; set to False to
 # force the fp32 SIMT kernel (tests compare the two).
 USE_UMMA = True
+# ... and among the tensor-core kernels the halo-resident / TMEM-operand one
+# (conv_halo.cu) wherever its plan fits; False falls back to conv_umma.cu.
+USE_HALO = True
 
 
 def conv(x, pc, act=None, residual=None, out=None, act_channels=0):
@@ -181,6 +184,13 @@ def conv(x, pc, act=None, residual=None, out=None, act_channels=0):
     if residual is not None:
         assert residual.shape == out.shape
     L = _lib.lib()
+    if USE_UMMA and USE_HALO and pc.wt_hi is not None and \
+            L.pw_conv_halo_supported(ctypes.byref(d)):
+        check(L.pw_conv_halo_fwd(ctypes.byref(d), _ptr(x), _ptr(pc.wt_hi),
+                                 _ptr(pc.wt_lo), _ptr(pc.scale), _ptr(pc.bias),
+                                 _ptr(residual), _ptr(out), _stream()),
+              'pw_conv_halo_fwd')
+        return out
     if USE_UMMA and pc.wt_hi is not None and \
             L.pw_conv_umma_supported(ctypes.byref(d)):
         check(L.pw_conv_umma_fwd(ctypes.byref(d), _ptr(x), _ptr(pc.wt_hi),
