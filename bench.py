@@ -114,7 +114,8 @@ class LaunchProfiler:
         from preworld_b200 import _lib
         for name in _lib.SIGNATURES:
             if name in ('pw_abi_version', 'pw_launch_count',
-                        'pw_lift_workspace_bytes', 'pw_conv_umma_supported'):
+                        'pw_lift_workspace_bytes', 'pw_conv_umma_supported',
+                        'pw_conv_halo_supported'):
                 continue
             fn = getattr(self.L, name)
             self.orig[name] = fn
@@ -135,7 +136,7 @@ class LaunchProfiler:
 
     @staticmethod
     def _shape(name, a):
-        if name in ('pw_conv_fwd', 'pw_conv_umma_fwd'):
+        if name in ('pw_conv_fwd', 'pw_conv_umma_fwd', 'pw_conv_halo_fwd'):
             d = a[0]._obj
             return (f'{d.n}x{d.d}x{d.h}x{d.w}x{d.cin}->{d.cout} '
                     f'k{d.kd}{d.kh}{d.kw} s{d.sw} d{d.dw}')
@@ -144,7 +145,7 @@ class LaunchProfiler:
     @staticmethod
     def _work(name, a):
         """(algorithmic flops, algorithmic bytes) of one call."""
-        if name in ('pw_conv_fwd', 'pw_conv_umma_fwd'):
+        if name in ('pw_conv_fwd', 'pw_conv_umma_fwd', 'pw_conv_halo_fwd'):
             d = a[0]._obj
             m = d.n * d.od * d.oh * d.ow
             k = d.kd * d.kh * d.kw * d.cin
@@ -372,9 +373,13 @@ def main():
                 json.dump(prof.layers, f, indent=1)
         top = max(kernels, key=lambda k: kernels[k]['ms_per_step'])
         k = kernels[top]
-        if top == 'pw_conv_umma_fwd':
-            roof = {'kernel': 'conv_umma_kernel (pw_conv_umma_fwd: tcgen05 '
-                              'kind::tf32 implicit GEMM, 3xTF32 split, TMA)',
+        if top in ('pw_conv_umma_fwd', 'pw_conv_halo_fwd'):
+            kname = ('conv_halo_kernel (pw_conv_halo_fwd: halo-resident tcgen05 '
+                     'kind::tf32 implicit GEMM, A operand in TMEM, 3xTF32 '
+                     'split, TMA)') if top == 'pw_conv_halo_fwd' else (
+                     'conv_umma_kernel (pw_conv_umma_fwd: tcgen05 kind::tf32 '
+                     'implicit GEMM, 3xTF32 split, TMA)')
+            roof = {'kernel': kname,
                     'bound': 'tensor', 'achieved': k['tflops'],
                     'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                     'frac': k['tflops'] / peaks['bf16_tflops_sustained'],

@@ -187,12 +187,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     int r = 0;
     uint32_t ph = 0;
     uint32_t accumulate = 0;                                   // first k-steps overwrite
+    long long cyc_b = 0, cyc_a = 0, cyc_i = 0, tq = 0;
     for (int ct = 0; ct < total_ct; ++ct) {
+      if (p.ts) tq = clock64();
       mbar_wait(b_full + 8 * r, ph);
+      if (p.ts) { cyc_b += clock64() - tq; }
       const uint64_t bdesc = desc0 + (uint64_t)(desc_stage * (uint32_t)r);
       for (int m = 0; m < p.mt; ++m) {
+        if (p.ts) tq = clock64();
         mbar_wait(a_full + 8 * (r * p.mt + m), ph);
         tc_fence_after();
+        if (p.ts) { cyc_a += clock64() - tq; tq = clock64(); }
         const uint32_t a_hi = tbase + a_ring_col + (uint32_t)((r * p.mt + m) * A_SLOT_COLS);
         const uint32_t acc = tbase + (uint32_t)(m * tile_cols);
         if (leader) {
@@ -208,6 +213,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
           }
         }
         __syncwarp();
+        if (p.ts) cyc_i += clock64() - tq;
       }
       accumulate = 1;
       if (leader) umma_commit(ring_empty + 8 * r);   // weight stage + A slots free on retire
@@ -216,6 +222,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     }
     if (leader) umma_commit(accum_bar);
     __syncwarp();
+    if (p.ts && leader) {
+      long long* t = p.ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
+      t[6] = clock64(); t[12] = t[0] + cyc_b; t[13] = t[0] + cyc_a; t[14] = t[0] + cyc_i;
+    }
   } else {
     // ===================== split warps, then epilogue ==========================
     const int sw_id = warp - FIRST_SPLIT_WARP;
@@ -318,8 +328,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       ++released;
     }
 
-    // ---- epilogue: TMEM -> regs (main + corr, affine) -> swizzled smem ->
-    //      coalesced residual / activation / store ----------------------------
+    // ---- epilogue: TMEM -> regs (main + corr) -> swizzled smem -> coalesced
+    //      affine / residual / activation / store (kept small: it is straight-line
+    //      code after the main loop and must not thrash the instruction cache) ----
     if (sw_id == 0 && lane == 0) PW_TS(11);
     mbar_wait(accum_bar, 0);
     tc_fence_after();
@@ -331,52 +342,45 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     const bool vec_ok = ((p.out_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                         (p.res == nullptr || ((p.res_ld & 3) == 0 &&
                                               (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
+    const int ch4 = lane & 7;
     for (int item = set; item < items; item += SPLIT_SETS) {
       const int m = item / ncg;
       const int col0 = (item - m * ncg) * 32;
       const int ncol = min(32, p.n_tile - col0);         // 16 or 32 (warp-uniform)
-      float acc[32];
+      // phase 1: this thread's accumulator row (32 channels) -> its staging row
+      for (int half = 0; half * 16 < ncol; ++half) {
+        float acc[16];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-      for (int copy = 0; copy < p.nacc; ++copy) {
-        uint32_t a[32], b[32];
-        const uint32_t taddr = tmem_base + lane_field +
-                               (uint32_t)(m * tile_cols + copy * 2 * p.n_tile + col0);
-        tmem_ld16_nowait(taddr, a);
-        tmem_ld16_nowait(taddr + p.n_tile, b);
-        if (ncol > 16) {
-          tmem_ld16_nowait(taddr + 16, a + 16);
-          tmem_ld16_nowait(taddr + p.n_tile + 16, b + 16);
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        for (int copy = 0; copy < p.nacc; ++copy) {
+          uint32_t a[16], b[16];
+          const uint32_t taddr = tmem_base + lane_field +
+                                 (uint32_t)(m * tile_cols + copy * 2 * p.n_tile + col0 + half * 16);
+          tmem_ld16_nowait(taddr, a);
+          tmem_ld16_nowait(taddr + p.n_tile, b);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(a[j]) + __uint_as_float(b[j]);
         }
-        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < 16 || ncol > 16) acc[j] += __uint_as_float(a[j]) + __uint_as_float(b[j]);
-      }
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        if (j4 * 4 < ncol) {
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = j4 * 4 + e;
-            const int ch = n0 + col0 + j;
-            float x = acc[j];
-            if (ch < p.cout) {
-              const float sc = p.scale ? __ldg(p.scale + ch) : 1.f;
-              const float bi = p.bias ? __ldg(p.bias + ch) : 0.f;
-              x = fmaf(x, sc, bi);
-            }
-            v[e] = x;
-          }
-          stage[lane * 8 + (j4 ^ (lane & 7))] = make_float4(v[0], v[1], v[2], v[3]);
-        }
+        for (int j4 = 0; j4 < 4; ++j4)
+          stage[lane * 8 + ((half * 4 + j4) ^ (lane & 7))] =
+              make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
       }
       __syncwarp();
-      const int ch4 = lane & 7;
+      // phase 2: lane -> (row group, 4 channels); 8 lanes cover one 128-byte row
       const int cbase = n0 + col0 + ch4 * 4;
       if (ch4 * 4 < ncol && cbase < p.cout) {
+        float sc[4], bi[4];
 #pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const bool ok = cbase + e < p.cout;
+          sc[e] = (p.scale && ok) ? __ldg(p.scale + cbase + e) : 1.f;
+          bi[e] = (p.bias && ok) ? __ldg(p.bias + cbase + e) : 0.f;
+        }
+        const int a_ = (cbase < act_end) ? p.act : PW_ACT_NONE;     // act_end % 4 == 0
+        const bool vec = vec_ok && cbase + 4 <= p.cout;
+#pragma unroll 2
         for (int i = 0; i < 8; ++i) {
           const int r = i * 4 + (lane >> 3);
           const int Rr = q * 32 + r;
@@ -388,21 +392,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
           else oz += m * p.bz;
           if (ox >= p.ow || oy >= p.oh || oz >= p.od) continue;
           const float4 v4 = stage[r * 8 + (ch4 ^ (r & 7))];
-          float v[4] = {v4.x, v4.y, v4.z, v4.w};
+          float v[4] = {fmaf(v4.x, sc[0], bi[0]), fmaf(v4.y, sc[1], bi[1]),
+                        fmaf(v4.z, sc[2], bi[2]), fmaf(v4.w, sc[3], bi[3])};
           const size_t pix = (((size_t)img * p.od + oz) * p.oh + oy) * p.ow + ox;
           float* yrow = p.y + pix * p.out_ld + cbase;
           const float* rrow = p.res ? p.res + pix * p.res_ld + cbase : nullptr;
-          const int a_ = (cbase < act_end) ? p.act : PW_ACT_NONE;   // act_end % 4 == 0
-          if (vec_ok && cbase + 4 <= p.cout) {
+          if (vec) {
             if (rrow) {
               const float4 rr = pw_ldg4(rrow);
               v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
             }
-            *reinterpret_cast<float4*>(yrow) =
-                make_float4(pw_activate(v[0], a_), pw_activate(v[1], a_),
-                            pw_activate(v[2], a_), pw_activate(v[3], a_));
-          } else {
+            if (a_ == PW_ACT_RELU) {
 #pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+            } else if (a_ != PW_ACT_NONE) {
+#pragma unroll 1
+              for (int e = 0; e < 4; ++e) v[e] = pw_activate(v[e], a_);
+            }
+            *reinterpret_cast<float4*>(yrow) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll 1
             for (int e = 0; e < 4; ++e) {
               if (cbase + e < p.cout) {
                 float tv = v[e];
