@@ -169,7 +169,10 @@ int pw_bev_pool_v2(int c, int n_intervals, const float* depth, const float* feat
  *   depth: [b*n, d, h, w] probabilities (planar, as the reference)
  *   feat:  [b*n, h, w, feat_ld] channels-last context features (c used)
  *   out:   [b, gz, gy, gx, c] channels-last, EVERY voxel written (no memset)
- *   workspace: pw_lift_workspace_bytes(...) bytes of device scratch.
+ *   workspace: pw_lift_workspace_bytes(...) bytes of device scratch whose first
+ *        256 bytes (grid-barrier / cursor words) must be ZERO before the first
+ *        call; the kernel leaves them zero, so one workspace serves any number
+ *        of calls on one stream.
  * Summation order inside a voxel is ascending frustum-point index -- the
  * order a stable sort gives the reference (its argsort is unstable,
  * view_transformer.py:246, so the reference's own order is unspecified). */

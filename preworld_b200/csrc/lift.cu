@@ -20,142 +20,434 @@ __device__ __forceinline__ float dot3(const float* m, float x, float y, float z)
   return fmaf(m[2], z, acc);
 }
 
-// One thread per frustum point p = (((b*N+n)*D+d)*H+h)*W+w.
+struct LiftGeom {
+  const float* cam; const float* bda; const float* xs; const float* ys; const float* ds;
+  float lx, ly, lz, ix, iy, iz;
+  int B, N, D, H, W, gx, gy, gz;
+};
+
+// Voxel rank (or -1) of frustum point p = (((b*N+n)*D+d)*H+h)*W+w.
 // Arithmetic order is pinned to oracle/oracle_ref.c:pw_ref_lift_ranks.
-__global__ void lift_rank_kernel(const float* __restrict__ cam, const float* __restrict__ bda,
-                                 const float* __restrict__ xs, const float* __restrict__ ys,
-                                 const float* __restrict__ ds, float lx, float ly, float lz,
-                                 float ix_, float iy_, float iz_, int B, int N, int D, int H,
-                                 int W, int gx, int gy, int gz, int* __restrict__ rank,
-                                 int* __restrict__ count) {
-  long long total = (long long)B * N * D * H * W;
+__device__ __forceinline__ int lift_rank_of(const LiftGeom& g, long long p) {
+  int w = (int)(p % g.W);
+  long long t = p / g.W;
+  int h = (int)(t % g.H); t /= g.H;
+  int d = (int)(t % g.D); t /= g.D;
+  int bn = (int)t;
+  int b = bn / g.N;
+  const float* c = g.cam + (long long)bn * PW_LIFT_CAM_FLOATS;
+  const float* bd = g.bda + b * 9;
+  float px = __ldg(g.xs + w) - c[9], py = __ldg(g.ys + h) - c[10], pz = __ldg(g.ds + d) - c[11];
+  float qx = dot3(c + 0, px, py, pz), qy = dot3(c + 3, px, py, pz), qz = dot3(c + 6, px, py, pz);
+  qx = qx * qz;
+  qy = qy * qz;
+  float ex = dot3(c + 12, qx, qy, qz) + c[21];
+  float ey = dot3(c + 15, qx, qy, qz) + c[22];
+  float ez = dot3(c + 18, qx, qy, qz) + c[23];
+  float fx = dot3(bd + 0, ex, ey, ez), fy = dot3(bd + 3, ex, ey, ez), fz = dot3(bd + 6, ex, ey, ez);
+  // (coor - lower) / interval -> .long(): truncation toward zero keeps
+  // points in (-1,0) voxel units in voxel 0 (view_transformer.py:226-236)
+  float vx = __fdiv_rn(fx - g.lx, g.ix), vy = __fdiv_rn(fy - g.ly, g.iy),
+        vz = __fdiv_rn(fz - g.lz, g.iz);
+  long long cx = (long long)vx, cy = (long long)vy, cz = (long long)vz;
+  bool ok = cx >= 0 && cx < g.gx && cy >= 0 && cy < g.gy && cz >= 0 && cz < g.gz;
+  return ok ? (int)((((long long)b * g.gz + cz) * g.gy + cy) * g.gx + cx) : -1;
+}
+
+__global__ void lift_rank_kernel(const LiftGeom g, int* __restrict__ rank) {
+  long long total = (long long)g.B * g.N * g.D * g.H * g.W;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total;
-       p += (long long)gridDim.x * blockDim.x) {
-    int w = (int)(p % W);
-    long long t = p / W;
-    int h = (int)(t % H); t /= H;
-    int d = (int)(t % D); t /= D;
-    int bn = (int)t;
-    int b = bn / N;
-    const float* c = cam + (long long)bn * PW_LIFT_CAM_FLOATS;
-    const float* bd = bda + b * 9;
-    float px = __ldg(xs + w) - c[9], py = __ldg(ys + h) - c[10], pz = __ldg(ds + d) - c[11];
-    float qx = dot3(c + 0, px, py, pz), qy = dot3(c + 3, px, py, pz), qz = dot3(c + 6, px, py, pz);
-    qx = qx * qz;
-    qy = qy * qz;
-    float ex = dot3(c + 12, qx, qy, qz) + c[21];
-    float ey = dot3(c + 15, qx, qy, qz) + c[22];
-    float ez = dot3(c + 18, qx, qy, qz) + c[23];
-    float fx = dot3(bd + 0, ex, ey, ez), fy = dot3(bd + 3, ex, ey, ez), fz = dot3(bd + 6, ex, ey, ez);
-    // (coor - lower) / interval -> .long(): truncation toward zero keeps
-    // points in (-1,0) voxel units in voxel 0 (view_transformer.py:226-236)
-    float vx = __fdiv_rn(fx - lx, ix_), vy = __fdiv_rn(fy - ly, iy_), vz = __fdiv_rn(fz - lz, iz_);
-    long long cx = (long long)vx, cy = (long long)vy, cz = (long long)vz;
-    bool ok = cx >= 0 && cx < gx && cy >= 0 && cy < gy && cz >= 0 && cz < gz;
-    int r = ok ? (int)((((long long)b * gz + cz) * gy + cy) * gx + cx) : -1;
-    rank[p] = r;
-    if (count != nullptr && ok) atomicAdd(count + r, 1);
+       p += (long long)gridDim.x * blockDim.x)
+    rank[p] = lift_rank_of(g, p);
+}
+
+// ---------------------------------------------------------------------------
+// The fused lift: ONE persistent kernel (cooperative launch, grid barriers).
+//
+//   phase 0  zero count[V]
+//   phase 1  rank[p], slot[p] = atomicAdd(count[rank], 1)      (per frustum point)
+//   phase 2  start[v] = exclusive offsets (per-CTA voxel range: one atomic + block scans)
+//   phase 3  list[start[rank[p]] + slot[p]] = p
+//   phase 4  pool the non-empty voxels (points in ascending frustum index);
+//            the rare voxels with more than 32 points are queued ...
+//   phase 5  ... and pooled one warp per voxel
+//
+// The only large stream is the 4*V*C-byte output.  It is zero-filled by ALL
+// threads in four slices issued between the arrive and the wait of the grid
+// barriers (the stores drain while the tiny phases 0-3 run), and phase 4 then
+// overwrites just the non-empty rows, which are still resident in L2.
+constexpr int LIFT_THREADS = 512;
+
+struct LiftFused {
+  LiftGeom g;
+  const float* depth; const float* feat; int feat_ld; int C;
+  float* out;
+  int* rank; int* slot; int* count; int* start; int* list;
+  unsigned* ctrl;               // [0] grid-barrier counter, [1] list cursor, [2] work-queue
+                                // length, [3] exit counter, [4] group ticket: zero on entry, re-zeroed on exit
+  long long P, V;
+};
+
+__device__ __forceinline__ void grid_arrive(unsigned* ctr) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+  }
+}
+__device__ __forceinline__ void grid_wait(unsigned* ctr, unsigned target) {
+  if (threadIdx.x == 0) {
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+// slice `k` of `n` of the output zero fill (float4 stores, grid-stride)
+__device__ __forceinline__ void zero_slice(float* out, long long n4, int k, int n) {
+  const long long lo = n4 * k / n, hi = n4 * (k + 1) / n;
+  float4* o = reinterpret_cast<float4*>(out);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi;
+       i += (long long)gridDim.x * blockDim.x)
+    __stcs(o + i, z);
+}
+
+// phase time stamps of CTA 0 (ctrl[8 + 2k], ns): read back by tools/lift_probe.py
+__device__ __forceinline__ void lift_stamp(unsigned* ctrl, int k) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    reinterpret_cast<unsigned long long*>(ctrl + 8)[k] = t;
   }
 }
 
-// start[v] = running offset of voxel v's point list.  The list placement is
-// arbitrary (one atomic per warp) -- the pooling kernel orders the points of
-// a voxel itself, so the result does not depend on it.
-__global__ void lift_offsets_kernel(const int* __restrict__ count, int* __restrict__ start,
-                                    int* __restrict__ cursor, int* __restrict__ fill, int V) {
-  int v = blockIdx.x * blockDim.x + threadIdx.x;
-  int lane = threadIdx.x & 31;
-  int c = v < V ? count[v] : 0;
-  int incl = c;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  int total = __shfl_sync(0xffffffffu, incl, 31);
-  int base = 0;
-  if (lane == 31 && total > 0) base = atomicAdd(cursor, total);
-  base = __shfl_sync(0xffffffffu, base, 31);
-  if (v < V) {
-    start[v] = base + incl - c;
-    fill[v] = 0;
-  }
-}
-
-__global__ void lift_fill_kernel(const int* __restrict__ rank, const int* __restrict__ start,
-                                 int* __restrict__ fill, int* __restrict__ list, long long P) {
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P;
-       p += (long long)gridDim.x * blockDim.x) {
-    int r = rank[p];
-    if (r >= 0) list[start[r] + atomicAdd(fill + r, 1)] = (int)p;
-  }
-}
-
-// One warp per group of 32 consecutive voxels; lane = channel while pooling.
-// Points of a voxel are consumed in ascending frustum index (== the stable
-// sort order of the oracle), each as psum = fmaf(feat, depth, psum) exactly
-// like bev_pool_cuda.cu:38-42 compiled with -fmad=true.
 template <int CPL>   // channels per lane: C <= 32*CPL
-__global__ void __launch_bounds__(256)
-lift_pool_kernel(const float* __restrict__ depth, const float* __restrict__ feat, int feat_ld,
-                 const int* __restrict__ count, const int* __restrict__ start,
-                 const int* __restrict__ list, int C, int D, int HW, long long V,
-                 float* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long v0 = warp * 32; v0 < V; v0 += nwarps * 32) {
-    long long vmine = v0 + lane;
-    int cnt = vmine < V ? __ldg(count + vmine) : 0;
-    int st = vmine < V ? __ldg(start + vmine) : 0;
-    int nvox = (int)min((long long)32, V - v0);
-    unsigned nonempty = __ballot_sync(0xffffffffu, cnt > 0);
-    // zero the empty voxels of this group first (coalesced 128-byte rows)
-    for (int j = 0; j < nvox; ++j) {
-      if ((nonempty >> j) & 1u) continue;
-      float* o = out + (v0 + j) * C;
+__global__ void __launch_bounds__(LIFT_THREADS, 2)
+lift_fused_kernel(const LiftFused a) {
+  __shared__ int s_scan[LIFT_THREADS / 32];
+  __shared__ int s_base;
+  __shared__ int s_row[LIFT_THREADS / 32][32];    // feature row (bn*HW + hw) of sorted entry t
+  __shared__ float s_d[LIFT_THREADS / 32][32];
+  __shared__ int s_v[LIFT_THREADS / 32][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const unsigned G = gridDim.x;
+  const long long n4 = a.V * a.C / 4;                // host guarantees V*C % 4 == 0
+  unsigned* bar = a.ctrl;
+
+  lift_stamp(a.ctrl, 0);
+  // ---- phase 0 -------------------------------------------------------------
+  {
+    int4* c4 = reinterpret_cast<int4*>(a.count);       // count[] is 256-byte aligned, padded
+    const long long n = (a.V + 3) / 4;
+    for (long long i = tid; i < n; i += nthreads) c4[i] = make_int4(0, 0, 0, 0);
+  }
+  grid_arrive(bar);
+  zero_slice(a.out, n4, 0, 4);
+  grid_wait(bar, G);
+  lift_stamp(a.ctrl, 1);
+
+  // ---- phase 1: rank + slot (4 points per thread in flight) -------------------
+  for (long long p0 = tid; p0 < a.P; p0 += 4 * nthreads) {
+    int r[4];
+    unsigned sl[4];
 #pragma unroll
-      for (int q = 0; q < CPL; ++q) {
-        int ch = lane + 32 * q;
-        if (ch < C) o[ch] = 0.f;
+    for (int u = 0; u < 4; ++u) {
+      const long long p = p0 + u * nthreads;
+      r[u] = p < a.P ? lift_rank_of(a.g, p) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      sl[u] = r[u] >= 0 ? atomicAdd(reinterpret_cast<unsigned*>(a.count) + r[u], 1u) : 0u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long p = p0 + u * nthreads;
+      if (p < a.P) {
+        a.rank[p] = r[u];
+        a.slot[p] = (int)sl[u];
       }
     }
-    while (nonempty) {
-      int j = __ffs(nonempty) - 1;
-      nonempty &= nonempty - 1;
-      int n = __shfl_sync(0xffffffffu, cnt, j);
-      int s = __shfl_sync(0xffffffffu, st, j);
-      float acc[CPL];
+  }
+  grid_arrive(bar);
+  zero_slice(a.out, n4, 1, 4);
+  grid_wait(bar, 2 * G);
+  lift_stamp(a.ctrl, 2);
+
+  // ---- phase 2: list offsets.  CTA b owns voxels [b*VB, (b+1)*VB), VB a multiple
+  // of LIFT_THREADS: one reduction + ONE atomic for the CTA's base, then a running
+  // block scan numbers the voxels in order (so a 32-voxel group's lists are one
+  // contiguous, voxel-ordered segment). ------------------------------------------
+  {
+    const long long VB = ((a.V + G - 1) / G + LIFT_THREADS - 1) / LIFT_THREADS * LIFT_THREADS;
+    const long long vb0 = blockIdx.x * VB;
+    const long long vb1 = min(a.V, vb0 + VB);
+    int mysum = 0;
+    for (long long v = vb0 + threadIdx.x; v < vb1; v += LIFT_THREADS) mysum += __ldcg(a.count + v);
+    mysum = __reduce_add_sync(0xffffffffu, mysum);
+    if (lane == 0) s_scan[warp] = mysum;
+    __syncthreads();
+    if (warp == 0) {
+      int w = lane < LIFT_THREADS / 32 ? s_scan[lane] : 0;
+      w = __reduce_add_sync(0xffffffffu, w);
+      if (lane == 0) s_base = w > 0 ? (int)atomicAdd(a.ctrl + 1, (unsigned)w) : 0;
+    }
+    __syncthreads();
+    int carry = s_base;
+    for (long long c0 = vb0; c0 < vb1; c0 += LIFT_THREADS) {
+      const long long v = c0 + threadIdx.x;
+      const int c = v < vb1 ? __ldcg(a.count + v) : 0;
+      int incl = c;
 #pragma unroll
-      for (int q = 0; q < CPL; ++q) acc[q] = 0.f;
-      int last = -1;
-      for (int it = 0; it < n; ++it) {
-        // next point index greater than `last`
-        int best = 0x7fffffff;
-        for (int k = lane; k < n; k += 32) {
-          int pnt = __ldg(list + s + k);
-          if (pnt > last && pnt < best) best = pnt;
-        }
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      __syncthreads();                                  // s_scan free (previous iteration)
+      if (lane == 31) s_scan[warp] = incl;
+      __syncthreads();
+      int woff = 0, total = 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-        last = best;
-        // p = (bn*D + d)*HW + hw  ->  feature row bn*HW + hw
-        int hw = best % HW;
-        int bn = best / HW / D;
-        float dv = __ldg(depth + best);
-        const float* f = feat + ((long long)bn * HW + hw) * feat_ld;
+      for (int w = 0; w < LIFT_THREADS / 32; ++w) {
+        const int t = s_scan[w];
+        if (w < warp) woff += t;
+        total += t;
+      }
+      if (v < vb1) a.start[v] = carry + woff + incl - c;
+      carry += total;
+    }
+  }
+  grid_arrive(bar);
+  zero_slice(a.out, n4, 2, 4);
+  grid_wait(bar, 3 * G);
+  lift_stamp(a.ctrl, 3);
+
+  // ---- phase 3: fill the per-voxel lists ------------------------------------------
+  for (long long p0 = tid; p0 < a.P; p0 += 4 * nthreads) {
+    int r[4], dst[4];
 #pragma unroll
-        for (int q = 0; q < CPL; ++q) {
-          int ch = lane + 32 * q;
-          if (ch < C) acc[q] = fmaf(__ldg(f + ch), dv, acc[q]);
+    for (int u = 0; u < 4; ++u) {
+      const long long p = p0 + u * nthreads;
+      r[u] = p < a.P ? __ldcg(a.rank + p) : -1;
+      dst[u] = p < a.P ? __ldcg(a.slot + p) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r[u] >= 0) dst[u] += __ldcg(a.start + r[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r[u] >= 0) a.list[dst[u]] = (int)(p0 + u * nthreads);
+  }
+  zero_slice(a.out, n4, 3, 4);               // must be ordered before phase 4's overwrites
+  grid_arrive(bar);
+  grid_wait(bar, 4 * G);
+  lift_stamp(a.ctrl, 4);
+
+  // ---- phase 4: pool.  One warp per group of 32 consecutive voxels, cut into
+  // batches of consecutive voxels with <= 32 points in total; lane i of a batch
+  // <-> its i-th list entry.  Points of a voxel are consumed in ascending
+  // frustum index (== the stable sort order of the oracle), each as
+  // acc = fmaf(feat, depth, acc) exactly like bev_pool_cuda.cu:38-42; lane =
+  // channel while accumulating.  Voxels with more than 32 points (next to a
+  // camera; rare) are queued for phase 5. ------------------------------------------
+  const int HW = a.g.H * a.g.W;
+  const long long ngroups = (a.V + 31) / 32;
+  const long long gwarp = tid >> 5, nwarps = nthreads >> 5;
+  // one batch: voxels j0..j1 of the group at v0 (their <= 32 points are one
+  // contiguous list segment starting at start[v0 + j0])
+  auto pool_batch = [&](long long v0, int cnt, int excl, int incl, int st, unsigned nonempty,
+                        int j0, unsigned fit) {
+    const int base = __shfl_sync(0xffffffffu, excl, j0);
+    const int j1 = 31 - __clz(fit);
+    const unsigned bmask = fit & nonempty;
+    const int T = __shfl_sync(0xffffffffu, incl, j1) - base;
+    const int seg = __shfl_sync(0xffffffffu, st, j0);
+    const bool mine = (bmask >> lane) & 1u;
+    const unsigned heads = __reduce_or_sync(0xffffffffu, mine ? (1u << (excl - base)) : 0u);
+    int pnt = 0x7fffffff, vox = j0;
+    if (lane < T) {
+      pnt = __ldcg(a.list + seg + lane);
+      const int k = __popc(heads & (0xffffffffu >> (31 - lane))) - 1;   // ordinal in the batch
+      vox = __fns(bmask, 0, k + 1);
+    }
+    const int e_i = __shfl_sync(0xffffffffu, excl, vox) - base;
+    const int c_i = __shfl_sync(0xffffffffu, cnt, vox);
+    // position inside the voxel = number of its points with a smaller index
+    const int maxc = __reduce_max_sync(0xffffffffu, mine ? cnt : 0);
+    int pos = e_i;
+    for (int t = 0; t < maxc; ++t) {
+      const int q = __shfl_sync(0xffffffffu, pnt, min(e_i + t, 31));
+      if (lane < T && t < c_i && q < pnt) ++pos;
+    }
+    __syncwarp();
+    if (lane < T) {
+      // p = (bn*D + d)*HW + hw  ->  feature row bn*HW + hw
+      s_row[warp][pos] = (pnt / HW / a.g.D) * HW + pnt % HW;
+      s_d[warp][pos] = __ldg(a.depth + pnt);
+      s_v[warp][pos] = vox;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int qc = 0; qc < CPL; ++qc) {
+      const int ch = lane + 32 * qc;
+      const bool chok = ch < a.C;
+      float f[32];
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        f[t] = 0.f;
+        if (t < T && chok) f[t] = __ldg(a.feat + (long long)s_row[warp][t] * a.feat_ld + ch);
+      }
+      float acc = 0.f;
+      int cur = -1;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        if (t < T) {
+          const int vx = s_v[warp][t];
+          if (vx != cur) {
+            if (cur >= 0 && chok) a.out[(v0 + cur) * a.C + ch] = acc;
+            cur = vx;
+            acc = 0.f;
+          }
+          acc = fmaf(f[t], s_d[warp][t], acc);
         }
       }
-      float* o = out + (v0 + j) * C;
+      if (cur >= 0 && chok) a.out[(v0 + cur) * a.C + ch] = acc;
+    }
+    __syncwarp();
+  };
+
+  int cnt_n = 0, st_n = 0;                              // prefetched for the next group
+  if (gwarp < ngroups && gwarp * 32 + lane < a.V) {
+    cnt_n = __ldcg(a.count + gwarp * 32 + lane);
+    st_n = __ldcg(a.start + gwarp * 32 + lane);
+  }
+  for (long long grp = gwarp; grp < ngroups; grp += nwarps) {
+    const long long v0 = grp * 32;
+    const int cnt = cnt_n, st = st_n;
+    {
+      const long long vn = (grp + nwarps) * 32 + lane;
+      const bool ok = grp + nwarps < ngroups && vn < a.V;
+      cnt_n = ok ? __ldcg(a.count + vn) : 0;
+      st_n = ok ? __ldcg(a.start + vn) : 0;
+    }
+    const unsigned nonempty = __ballot_sync(0xffffffffu, cnt > 0);
+    if (nonempty == 0) continue;                       // rows already zero
+    int incl = cnt;
 #pragma unroll
-      for (int q = 0; q < CPL; ++q) {
-        int ch = lane + 32 * q;
-        if (ch < C) o[ch] = acc[q];
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int excl = incl - cnt;
+    const int Tg = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned todo = nonempty;
+    while (todo) {
+      const int j0 = __ffs(todo) - 1;
+      const int base = __shfl_sync(0xffffffffu, excl, j0);
+      const int c0 = __shfl_sync(0xffffffffu, cnt, j0);
+      if (c0 > 32) {                                       // big voxel -> phase 5
+        if (lane == 0) a.rank[atomicAdd(a.ctrl + 2, 1u)] = (int)(v0 + j0);   // rank[] is free now
+        todo &= todo - 1;
+        continue;
       }
+      // voxels j0..j1: the longest run whose points fit 32 lanes (incl is monotone)
+      const unsigned fit = __ballot_sync(0xffffffffu, lane >= j0 && incl - base <= 32);
+      todo &= ~fit;
+      if (Tg > 64) {                                       // crowded group: spread its batches
+        if (lane == 0) a.rank[atomicAdd(a.ctrl + 2, 1u)] = (int)(v0 + j0);
+        continue;
+      }
+      pool_batch(v0, cnt, excl, incl, st, nonempty, j0, fit);
+    }
+  }
+  lift_stamp(a.ctrl, 5);
+  grid_arrive(bar);
+  grid_wait(bar, 5 * G);
+  lift_stamp(a.ctrl, 6);
+
+  // ---- phase 5: one warp per queued item: a batch of a crowded group, or a
+  // voxel with more than 32 points (any list length) -------------------------------
+  const unsigned qlen = __ldcg(a.ctrl + 2);
+  for (unsigned qi = (unsigned)gwarp; qi < qlen; qi += (unsigned)nwarps) {
+    const long long v = __ldcg(a.rank + qi);
+    {
+      const long long v0 = v & ~31ll;
+      const int j0 = (int)(v & 31);
+      const long long vmine = v0 + lane;
+      const int cnt = vmine < a.V ? __ldcg(a.count + vmine) : 0;
+      if (__shfl_sync(0xffffffffu, cnt, j0) <= 32) {
+        const int st = vmine < a.V ? __ldcg(a.start + vmine) : 0;
+        const unsigned nonempty = __ballot_sync(0xffffffffu, cnt > 0);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int excl = incl - cnt;
+        const int base = __shfl_sync(0xffffffffu, excl, j0);
+        const unsigned fit = __ballot_sync(0xffffffffu, lane >= j0 && incl - base <= 32);
+        pool_batch(v0, cnt, excl, incl, st, nonempty, j0, fit);
+        continue;
+      }
+    }
+    const int n = __ldcg(a.count + v);
+    const int s = __ldcg(a.start + v);
+    // sort the list by frustum index into slot[s .. s+n) (slot[] is free now):
+    // position = number of smaller entries
+    for (int b0 = 0; b0 < n; b0 += 32) {
+      const int i = b0 + lane;
+      const int e = i < n ? __ldcg(a.list + s + i) : 0x7fffffff;
+      int pos = 0;
+      for (int k = 0; k < n; ++k) pos += (__ldcg(a.list + s + k) < e) ? 1 : 0;
+      if (i < n) a.slot[s + pos] = e;
+    }
+    __syncwarp();
+    float acc[CPL];
+#pragma unroll
+    for (int qc = 0; qc < CPL; ++qc) acc[qc] = 0.f;
+    for (int b0 = 0; b0 < n; b0 += 32) {
+      const int nb = min(32, n - b0);
+      __syncwarp();
+      if (lane < nb) {
+        const int pnt = __ldcg(a.slot + s + b0 + lane);
+        s_row[warp][lane] = (pnt / HW / a.g.D) * HW + pnt % HW;
+        s_d[warp][lane] = __ldg(a.depth + pnt);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int qc = 0; qc < CPL; ++qc) {
+        const int ch = lane + 32 * qc;
+        const bool chok = ch < a.C;
+        float f[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          f[t] = 0.f;
+          if (t < nb && chok) f[t] = __ldg(a.feat + (long long)s_row[warp][t] * a.feat_ld + ch);
+        }
+#pragma unroll
+        for (int t = 0; t < 32; ++t)
+          if (t < nb) acc[qc] = fmaf(f[t], s_d[warp][t], acc[qc]);
+      }
+    }
+#pragma unroll
+    for (int qc = 0; qc < CPL; ++qc) {
+      const int ch = lane + 32 * qc;
+      if (ch < a.C) a.out[v * a.C + ch] = acc[qc];
+    }
+  }
+  lift_stamp(a.ctrl, 7);
+  // leave the control words zeroed for the next call: the last CTA to get here
+  // knows every CTA is past its final barrier wait
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(a.ctrl + 3, 1u) == G - 1) {
+      a.ctrl[0] = 0; a.ctrl[1] = 0; a.ctrl[2] = 0; a.ctrl[3] = 0; a.ctrl[4] = 0;
+      __threadfence();
     }
   }
 }
@@ -186,11 +478,11 @@ __global__ void bev_pool_v2_kernel(int c, int n_intervals, const float* __restri
 
 struct LiftWs {
   int* rank;    // [P]
+  int* slot;    // [P]
+  int* list;    // [P]
   int* count;   // [V]
   int* start;   // [V]
-  int* fill;    // [V]
-  int* list;    // [P]
-  int* cursor;  // [1] (+pad)
+  unsigned* ctrl;  // 256 bytes: grid-barrier counter, list cursor
 };
 
 inline long long align256(long long x) { return (x + 255) / 256 * 256; }
@@ -198,13 +490,45 @@ inline long long align256(long long x) { return (x + 255) / 256 * 256; }
 inline LiftWs carve(void* ws, long long P, long long V) {
   char* p = (char*)ws;
   LiftWs w;
+  w.ctrl = (unsigned*)p; p += 256;
   w.rank = (int*)p; p += align256(P * 4);
+  w.slot = (int*)p; p += align256(P * 4);
+  w.list = (int*)p; p += align256(P * 4);
   w.count = (int*)p; p += align256(V * 4);
-  w.cursor = (int*)p; p += 256;
-  w.start = (int*)p; p += align256(V * 4);
-  w.fill = (int*)p; p += align256(V * 4);
-  w.list = (int*)p;
+  w.start = (int*)p;
   return w;
+}
+
+inline LiftGeom make_geom(const float* cam, const float* bda, const float* xs, const float* ys,
+                          const float* ds, const float* lower, const float* interval, int b, int n,
+                          int d, int h, int w, int gx, int gy, int gz) {
+  LiftGeom g;
+  g.cam = cam; g.bda = bda; g.xs = xs; g.ys = ys; g.ds = ds;
+  g.lx = lower[0]; g.ly = lower[1]; g.lz = lower[2];
+  g.ix = interval[0]; g.iy = interval[1]; g.iz = interval[2];
+  g.B = b; g.N = n; g.D = d; g.H = h; g.W = w; g.gx = gx; g.gy = gy; g.gz = gz;
+  return g;
+}
+
+template <int CPL>
+int launch_lift_fused(const LiftFused& a, cudaStream_t st) {
+  // persistent grid: every CTA must be co-resident (grid barriers)
+  static int ctas_per_sm = 0, sms = 0;
+  if (ctas_per_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &ctas_per_sm, lift_fused_kernel<CPL>, LIFT_THREADS, 0);
+    if (e != cudaSuccess) return (int)e;
+    if (ctas_per_sm < 1) return PW_ERR_INVALID_ARGUMENT;
+    if (ctas_per_sm > 2) ctas_per_sm = 2;
+  }
+  // grid == resident capacity, so all CTAs are co-resident as soon as the SMs
+  // drain (same guarantee a cooperative launch checks, without its launch cost)
+  lift_fused_kernel<CPL><<<sms * ctas_per_sm, LIFT_THREADS, 0, st>>>(a);
+  PW_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace
@@ -212,7 +536,7 @@ inline LiftWs carve(void* ws, long long P, long long V) {
 PW_API long long pw_lift_workspace_bytes(int b, int n, int d, int h, int w, int gx, int gy,
                                          int gz) {
   long long P = (long long)b * n * d * h * w, V = (long long)b * gx * gy * gz;
-  return 2 * align256(P * 4) + 3 * align256(V * 4) + 256;
+  return 256 + 3 * align256(P * 4) + 2 * align256(V * 4);
 }
 
 PW_API int pw_lift_ranks(const float* cam, const float* bda, const float* xs, const float* ys,
@@ -223,8 +547,7 @@ PW_API int pw_lift_ranks(const float* cam, const float* bda, const float* xs, co
   PW_REQUIRE(P > 0 && P < (1ll << 31) && (long long)b * gx * gy * gz < (1ll << 31));
   int blocks = (int)min((long long)148 * 8, (P + 255) / 256);
   lift_rank_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-      cam, bda, xs, ys, ds, lower[0], lower[1], lower[2], interval[0], interval[1], interval[2], b,
-      n, d, h, w, gx, gy, gz, rank, nullptr);
+      make_geom(cam, bda, xs, ys, ds, lower, interval, b, n, d, h, w, gx, gy, gz), rank);
   PW_LAUNCH_CHECK(); pw_count_launch(1);
   return 0;
 }
@@ -238,34 +561,18 @@ PW_API int pw_lift_fused(const float* depth, const float* feat, int feat_ld, con
   PW_REQUIRE(c > 0 && c <= 128 && feat_ld >= c);
   long long P = (long long)b * n * d * h * w, V = (long long)b * gx * gy * gz;
   PW_REQUIRE(P > 0 && P < (1ll << 31) && V > 0 && V < (1ll << 31));
+  PW_REQUIRE((V * c) % 4 == 0 && ((uintptr_t)out & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
   LiftWs ws = carve(workspace, P, V);
-  // count[V] and cursor are contiguous: one memset
-  cudaError_t e = cudaMemsetAsync(ws.count, 0, align256(V * 4) + 256, st);
-  if (e != cudaSuccess) return (int)e;
-  int blocks = (int)min((long long)148 * 8, (P + 255) / 256);
-  lift_rank_kernel<<<blocks, 256, 0, st>>>(cam, bda, xs, ys, ds, lower[0], lower[1], lower[2],
-                                           interval[0], interval[1], interval[2], b, n, d, h, w,
-                                           gx, gy, gz, ws.rank, ws.count);
-  PW_LAUNCH_CHECK();
-  lift_offsets_kernel<<<pw_ceil_div(V, 256), 256, 0, st>>>(ws.count, ws.start, ws.cursor, ws.fill,
-                                                           (int)V);
-  PW_LAUNCH_CHECK();
-  lift_fill_kernel<<<blocks, 256, 0, st>>>(ws.rank, ws.start, ws.fill, ws.list, P);
-  PW_LAUNCH_CHECK();
-  // 8 warps/block, 32 voxels per warp-iteration; grid sized to the SM count
-  int pblocks = (int)min((long long)148 * 8, (V + 255) / 256);
-  int HW = h * w;
-  if (c <= 32)
-    lift_pool_kernel<1><<<pblocks, 256, 0, st>>>(depth, feat, feat_ld, ws.count, ws.start, ws.list,
-                                                 c, d, HW, V, out);
-  else if (c <= 64)
-    lift_pool_kernel<2><<<pblocks, 256, 0, st>>>(depth, feat, feat_ld, ws.count, ws.start, ws.list,
-                                                 c, d, HW, V, out);
-  else
-    lift_pool_kernel<4><<<pblocks, 256, 0, st>>>(depth, feat, feat_ld, ws.count, ws.start, ws.list,
-                                                 c, d, HW, V, out);
-  PW_LAUNCH_CHECK(); pw_count_launch(4);
+  LiftFused a;
+  a.g = make_geom(cam, bda, xs, ys, ds, lower, interval, b, n, d, h, w, gx, gy, gz);
+  a.depth = depth; a.feat = feat; a.feat_ld = feat_ld; a.C = c; a.out = out;
+  a.rank = ws.rank; a.slot = ws.slot; a.count = ws.count; a.start = ws.start; a.list = ws.list;
+  a.ctrl = ws.ctrl; a.P = P; a.V = V;
+  int rc = c <= 32 ? launch_lift_fused<1>(a, st)
+                   : (c <= 64 ? launch_lift_fused<2>(a, st) : launch_lift_fused<4>(a, st));
+  if (rc != 0) return rc;
+  pw_count_launch(1);
   return 0;
 }
 

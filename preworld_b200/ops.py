@@ -392,7 +392,8 @@ def lift_fused(depth, feat_cl, cam, bda, xs, ys, ds, lower, interval, b, n,
     key = (depth.device, torch.cuda.current_stream().cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(nbytes, device=depth.device, dtype=torch.uint8)
+        # control words must start zeroed; the kernel re-zeroes them on exit
+        ws = torch.zeros(nbytes, device=depth.device, dtype=torch.uint8)
         _ws_cache[key] = ws
     check(_lib.lib().pw_lift_fused(
         _ptr(depth), _ptr(feat_cl), cl_ld(feat_cl), _ptr(cam), _ptr(bda),
