@@ -40,6 +40,12 @@ __device__ __forceinline__ float pw_activate(float v, int act) {
   }
 }
 
+// out-of-line variant for epilogues that are almost always ReLU / none: keeps
+// the transcendental code out of the unrolled store loops
+__device__ __noinline__ static float pw_activate_slow(float v, int act) {
+  return pw_activate(v, act);
+}
+
 __device__ __forceinline__ float4 pw_ldg4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
 }

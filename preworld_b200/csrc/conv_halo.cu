@@ -63,6 +63,7 @@ struct HaloParams {
   int nacc;                    // accumulator copies per M tile (k-step k -> copy k % nacc):
                                // independent MMA chains hide the accumulate latency at small N
   int tmem_cols;
+  int cps;                     // CTAs per SM the plan counts on (1 or 2)
   int dbg;                     // PW_HALO_DBG knock-out bits (timing experiments only)
   long long* ts;               // PW_HALO_TS: per-CTA clock64 milestones (debug)
   int out_ld, res_ld, act, act_channels;
@@ -74,7 +75,8 @@ struct HaloParams {
 
 #define PW_TS(k) do { if (p.ts) p.ts[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (k)] = clock64(); } while (0)
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int MIN_CTAS>   // 2: register-capped variant so two CTAs fit one SM
+__global__ void __launch_bounds__(NUM_THREADS, MIN_CTAS)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
                  const __grid_constant__ CUtensorMap map_bh,
                  const __grid_constant__ CUtensorMap map_bl, const HaloParams p) {
@@ -238,6 +240,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     const int rz = R >> (p.lbx + p.lby);
     const int row_base = ((rz * p.sd) * p.hy + ry * p.sh) * p.hx + rx * p.sw;
     const uint32_t a_ring = tmem_base + lane_field + a_ring_col;
+    const uint32_t smem_base_u32 = smem_u32(smem);
 
     // Iteration state, advanced incrementally (no divisions in the loop):
     // it = (c*T + t)*mt + m; this set takes it = set, set+SETS, ...
@@ -260,11 +263,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     auto load_row = [&](const It& s, float4 (&raw)[8]) {
       const int hrow = row_base + s.m * p.mt_halo_off +
                        ((s.kz * p.dd) * p.hy + s.ky * p.dh) * p.hx + s.kx * p.dw;
-      const uint8_t* src = smem + (size_t)s.hs * p.halo_stride + (size_t)hrow * ROW_BYTES;
+      const uint32_t src = smem_base_u32 + (uint32_t)(s.hs * p.halo_stride + hrow * ROW_BYTES);
       const int swz = hrow & 7;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        raw[j] = *reinterpret_cast<const float4*>(src + ((j ^ swz) << 4));
+      for (int j = 0; j < 8; ++j) raw[j] = lds128(src + ((j ^ swz) << 4));
     };
 
     It cur{0, 0, 0, 0, 0, 0, 0, 1u, 0u};               // eph = parity to wait on ring_empty
@@ -335,7 +337,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     if (sw_id == 0 && lane == 0) PW_TS(7);
-    float4* stage = reinterpret_cast<float4*>(smem + (size_t)sw_id * STAGE_BYTES_PER_WARP);
+    const uint32_t stage = smem_base_u32 + (uint32_t)(sw_id * STAGE_BYTES_PER_WARP);
     const int ncg = (p.n_tile + 31) >> 5;
     const int items = p.mt * ncg;
     const int act_end = p.act_channels > 0 ? p.act_channels : p.cout;
@@ -343,6 +345,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
                         (p.res == nullptr || ((p.res_ld & 3) == 0 &&
                                               (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
     const int ch4 = lane & 7;
+    // pixel index (within the output tensor) of the 8 rows this lane stores, for
+    // M tile 0; tile m adds m * mt_pix.  -1 = outside the output.
+    int rowpix[2][8];
+#pragma unroll
+    for (int mm = 0; mm < 2; ++mm) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int Rr = q * 32 + i * 4 + (lane >> 3);
+        int ox = x0 + (Rr & (p.bx - 1));
+        int oy = y0 + ((Rr >> p.lbx) & (p.by - 1));
+        int oz = z0 + (Rr >> (p.lbx + p.lby));
+        if (p.mt_axis == 0) ox += mm * p.bx;
+        else if (p.mt_axis == 1) oy += mm * p.by;
+        else oz += mm * p.bz;
+        const bool ok = mm < p.mt && ox < p.ow && oy < p.oh && oz < p.od;
+        rowpix[mm][i] = ok ? ((img * p.od + oz) * p.oh + oy) * p.ow + ox : -1;
+      }
+    }
+    if (sw_id == 0 && lane == 0) PW_TS(2);
     for (int item = set; item < items; item += SPLIT_SETS) {
       const int m = item / ncg;
       const int col0 = (item - m * ncg) * 32;
@@ -359,15 +380,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
           tmem_ld16_nowait(taddr, a);
           tmem_ld16_nowait(taddr + p.n_tile, b);
           tmem_ld_wait();
+          if (item == set && half == 0 && sw_id == 0 && lane == 0) PW_TS(5);
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(a[j]) + __uint_as_float(b[j]);
         }
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4)
-          stage[lane * 8 + ((half * 4 + j4) ^ (lane & 7))] =
-              make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
+          sts128(stage + (uint32_t)((lane * 8 + ((half * 4 + j4) ^ (lane & 7))) << 4),
+                 make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]));
       }
       __syncwarp();
+      if (item == set && sw_id == 0 && lane == 0) PW_TS(10);
       // phase 2: lane -> (row group, 4 channels); 8 lanes cover one 128-byte row
       const int cbase = n0 + col0 + ch4 * 4;
       if (ch4 * 4 < ncol && cbase < p.cout) {
@@ -380,45 +403,40 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
         }
         const int a_ = (cbase < act_end) ? p.act : PW_ACT_NONE;     // act_end % 4 == 0
         const bool vec = vec_ok && cbase + 4 <= p.cout;
-#pragma unroll 2
+#pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = i * 4 + (lane >> 3);
-          const int Rr = q * 32 + r;
-          int ox = x0 + (Rr & (p.bx - 1));
-          int oy = y0 + ((Rr >> p.lbx) & (p.by - 1));
-          int oz = z0 + (Rr >> (p.lbx + p.lby));
-          if (p.mt_axis == 0) ox += m * p.bx;
-          else if (p.mt_axis == 1) oy += m * p.by;
-          else oz += m * p.bz;
-          if (ox >= p.ow || oy >= p.oh || oz >= p.od) continue;
-          const float4 v4 = stage[r * 8 + (ch4 ^ (r & 7))];
-          float v[4] = {fmaf(v4.x, sc[0], bi[0]), fmaf(v4.y, sc[1], bi[1]),
-                        fmaf(v4.z, sc[2], bi[2]), fmaf(v4.w, sc[3], bi[3])};
-          const size_t pix = (((size_t)img * p.od + oz) * p.oh + oy) * p.ow + ox;
-          float* yrow = p.y + pix * p.out_ld + cbase;
-          const float* rrow = p.res ? p.res + pix * p.res_ld + cbase : nullptr;
+          const int pixi = m == 0 ? rowpix[0][i] : rowpix[1][i];
+          if (pixi < 0) continue;
+          const float4 v4 = lds128(stage + (uint32_t)((r * 8 + (ch4 ^ (r & 7))) << 4));
+          float va = fmaf(v4.x, sc[0], bi[0]), vb = fmaf(v4.y, sc[1], bi[1]);
+          float vc = fmaf(v4.z, sc[2], bi[2]), vd = fmaf(v4.w, sc[3], bi[3]);
+          float* yrow = p.y + (size_t)pixi * p.out_ld + cbase;
+          const float* rrow = p.res ? p.res + (size_t)pixi * p.res_ld + cbase : nullptr;
           if (vec) {
             if (rrow) {
               const float4 rr = pw_ldg4(rrow);
-              v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+              va += rr.x; vb += rr.y; vc += rr.z; vd += rr.w;
             }
-            if (a_ == PW_ACT_RELU) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
-            } else if (a_ != PW_ACT_NONE) {
-#pragma unroll 1
-              for (int e = 0; e < 4; ++e) v[e] = pw_activate(v[e], a_);
-            }
-            *reinterpret_cast<float4*>(yrow) = make_float4(v[0], v[1], v[2], v[3]);
+          } else if (rrow) {
+            va += __ldg(rrow);
+            if (cbase + 1 < p.cout) vb += __ldg(rrow + 1);
+            if (cbase + 2 < p.cout) vc += __ldg(rrow + 2);
+            if (cbase + 3 < p.cout) vd += __ldg(rrow + 3);
+          }
+          if (a_ == PW_ACT_RELU) {
+            va = fmaxf(va, 0.f); vb = fmaxf(vb, 0.f); vc = fmaxf(vc, 0.f); vd = fmaxf(vd, 0.f);
+          } else if (a_ != PW_ACT_NONE) {
+            va = pw_activate_slow(va, a_); vb = pw_activate_slow(vb, a_);
+            vc = pw_activate_slow(vc, a_); vd = pw_activate_slow(vd, a_);
+          }
+          if (vec) {
+            *reinterpret_cast<float4*>(yrow) = make_float4(va, vb, vc, vd);
           } else {
-#pragma unroll 1
-            for (int e = 0; e < 4; ++e) {
-              if (cbase + e < p.cout) {
-                float tv = v[e];
-                if (rrow) tv += __ldg(rrow + e);
-                yrow[e] = pw_activate(tv, a_);
-              }
-            }
+            yrow[0] = va;
+            if (cbase + 1 < p.cout) yrow[1] = vb;
+            if (cbase + 2 < p.cout) yrow[2] = vc;
+            if (cbase + 3 < p.cout) yrow[3] = vd;
           }
         }
       }
@@ -478,6 +496,7 @@ HaloPlan make_plan(const pw_conv_desc& in) {
   for (int ntry = 0; ntry < 3; ++ntry) {
     const int n_tile = ntry == 0 ? n_full : (ntry == 1 ? 64 : 32);
     if (ntry > 0 && n_tile >= n_full) continue;
+    if (const char* e = getenv("PW_HALO_NT")) { if (atoi(e) != n_tile && atoi(e) < n_full) continue; }
     const int slabs = pw_ceil_div(c.cout, n_tile);
     const int b_stage = 2 * n_tile * ROW_BYTES;
     for (int bi = 0; bi < nboxes; ++bi) {
@@ -531,8 +550,16 @@ HaloPlan make_plan(const pw_conv_desc& in) {
           const double per_ct = 430.0 + mt * 4.0 * kstep;
           double cta = chunks * (T * per_ct + (nh > 1 ? 0.25 : 1.0) * hrows * 2.0) + 3000.0 +
                        mt * n_tile * 40.0;
-          const double waves = (double)((tiles + 147) / 148);
-          const double cost = waves * cta;
+          // co-resident CTAs (TMEM columns and shared memory permitting) overlap one
+          // CTA's prologue / epilogue with the other's main loop
+          int cols_need = acc_cols + nb * mt * A_SLOT_COLS, tcols = 32;
+          while (tcols < cols_need) tcols <<= 1;
+          const long long smem_cta = smem_need(nh, nb);
+          int cps = min(512 / tcols, (int)((228 * 1024 - 1024) / (smem_cta + 1024)));
+          cps = max(1, min(cps, 2));
+          if (const char* e = getenv("PW_HALO_CPS")) cps = min(cps, max(1, atoi(e)));
+          const double waves = (double)((tiles + 148 * cps - 1) / (148 * cps));
+          const double cost = waves * cta * (cps == 2 ? 1.3 : 1.0);
           if (best < 0 || cost < best) {
             best = cost;
             HaloParams& p = plan.p;
@@ -552,6 +579,7 @@ HaloPlan make_plan(const pw_conv_desc& in) {
             int cols = acc_cols + nb * mt * A_SLOT_COLS, pw2 = 32;
             while (pw2 < cols) pw2 <<= 1;
             p.tmem_cols = pw2;
+            p.cps = cps;
             plan.smem = (size_t)p.halo_region + (size_t)nb * b_stage + SMEM_SLACK;
             plan.grid = dim3((unsigned)(tiles / slabs), (unsigned)slabs);
             plan.ok = true;
@@ -629,8 +657,11 @@ PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* 
 
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<1>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SMEM_LIMIT / 2);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
@@ -640,7 +671,10 @@ PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* 
     cudaMalloc(&p.ts, n_cta * 16 * sizeof(long long));
     cudaMemset(p.ts, 0, n_cta * 16 * sizeof(long long));
   }
-  conv_halo_kernel<<<plan.grid, NUM_THREADS, plan.smem, st>>>(ma, mbh, mbl, p);
+  if (p.cps == 2)
+    conv_halo_kernel<2><<<plan.grid, NUM_THREADS, plan.smem, st>>>(ma, mbh, mbl, p);
+  else
+    conv_halo_kernel<1><<<plan.grid, NUM_THREADS, plan.smem, st>>>(ma, mbh, mbl, p);
   PW_LAUNCH_CHECK();
   if (want_ts) {
     cudaStreamSynchronize(st);
@@ -649,9 +683,9 @@ PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* 
     double sum[16] = {0};
     for (size_t i = 0; i < n_cta; ++i)
       for (int k = 0; k < 16; ++k) sum[k] += (double)(h[i * 16 + k] - h[i * 16]);
-    fprintf(stderr, "[halo ts] grid %u x %u mt %d n_tile %d nh %d nb %d nacc %d box %dx%dx%d halo %dx%dx%d smem %zu tmem %d:",
+    fprintf(stderr, "[halo ts] grid %u x %u mt %d n_tile %d nh %d nb %d nacc %d box %dx%dx%d halo %dx%dx%d smem %zu tmem %d cps %d:",
             plan.grid.x, plan.grid.y, p.mt, p.n_tile, p.nh, p.nb, p.nacc, p.cbx, p.cby, p.cbz,
-            p.hx, p.hy, p.hz, plan.smem, p.tmem_cols);
+            p.hx, p.hy, p.hz, plan.smem, p.tmem_cols, p.cps);
     for (int k = 0; k < 15; ++k) fprintf(stderr, " t%d=%.0f", k, sum[k] / n_cta);
     fprintf(stderr, "\n");
     free(h);
