@@ -214,15 +214,20 @@ def linear(x2d, pc, act=None, residual=None, out=None):
 
 
 # ---------------------------------------------------------------- image side
-def nchw_to_nhwc(x, c_pad=None):
+def nchw_to_nhwc(x, c_pad=None, out=None):
     """x [n,c,h,w]: each image dense NCHW; images may be strided (a frame
-    slice of the loader's camera-major batch)."""
+    slice of the loader's camera-major batch).  ``out``: dense [n,h,w,c_pad]
+    destination (e.g. a batch slice of a larger buffer)."""
     _require_cuda(x)
     n, c, h, w = x.shape
     if x.stride()[1:] != (h * w, w, 1):
         raise ValueError(f'images must be dense CHW planes, got {x.stride()}')
     c_pad = c_pad or c
-    y = torch.empty((n, h, w, c_pad), device=x.device, dtype=torch.float32)
+    if out is None:
+        y = torch.empty((n, h, w, c_pad), device=x.device, dtype=torch.float32)
+    else:
+        assert out.shape == (n, h, w, c_pad) and out.is_contiguous()
+        y = out
     img_stride = x.stride(0) if n > 1 else c * h * w
     check(_lib.lib().pw_nchw_to_nhwc_pad(_ptr(x), img_stride, _ptr(y), n, c,
                                          h, w, c_pad, _stream()),

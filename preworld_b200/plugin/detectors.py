@@ -181,12 +181,51 @@ class BEVStereo4DOCC(BaseModule):
         return x
 
     # -- bevdet_occ.py:141-165 ------------------------------------------------
+    def encode_frames(self, imgs):
+        """Image side of ALL frames in two batched passes (the reference runs
+        frame by frame, bevdet_occ.py:219-240; the weights are shared, so the
+        result is the same): stem + layer1 on every image (the stereo
+        features, bevdet.py:573-588), layers 2.. + neck on the frames that are
+        lifted.  Returns per-frame lists (x [B,N,C,h,w] or None, stereo)."""
+        nf = len(imgs)
+        B, N, C, imH, imW = imgs[0].shape
+        bn = B * N
+        bb = self.img_backbone
+        if not (hasattr(bb, 'run_stem_cl') and 0 in bb.out_indices):
+            return None
+        cin = bb.packs()['stem'].cin
+        x_all = torch.empty((nf * bn, imH, imW, cin), device=imgs[0].device,
+                            dtype=torch.float32)
+        for f in range(nf):
+            ops.nchw_to_nhwc(imgs[f].reshape(bn, C, imH, imW), cin,
+                             out=x_all[f * bn:(f + 1) * bn])
+        l1 = bb.run_layer(0, bb.run_stem_cl(x_all))          # [nf*bn,h4,w4,256]
+        n_full = nf - self.extra_ref_frames                   # frames 0..n_full-1
+        x = bb.run_from_layer(1, l1[:n_full * bn])
+        if self.with_img_neck:
+            x = self.img_neck(tuple(x))      # stereo=True: x[0] (layer1) is split off
+            if type(x) in [list, tuple]:
+                x = x[0]
+        _, cdim, oh, ow = x.shape
+        feats, stereo = [], []
+        for f in range(nf):
+            stereo.append(ops.to_logical(l1[f * bn:(f + 1) * bn]))
+            feats.append(x[f * bn:(f + 1) * bn].view(B, N, cdim, oh, ow)
+                         if f < n_full else None)
+        return feats, stereo
+
     def prepare_bev_feat(self, img, sensor2keyego, ego2global, intrin,
                          post_rot, post_tran, bda, mlp_input, feat_prev_iv,
-                         k2s_sensor, extra_ref_frame, depth_gt=None):
-        if extra_ref_frame:
+                         k2s_sensor, extra_ref_frame, depth_gt=None,
+                         encoded=None):
+        if encoded is not None:
+            x, stereo_feat = encoded
+            if extra_ref_frame:
+                return None, None, stereo_feat
+        elif extra_ref_frame:
             return None, None, self.extract_stereo_ref_feat(img)
-        x, stereo_feat = self.image_encoder(img, stereo=True)
+        else:
+            x, stereo_feat = self.image_encoder(img, stereo=True)
         vt = self.img_view_transformer
         metas = dict(k2s_sensor=k2s_sensor, intrins=intrin,
                      post_rots=post_rot, post_trans=post_tran,
@@ -218,6 +257,7 @@ class BEVStereo4DOCC(BaseModule):
         depth_key_frame = None
         feat_prev_iv = None
         vt = self.img_view_transformer
+        enc = self.encode_frames(imgs)
         for fid in range(self.num_frame - 1, -1, -1):
             key_frame = fid == 0
             extra_ref_frame = fid == self.num_frame - self.extra_ref_frames
@@ -227,7 +267,8 @@ class BEVStereo4DOCC(BaseModule):
             bev_feat, depth, feat_curr_iv = self.prepare_bev_feat(
                 imgs[fid], sensor2keyegos[fid], ego2globals[fid],
                 intrins[fid], post_rots[fid], post_trans[fid], bda, mlp_input,
-                feat_prev_iv, curr2adjsensor[fid], extra_ref_frame)
+                feat_prev_iv, curr2adjsensor[fid], extra_ref_frame,
+                encoded=(enc[0][fid], enc[1][fid]) if enc else None)
             if key_frame:
                 depth_key_frame = depth
             if not extra_ref_frame:

@@ -136,9 +136,21 @@ class ResNet(BaseModule):
     def run_stem(self, img_nchw):
         """NCHW image batch -> cl array after conv1/bn1/relu/maxpool."""
         p = self.packs()
-        x = ops.nchw_to_nhwc(img_nchw, p['stem'].cin)
-        x = ops.conv(x, p['stem'], 'relu')
+        return self.run_stem_cl(ops.nchw_to_nhwc(img_nchw, p['stem'].cin))
+
+    def run_stem_cl(self, x_cl):
+        """channels-last (zero-padded to the packed stem cin) image batch."""
+        x = ops.conv(x_cl, self.packs()['stem'], 'relu')
         return ops.maxpool3x3s2(x)
+
+    def run_from_layer(self, i0, x):
+        """layers i0.. on a cl array -> logical maps for out_indices >= i0."""
+        outs = []
+        for i in range(i0, len(self.res_layers)):
+            x = self.run_layer(i, x)
+            if i in self.out_indices:
+                outs.append(ops.to_logical(x))
+        return tuple(outs)
 
     def run_layer(self, i, x):
         p = self.packs()
