@@ -43,8 +43,13 @@ cost_volume_kernel(const float* __restrict__ curr, const float* __restrict__ pre
   const int own_q = (C - 4) / 128, own_lane = ((C - 4) % 128) / 4;
   const float* pimg = prev + (long long)img * H * W * C;
 
-  float my_cost[4] = {0.f, 0.f, 0.f, 0.f};   // bins lane, lane+32, lane+64, lane+96
-  for (int d = 0; d < D; ++d) {
+  // ---- sampling geometry: lane l computes depth bins l, l+32, l+64, l+96 once
+  // (cell + bilinear weights); the gather loop below fetches them by shuffle ----
+  int gx0[4], gy0[4];
+  float gw[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int d = min(k * 32 + lane, D - 1);
     float pz = __ldg(ds + d) - cm[11];
     float qx = dot3(cm + 0, fx, fy, pz), qy = dot3(cm + 3, fx, fy, pz), qz = dot3(cm + 6, fx, fy, pz);
     qx *= qz; qy *= qz;
@@ -62,42 +67,86 @@ cost_volume_kernel(const float* __restrict__ curr, const float* __restrict__ pre
     float ix = ((gx + 1.f) * 0.5f) * (float)(W - 1);
     float iy = ((gy + 1.f) * 0.5f) * (float)(H - 1);
     float x0f = floorf(ix), y0f = floorf(iy);
-    float wnw = (x0f + 1.f - ix) * (y0f + 1.f - iy);
-    float wne = (ix - x0f) * (y0f + 1.f - iy);
-    float wsw = (x0f + 1.f - ix) * (iy - y0f);
-    float wse = (ix - x0f) * (iy - y0f);
+    gw[k][0] = (x0f + 1.f - ix) * (y0f + 1.f - iy);
+    gw[k][1] = (ix - x0f) * (y0f + 1.f - iy);
+    gw[k][2] = (x0f + 1.f - ix) * (iy - y0f);
+    gw[k][3] = (ix - x0f) * (iy - y0f);
     // clamp before the int cast so far-away samples cannot overflow
-    int x0 = (int)fminf(fmaxf(x0f, -2.f), (float)W + 1.f);
-    int y0 = (int)fminf(fmaxf(y0f, -2.f), (float)H + 1.f);
-    bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
-    bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
-    const float* r00 = pimg + ((long long)y0 * W + x0) * C;
-    float part = 0.f;
-    bool zero_flag = false;
+    gx0[k] = (int)fminf(fmaxf(x0f, -2.f), (float)W + 1.f);
+    gy0[k] = (int)fminf(fmaxf(y0f, -2.f), (float)H + 1.f);
+  }
+
+  // ---- gather.  The four corner rows of the current bilinear cell stay in
+  // registers: consecutive depth bins mostly fall into the same or the
+  // neighbouring cell of the epipolar line (out-of-image corners are zeros,
+  // which is what grid_sample's zero padding contributes). ---------------------
+  float4 c00[Q], c01[Q], c10[Q], c11[Q];
+  int cx = -1000000, cy = -1000000;
+  auto load_corner = [&](int x, int y, float4 (&dst)[Q]) {
+    const bool ok = (unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H;
+    const float* r = pimg + ((long long)y * W + x) * C + lane * 4;
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const int off = q * 128 + lane * 4;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (vy0 && vx0) { float4 v = pw_ldg4(r00 + off);
-        acc.x = v.x * wnw; acc.y = v.y * wnw; acc.z = v.z * wnw; acc.w = v.w * wnw; }
-      if (vy0 && vx1) { float4 v = pw_ldg4(r00 + C + off);
-        acc.x = fmaf(v.x, wne, acc.x); acc.y = fmaf(v.y, wne, acc.y);
-        acc.z = fmaf(v.z, wne, acc.z); acc.w = fmaf(v.w, wne, acc.w); }
-      if (vy1 && vx0) { float4 v = pw_ldg4(r00 + (long long)W * C + off);
-        acc.x = fmaf(v.x, wsw, acc.x); acc.y = fmaf(v.y, wsw, acc.y);
-        acc.z = fmaf(v.z, wsw, acc.z); acc.w = fmaf(v.w, wsw, acc.w); }
-      if (vy1 && vx1) { float4 v = pw_ldg4(r00 + (long long)W * C + C + off);
-        acc.x = fmaf(v.x, wse, acc.x); acc.y = fmaf(v.y, wse, acc.y);
-        acc.z = fmaf(v.z, wse, acc.z); acc.w = fmaf(v.w, wse, acc.w); }
-      part += ((fabsf(cur[q].x - acc.x) + fabsf(cur[q].y - acc.y)) + fabsf(cur[q].z - acc.z)) +
-              fabsf(cur[q].w - acc.w);
-      if (q == own_q && lane == own_lane) zero_flag = (acc.x == 0.f);
+    for (int q = 0; q < Q; ++q)
+      dst[q] = ok ? pw_ldg4(r + q * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto copy = [&](float4 (&dst)[Q], const float4 (&src)[Q]) {
+#pragma unroll
+    for (int q = 0; q < Q; ++q) dst[q] = src[q];
+  };
+
+  float my_cost[4] = {0.f, 0.f, 0.f, 0.f};   // bins lane, lane+32, lane+64, lane+96
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k * 32 >= D) break;
+    const int dn = min(32, D - k * 32);
+    for (int dl = 0; dl < dn; ++dl) {
+      const int x0 = __shfl_sync(0xffffffffu, gx0[k], dl);
+      const int y0 = __shfl_sync(0xffffffffu, gy0[k], dl);
+      const float wnw = __shfl_sync(0xffffffffu, gw[k][0], dl);
+      const float wne = __shfl_sync(0xffffffffu, gw[k][1], dl);
+      const float wsw = __shfl_sync(0xffffffffu, gw[k][2], dl);
+      const float wse = __shfl_sync(0xffffffffu, gw[k][3], dl);
+      if (x0 != cx || y0 != cy) {                      // warp-uniform
+        if (y0 == cy && x0 == cx + 1) {
+          copy(c00, c01); copy(c10, c11);
+          load_corner(x0 + 1, y0, c01); load_corner(x0 + 1, y0 + 1, c11);
+        } else if (y0 == cy && x0 == cx - 1) {
+          copy(c01, c00); copy(c11, c10);
+          load_corner(x0, y0, c00); load_corner(x0, y0 + 1, c10);
+        } else if (x0 == cx && y0 == cy + 1) {
+          copy(c00, c10); copy(c01, c11);
+          load_corner(x0, y0 + 1, c10); load_corner(x0 + 1, y0 + 1, c11);
+        } else if (x0 == cx && y0 == cy - 1) {
+          copy(c10, c00); copy(c11, c01);
+          load_corner(x0, y0, c00); load_corner(x0 + 1, y0, c01);
+        } else {
+          load_corner(x0, y0, c00); load_corner(x0 + 1, y0, c01);
+          load_corner(x0, y0 + 1, c10); load_corner(x0 + 1, y0 + 1, c11);
+        }
+        cx = x0; cy = y0;
+      }
+      float part = 0.f;
+      bool zero_flag = false;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        float4 acc;
+        acc.x = c00[q].x * wnw; acc.y = c00[q].y * wnw; acc.z = c00[q].z * wnw; acc.w = c00[q].w * wnw;
+        acc.x = fmaf(c01[q].x, wne, acc.x); acc.y = fmaf(c01[q].y, wne, acc.y);
+        acc.z = fmaf(c01[q].z, wne, acc.z); acc.w = fmaf(c01[q].w, wne, acc.w);
+        acc.x = fmaf(c10[q].x, wsw, acc.x); acc.y = fmaf(c10[q].y, wsw, acc.y);
+        acc.z = fmaf(c10[q].z, wsw, acc.z); acc.w = fmaf(c10[q].w, wsw, acc.w);
+        acc.x = fmaf(c11[q].x, wse, acc.x); acc.y = fmaf(c11[q].y, wse, acc.y);
+        acc.z = fmaf(c11[q].z, wse, acc.z); acc.w = fmaf(c11[q].w, wse, acc.w);
+        part += ((fabsf(cur[q].x - acc.x) + fabsf(cur[q].y - acc.y)) + fabsf(cur[q].z - acc.z)) +
+                fabsf(cur[q].w - acc.w);
+        if (q == own_q && lane == own_lane) zero_flag = (acc.x == 0.f);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      zero_flag = __shfl_sync(0xffffffffu, (int)zero_flag, own_lane) != 0;
+      if (bias != 0.f && zero_flag) part += bias;
+      if (dl == lane) my_cost[k] = part;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    zero_flag = __shfl_sync(0xffffffffu, (int)zero_flag, own_lane) != 0;
-    if (bias != 0.f && zero_flag) part += bias;
-    if ((d & 31) == lane) my_cost[d >> 5] = part;
   }
 
   // softmax over D of -cost
