@@ -137,13 +137,14 @@ int pw_softmax_depth(const float* logits, int in_ld, float* prob_cl,
  *   curr/prev: [n,h,w,c] channels-last stereo features (c % 4 == 0);
  *   cam: [n, PW_CV_CAM_FLOATS] per-camera constants built by the host
  *   (inv(post_rot), post_tran, k2s_rot @ inv(K), k2s_tran, K, post_rot[:2,:2],
- *   post_tran[:2]);  frustum x/y/depth values; out: [n,h,w,d] channels-last.
+ *   post_tran[:2]);  frustum x/y/depth values; out: [n,h,w,out_ld] channels-last,
+ *   channels [d, out_ld) written as zeros (padding for a 32-multiple Cin).
  * ---------------------------------------------------------------------- */
 #define PW_CV_CAM_FLOATS 48
 int pw_cost_volume(const float* curr, const float* prev, const float* cam,
                    const float* xs, const float* ys, const float* ds, float* out,
-                   int n, int h, int w, int c, int d, float bias, int img_h,
-                   int img_w, void* stream);
+                   int out_ld, int n, int h, int w, int c, int d, float bias,
+                   int img_h, int img_w, void* stream);
 
 /* ------------------------------------------------------------------------
  * Voxel lift.

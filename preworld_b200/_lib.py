@@ -62,7 +62,7 @@ SIGNATURES = {
     'pw_broadcast_channels': [c_p, c_p, c_int, c_int, c_ll, c_int, c_p],
     'pw_softmax_depth': [c_p, c_int, c_p, c_p, c_int, c_ll, c_int, c_p],
     'pw_cost_volume': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int,
-                       c_int, c_int, c_f, c_int, c_int, c_p],
+                       c_int, c_int, c_int, c_f, c_int, c_int, c_p],
     'pw_bev_pool_v2': [c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
                        c_p],
     'pw_lift_camera_params': [c_int, c_p, c_p, c_p, c_p, c_p, c_p],

@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include "../../include/preworld_b200.h"
 
 namespace {
@@ -185,62 +186,77 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
   const int n0 = blockIdx.y * p.n_tile;
   const int KT = p.n_taps * p.chunks;
 
+  // Warps 4 and 5 run their loops warp-converged; only the TMA / MMA / commit
+  // instruction is issued by one elected lane (a loop under `if (lane == 0)`
+  // turns every uniform-register operand into a waterfall loop).
   if (warp == 4) {
-    // ===================== TMA producer (one lane) ==========================
-    if (lane == 0) {
-      const uint32_t tx_bytes = A_BYTES + 2 * b_bytes;
-      for (int it = 0; it < KT; ++it) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_expect_tx(full_bar(s), tx_bytes);
-        const int tap = it / p.chunks;
-        const int c0 = (it - tap * p.chunks) * BLOCK_K;
-        const int kx = tap % p.taps_w;
-        const int t2 = tap / p.taps_w;
-        const int ky = t2 % p.taps_h;
-        const int kz = t2 / p.taps_h;
-        const uint32_t a_dst = smem_u32(smem + (size_t)s * stage_bytes);
-        tma_load_5d(a_dst, &map_a, full_bar(s), c0, x0 * p.sw - p.pw + kx * p.dw,
-                    y0 * p.sh - p.ph + ky * p.dh, z0 * p.sd - p.pd + kz * p.dd, img);
-        tma_load_2d(a_dst + 2 * A_BYTES, &map_bh, full_bar(s), it * BLOCK_K, n0);
-        tma_load_2d(a_dst + 2 * A_BYTES + b_bytes, &map_bl, full_bar(s), it * BLOCK_K, n0);
+    // ===================== TMA producer =====================================
+    const bool leader = pwtc::elect_one();
+    const uint32_t tx_bytes = A_BYTES + 2 * b_bytes;
+    const uint32_t smem0 = smem_u32(smem);
+    int s = 0;
+    uint32_t ph = 1;
+    int it = 0;
+    for (int tap = 0; tap < p.n_taps; ++tap) {
+      const int kx = tap % p.taps_w;
+      const int t2 = tap / p.taps_w;
+      const int ky = t2 % p.taps_h;
+      const int kz = t2 / p.taps_h;
+      const int ax = x0 * p.sw - p.pw + kx * p.dw, ay = y0 * p.sh - p.ph + ky * p.dh,
+                az = z0 * p.sd - p.pd + kz * p.dd;
+      for (int c = 0; c < p.chunks; ++c, ++it) {
+        mbar_wait(empty_bar(s), ph);
+        if (leader) {
+          mbar_expect_tx(full_bar(s), tx_bytes);
+          const uint32_t a_dst = smem0 + (uint32_t)(s * stage_bytes);
+          tma_load_5d(a_dst, &map_a, full_bar(s), c * BLOCK_K, ax, ay, az, img);
+          tma_load_2d(a_dst + 2 * A_BYTES, &map_bh, full_bar(s), it * BLOCK_K, n0);
+          tma_load_2d(a_dst + 2 * A_BYTES + b_bytes, &map_bl, full_bar(s), it * BLOCK_K, n0);
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 5) {
-    // ===================== MMA issuer (one lane) ============================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=tf32, K-major both, N, M=128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) |
-                             ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-      for (int it = 0; it < KT; ++it) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        mbar_wait(full_bar(s), ph);
-        mbar_wait(ready_bar(s), ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t a_lo = a_hi + A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * A_BYTES;
-        const uint32_t b_lo = b_hi + b_bytes;
+    // ===================== MMA issuer =======================================
+    const bool leader = pwtc::elect_one();
+    // instruction descriptor: D=f32, A=B=tf32, K-major both, N, M=128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) |
+                           ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t tcorr = tbase + (uint32_t)p.n_tile;
+    const uint64_t desc0 = umma_desc(smem_u32(smem));
+    const uint32_t dstage = (uint32_t)(stage_bytes >> 4);
+    const uint32_t d_alo = (uint32_t)(A_BYTES >> 4), d_bhi = (uint32_t)(2 * A_BYTES >> 4),
+                   d_blo = (uint32_t)((2 * A_BYTES + b_bytes) >> 4);
+    int s = 0;
+    uint32_t ph = 0, acc = 0;
+    for (int it = 0; it < KT; ++it) {
+      mbar_wait(full_bar(s), ph);
+      mbar_wait(ready_bar(s), ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint64_t a_hi = desc0 + (uint64_t)(dstage * (uint32_t)s);
+      if (leader) {
 #pragma unroll
         for (int k = 0; k < BLOCK_K / 8; ++k) {
-          const uint32_t off = k * 32;       // 8 tf32 = 32 bytes inside the swizzle row
+          const uint64_t off = (uint64_t)(k * 2);   // 8 tf32 = 32 bytes inside the swizzle row
           // The tensor core truncates (does not round) when it adds into the
           // fp32 accumulator, a bias that grows with the number of
           // accumulations.  The two correction terms (2^-11 of the main term)
           // go to a second accumulator so the main one sees a third of the
           // adds; the epilogue sums the two in fp32.
-          umma_tf32(tmem_corr, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc,
-                    (it | k) != 0);
-          umma_tf32(tmem_corr, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1);
-          umma_tf32(tmem_base, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc,
-                    (it | k) != 0);
+          umma_tf32(tcorr, a_hi + d_alo + off, a_hi + d_bhi + off, idesc, k == 0 ? acc : 1u);
+          umma_tf32(tcorr, a_hi + off, a_hi + d_blo + off, idesc, 1);
+          umma_tf32(tbase, a_hi + off, a_hi + d_bhi + off, idesc, k == 0 ? acc : 1u);
         }
         umma_commit(empty_bar(s));           // frees the stage when the MMAs retire
       }
-      umma_commit(accum_bar);
+      __syncwarp();
+      acc = 1;
+      if (++s == S) { s = 0; ph ^= 1; }
     }
+    if (leader) umma_commit(accum_bar);
+    __syncwarp();
   } else {
     // ===================== split warps, then epilogue =======================
     for (int it = 0; it < KT; ++it) {

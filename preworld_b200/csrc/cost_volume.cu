@@ -22,8 +22,8 @@ __global__ void __launch_bounds__(256)
 cost_volume_kernel(const float* __restrict__ curr, const float* __restrict__ prev,
                    const float* __restrict__ cam, const float* __restrict__ xs,
                    const float* __restrict__ ys, const float* __restrict__ ds,
-                   float* __restrict__ out, int n, int H, int W, int C, int D, float bias,
-                   float wi_m1, float hi_m1) {
+                   float* __restrict__ out, int out_ld, int n, int H, int W, int C, int D,
+                   float bias, float wi_m1, float hi_m1) {
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long total = (long long)n * H * W;
@@ -166,26 +166,27 @@ cost_volume_kernel(const float* __restrict__ curr, const float* __restrict__ pre
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
 #pragma unroll
   for (int k = 0; k < 4; ++k)
-    if (k * 32 + lane < D) out[warp * D + k * 32 + lane] = e[k] / s;
+    if (k * 32 + lane < out_ld)                      // channels [D, out_ld) are zero padding
+      out[warp * out_ld + k * 32 + lane] = (k * 32 + lane < D) ? e[k] / s : 0.f;
 }
 
 }  // namespace
 
 PW_API int pw_cost_volume(const float* curr, const float* prev, const float* cam, const float* xs,
-                          const float* ys, const float* ds, float* out, int n, int h, int w, int c,
-                          int d, float bias, int img_h, int img_w, void* stream) {
+                          const float* ys, const float* ds, float* out, int out_ld, int n, int h,
+                          int w, int c, int d, float bias, int img_h, int img_w, void* stream) {
   PW_REQUIRE(curr && prev && cam && xs && ys && ds && out);
-  PW_REQUIRE(n > 0 && h > 0 && w > 0 && d > 0 && d <= 128);
+  PW_REQUIRE(n > 0 && h > 0 && w > 0 && d > 0 && d <= 128 && out_ld >= d && out_ld <= 128);
   PW_REQUIRE(c % 128 == 0 && c <= 512);
   long long warps = (long long)n * h * w;
   int blocks = pw_ceil_div(warps * 32, 256);
   cudaStream_t st = (cudaStream_t)stream;
   float wi_m1 = (float)img_w - 1.f, hi_m1 = (float)img_h - 1.f;
   switch (c / 128) {
-    case 1: cost_volume_kernel<1><<<blocks, 256, 0, st>>>(curr, prev, cam, xs, ys, ds, out, n, h, w, c, d, bias, wi_m1, hi_m1); break;
-    case 2: cost_volume_kernel<2><<<blocks, 256, 0, st>>>(curr, prev, cam, xs, ys, ds, out, n, h, w, c, d, bias, wi_m1, hi_m1); break;
-    case 3: cost_volume_kernel<3><<<blocks, 256, 0, st>>>(curr, prev, cam, xs, ys, ds, out, n, h, w, c, d, bias, wi_m1, hi_m1); break;
-    default: cost_volume_kernel<4><<<blocks, 256, 0, st>>>(curr, prev, cam, xs, ys, ds, out, n, h, w, c, d, bias, wi_m1, hi_m1); break;
+    case 1: cost_volume_kernel<1><<<blocks, 256, 0, st>>>(curr, prev, cam, xs, ys, ds, out, out_ld, n, h, w, c, d, bias, wi_m1, hi_m1); break;
+    case 2: cost_volume_kernel<2><<<blocks, 256, 0, st>>>(curr, prev, cam, xs, ys, ds, out, out_ld, n, h, w, c, d, bias, wi_m1, hi_m1); break;
+    case 3: cost_volume_kernel<3><<<blocks, 256, 0, st>>>(curr, prev, cam, xs, ys, ds, out, out_ld, n, h, w, c, d, bias, wi_m1, hi_m1); break;
+    default: cost_volume_kernel<4><<<blocks, 256, 0, st>>>(curr, prev, cam, xs, ys, ds, out, out_ld, n, h, w, c, d, bias, wi_m1, hi_m1); break;
   }
   PW_LAUNCH_CHECK(); pw_count_launch(1);
   return 0;

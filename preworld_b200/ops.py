@@ -79,13 +79,16 @@ class PackedConv:
 
     def __init__(self, weight, bias=None, bn=None, stride=1, padding=0,
                  dilation=1, in_scale=None, in_shift=None, eps=None,
-                 spatial_perm=None):
+                 spatial_perm=None, cin_pad=None, cout_pad=None):
         """weight [Cout,Cin,*k] (or [Cout,Cin] for Linear).  bn = (gamma,
         beta, mean, var, eps) folded as y = conv*s + (beta - mean*s + b*s).
         in_scale/in_shift fold a per-input-channel affine applied BEFORE a
         1x1 conv / linear (BatchNorm1d in front of DepthNet's Mlp).
         spatial_perm re-orders the kernel's spatial axes (used to run the
-        reference's [X,Y,Z]-ordered OccHead on [Z,Y,X] volumes)."""
+        reference's [X,Y,Z]-ordered OccHead on [Z,Y,X] volumes).
+        cin_pad / cout_pad widen the packed conv with ZERO weights (zero
+        scale-free outputs): a 344- or 88-channel tensor padded to a multiple
+        of 32 runs on the tensor-core kernels; padded outputs are exact 0."""
         w = weight.detach().float()
         if w.dim() == 2:
             w = w[:, :, None, None, None]
@@ -94,6 +97,21 @@ class PackedConv:
         assert w.dim() == 5
         if spatial_perm is not None:
             w = w.permute(0, 1, *[2 + p for p in spatial_perm])
+        if cin_pad or cout_pad:
+            co, ci = w.shape[:2]
+            wp = torch.zeros((cout_pad or co, cin_pad or ci, *w.shape[2:]),
+                             device=w.device)
+            wp[:co, :ci] = w
+            w = wp
+            if cout_pad and cout_pad > co:
+                padv = lambda v, fill: None if v is None else torch.cat(
+                    [v.detach().float(), torch.full((cout_pad - co,), fill,
+                                                    device=v.device)])
+                bias = padv(bias, 0.)
+                if bn is not None:
+                    g_, b_, m_, v_, e_ = bn
+                    bn = (padv(g_, 1.), padv(b_, 0.), padv(m_, 0.),
+                          padv(v_, 1.), e_)
         cout, cin = w.shape[:2]
         k = tuple(w.shape[2:])
         b = bias.detach().float() if bias is not None else None
@@ -313,14 +331,17 @@ def softmax_depth(logits_cl, d):
     return y
 
 
-def cost_volume(curr, prev, cam, xs, ys, ds, bias, img_hw):
+def cost_volume(curr, prev, cam, xs, ys, ds, bias, img_hw, pad_to=None):
+    """-> [n,h,w,d] (or [n,h,w,pad_to] with zero padding channels, so that a
+    following conv sees a 32-multiple Cin)."""
     n, h, w, c = curr.shape
     assert cl_ld(curr) == c and cl_ld(prev) == c and prev.shape == curr.shape
     d = ds.numel()
-    out = torch.empty((n, h, w, d), device=curr.device, dtype=torch.float32)
+    ld = pad_to or d
+    out = torch.empty((n, h, w, ld), device=curr.device, dtype=torch.float32)
     check(_lib.lib().pw_cost_volume(_ptr(curr), _ptr(prev), _ptr(cam), _ptr(xs),
-                                    _ptr(ys), _ptr(ds), _ptr(out), n, h, w, c,
-                                    d, float(bias), int(img_hw[0]),
+                                    _ptr(ys), _ptr(ds), _ptr(out), ld, n, h, w,
+                                    c, d, float(bias), int(img_hw[0]),
                                     int(img_hw[1]), _stream()),
           'pw_cost_volume')
     return out

@@ -75,6 +75,10 @@ class _DepthBasicBlock(nn.Module):
         self.downsample = downsample
 
 
+def _pad32(c):
+    return (c + 31) // 32 * 32
+
+
 class DepthNet(nn.Module):
     """Parameter container with the reference DepthNet's keys
     (view_transformer.py:473-544)."""
@@ -133,14 +137,22 @@ class DepthNet(nn.Module):
             P[k + '_fc2'] = pack_linear(mlp.fc2)
             P[k + '_red'] = pack_conv(se.conv_reduce)
             P[k + '_exp'] = pack_conv(se.conv_expand)
+        # 88- and (mid+88)-channel tensors are carried zero-padded to a multiple
+        # of 32 channels (zero weights on the padding) so these convs run on
+        # the tensor-core kernels
+        dpad = _pad32(self.depth_channels)
+        cpad = self.mid_channels + dpad
         P['cvnet'] = [pack_conv(self.cost_volumn_net[i],
-                                self.cost_volumn_net[i + 1]) for i in (0, 2)]
+                                self.cost_volumn_net[i + 1], cin_pad=dpad,
+                                cout_pad=dpad) for i in (0, 2)]
         blocks = []
-        for b in list(self.depth_conv)[:3]:
+        for j, b in enumerate(list(self.depth_conv)[:3]):
+            kw = dict(cin_pad=cpad) if j == 0 else {}
             blocks.append(dict(
-                c1=pack_conv(b.conv1, b.bn1), c2=pack_conv(b.conv2, b.bn2),
-                down=pack_conv(b.downsample) if b.downsample is not None
-                else None))
+                c1=pack_conv(b.conv1, b.bn1, **kw),
+                c2=pack_conv(b.conv2, b.bn2),
+                down=pack_conv(b.downsample, **kw)
+                if b.downsample is not None else None))
         P['blocks'] = blocks
         aspp = self.depth_conv[3]
         P['aspp'] = [pack_conv(m.atrous_conv, m.bn)
@@ -240,13 +252,14 @@ class LSSViewTransformerBEVStereo(BaseModule):
         g = ops.linear(g, P[k + '_red'], 'relu')
         return ops.linear(g, P[k + '_exp'], 'sigmoid')
 
-    def _cost_volume(self, P, metas, BN, H, W, device):
+    def _cost_volume(self, P, metas, BN, H, W, device, out=None):
         dn = self.depth_net
         prev, curr = metas['cv_feat_list']
         if prev is None:
             # view_transformer.py:619-625: all-zero cost volume
             s = float(metas['downsample']) / metas['cv_downsample']
-            cv = torch.zeros((BN, int(H * s), int(W * s), dn.depth_channels),
+            cv = torch.zeros((BN, int(H * s), int(W * s),
+                              _pad32(dn.depth_channels)),
                              device=device, dtype=torch.float32)
         else:
             xs, ys, ds = self._frustum_axes(metas['frustum'], device)
@@ -256,10 +269,10 @@ class LSSViewTransformerBEVStereo(BaseModule):
             curr_cl, prev_cl = ops.from_logical(curr), ops.from_logical(prev)
             hf, wf = curr_cl.shape[1:3]
             cv = ops.cost_volume(curr_cl, prev_cl, cam, xs, ys, ds, dn.bias,
-                                 (hf * 4, wf * 4))
-        for pc in P['cvnet']:
-            cv = ops.conv(cv, pc)
-        return cv
+                                 (hf * 4, wf * 4),
+                                 pad_to=_pad32(dn.depth_channels))
+        cv = ops.conv(cv, P['cvnet'][0])
+        return ops.conv(cv, P['cvnet'][1], out=out)
 
     def _depth_net(self, P, x, mlp_input, metas):
         dn = self.depth_net
@@ -274,12 +287,12 @@ class LSSViewTransformerBEVStereo(BaseModule):
         ctx = ops.scale_channels(x, self._se_gate(P, 'context', mlp_in))
         ops.conv(ctx, P['context'], out=out[..., dn.depth_channels:])
         # depth branch: cat([gated x, cost volume]) built in place
-        cat = torch.empty((BN, H, W, mid + dn.depth_channels),
+        cat = torch.empty((BN, H, W, mid + _pad32(dn.depth_channels)),
                           device=x.device, dtype=torch.float32)
         ops.scale_channels(x, self._se_gate(P, 'depth', mlp_in),
                            out=cat[..., :mid])
-        cv = self._cost_volume(P, metas, BN, H, W, x.device)
-        ops.copy_channels_(cat[..., mid:], cv)
+        # cost_volumn_net's last conv writes its (zero-padded) output in place
+        self._cost_volume(P, metas, BN, H, W, x.device, out=cat[..., mid:])
         d = cat
         for b in P['blocks']:
             identity = ops.conv(d, b['down']) if b['down'] is not None else d
