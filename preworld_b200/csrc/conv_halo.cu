@@ -334,9 +334,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     //      affine / residual / activation / store (kept small: it is straight-line
     //      code after the main loop and must not thrash the instruction cache) ----
     if (sw_id == 0 && lane == 0) PW_TS(11);
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    if (sw_id == 0 && lane == 0) PW_TS(7);
     const uint32_t stage = smem_base_u32 + (uint32_t)(sw_id * STAGE_BYTES_PER_WARP);
     const int ncg = (p.n_tile + 31) >> 5;
     const int items = p.mt * ncg;
@@ -363,11 +360,31 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
         rowpix[mm][i] = ok ? ((img * p.od + oz) * p.oh + oy) * p.ow + ox : -1;
       }
     }
+    // residual rows of an item are fetched ahead of use: for the first item while
+    // the last MMAs are still running, for the others under the TMEM loads
+    float4 rr[8];
+    auto prefetch_res = [&](int item) {
+      const int m = item / ncg;
+      const int cb = n0 + (item - m * ncg) * 32 + ch4 * 4;
+      const bool on = p.res != nullptr && vec_ok && cb + 4 <= p.cout &&
+                      (item - m * ncg) * 32 + ch4 * 4 < p.n_tile;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int pixi = m == 0 ? rowpix[0][i] : rowpix[1][i];
+        rr[i] = (on && pixi >= 0) ? pw_ldg4(p.res + (size_t)pixi * p.res_ld + cb)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (set < items) prefetch_res(set);
     if (sw_id == 0 && lane == 0) PW_TS(2);
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    if (sw_id == 0 && lane == 0) PW_TS(7);
     for (int item = set; item < items; item += SPLIT_SETS) {
       const int m = item / ncg;
       const int col0 = (item - m * ncg) * 32;
       const int ncol = min(32, p.n_tile - col0);         // 16 or 32 (warp-uniform)
+      if (item != set) prefetch_res(item);
       // phase 1: this thread's accumulator row (32 channels) -> its staging row
       for (int half = 0; half * 16 < ncol; ++half) {
         float acc[16];
@@ -414,10 +431,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
           float* yrow = p.y + (size_t)pixi * p.out_ld + cbase;
           const float* rrow = p.res ? p.res + (size_t)pixi * p.res_ld + cbase : nullptr;
           if (vec) {
-            if (rrow) {
-              const float4 rr = pw_ldg4(rrow);
-              va += rr.x; vb += rr.y; vc += rr.z; vd += rr.w;
-            }
+            va += rr[i].x; vb += rr[i].y; vc += rr[i].z; vd += rr[i].w;   // zeros if no residual
           } else if (rrow) {
             va += __ldg(rrow);
             if (cbase + 1 < p.cout) vb += __ldg(rrow + 1);
@@ -556,8 +570,12 @@ HaloPlan make_plan(const pw_conv_desc& in) {
           while (tcols < cols_need) tcols <<= 1;
           const long long smem_cta = smem_need(nh, nb);
           int cps = min(512 / tcols, (int)((228 * 1024 - 1024) / (smem_cta + 1024)));
-          cps = max(1, min(cps, 2));
-          if (const char* e = getenv("PW_HALO_CPS")) cps = min(cps, max(1, atoi(e)));
+          // measured: the register-capped two-CTA variant spills in the split loop and
+          // loses more than the overlap gains; opt-in only (PW_HALO_CPS=2)
+          {
+            const char* e = getenv("PW_HALO_CPS");
+            cps = max(1, min(cps, e ? atoi(e) : 1));
+          }
           const double waves = (double)((tiles + 148 * cps - 1) / (148 * cps));
           const double cost = waves * cta * (cps == 2 ? 1.3 : 1.0);
           if (best < 0 || cost < best) {
