@@ -213,6 +213,13 @@ int pw_lift_ranks(const float* cam, const float* bda, const float* xs,
 int pw_upsample_trilinear(const float* x, int x_ld, float* y, int y_ld, int b,
                           int z, int yy, int xx, int c, int oz, int oy, int ox,
                           void* stream);
+/* y = up(x1) + up(x2), both trilinear (align_corners=True) to [b,oz,oy,ox,c]:
+ * LSSFPN3D with its 1x1x1 conv commuted in front of the interpolation
+ * (lss_fpn.py:139-148), so the 224-channel concatenation never exists. */
+int pw_upsample_trilinear2(const float* x1, int x1_ld, int z1, int y1, int w1,
+                           const float* x2, int x2_ld, int z2, int y2, int w2,
+                           float* y, int y_ld, int b, int c, int oz, int oy,
+                           int ox, void* stream);
 /* Strided channel-slice copy y[p, 0:c] = x[p, 0:c] (concatenation). */
 int pw_copy_channels(const float* x, int x_ld, float* y, int y_ld,
                      long long pixels, int c, void* stream);

@@ -77,6 +77,9 @@ SIGNATURES = {
                       c_int, c_int, c_int, c_p, c_p],
     'pw_upsample_trilinear': [c_p, c_int, c_p, c_int, c_int, c_int, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_p],
+    'pw_upsample_trilinear2': [c_p, c_int, c_int, c_int, c_int, c_p, c_int, c_int,
+                               c_int, c_int, c_p, c_int, c_int, c_int, c_int,
+                               c_int, c_int, c_p],
     'pw_copy_channels': [c_p, c_int, c_p, c_int, c_ll, c_int, c_p],
     'pw_argmax_zyx_to_xyz': [c_p, c_int, c_int, c_p, c_int, c_int, c_int, c_p],
     'pw_density_occ_zyx_to_xyz': [c_p, c_int, c_p, c_int, c_int, c_f, c_int,

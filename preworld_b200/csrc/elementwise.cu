@@ -210,6 +210,55 @@ __global__ void upsample_trilinear_kernel(const float* __restrict__ x, int x_ld,
   }
 }
 
+// y = up(x1) + up(x2): both inputs trilinearly upsampled (align_corners=True)
+// to the output grid in one pass (LSSFPN3D after commuting its 1x1x1 conv with
+// the interpolation; necks/lss_fpn.py:139-146).
+__device__ __forceinline__ float4 trilerp4(const float* __restrict__ x, int x_ld, int bb, int iz,
+                                           int iy, int ix, int oz, int oy, int ox, int z_o,
+                                           int y_o, int x_o, int ch) {
+  const float sz = oz > 1 ? (float)(iz - 1) / (float)(oz - 1) : 0.f;
+  const float sy = oy > 1 ? (float)(iy - 1) / (float)(oy - 1) : 0.f;
+  const float sx = ox > 1 ? (float)(ix - 1) / (float)(ox - 1) : 0.f;
+  float fz = sz * z_o, fy = sy * y_o, fx = sx * x_o;
+  int z0 = (int)fz, y0 = (int)fy, x0 = (int)fx;
+  int z1 = z0 + (z0 < iz - 1), y1 = y0 + (y0 < iy - 1), x1 = x0 + (x0 < ix - 1);
+  float lz1 = fz - z0, ly1 = fy - y0, lx1 = fx - x0;
+  float lz0 = 1.f - lz1, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  auto at = [&](int zz, int yy, int xx) {
+    return pw_ldg4(x + ((((long long)bb * iz + zz) * iy + yy) * ix + xx) * x_ld + ch * 4);
+  };
+  float4 v000 = at(z0, y0, x0), v001 = at(z0, y0, x1), v010 = at(z0, y1, x0),
+         v011 = at(z0, y1, x1), v100 = at(z1, y0, x0), v101 = at(z1, y0, x1),
+         v110 = at(z1, y1, x0), v111 = at(z1, y1, x1);
+#define TRI(f)                                                                       \
+  (lz0 * (ly0 * (lx0 * v000.f + lx1 * v001.f) + ly1 * (lx0 * v010.f + lx1 * v011.f)) + \
+   lz1 * (ly0 * (lx0 * v100.f + lx1 * v101.f) + ly1 * (lx0 * v110.f + lx1 * v111.f)))
+  float4 o = make_float4(TRI(x), TRI(y), TRI(z), TRI(w));
+#undef TRI
+  return o;
+}
+
+__global__ void upsample_trilinear2_kernel(const float* __restrict__ x1, int x1_ld, int z1, int y1,
+                                           int w1, const float* __restrict__ x2, int x2_ld, int z2,
+                                           int y2, int w2, float* __restrict__ y, int y_ld, int b,
+                                           int c4, int oz, int oy, int ox) {
+  long long total = (long long)b * oz * oy * ox * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % c4);
+    long long t = i / c4;
+    int x_o = (int)(t % ox); t /= ox;
+    int y_o = (int)(t % oy); t /= oy;
+    int z_o = (int)(t % oz);
+    int bb = (int)(t / oz);
+    const float4 a = trilerp4(x1, x1_ld, bb, z1, y1, w1, oz, oy, ox, z_o, y_o, x_o, ch);
+    const float4 c = trilerp4(x2, x2_ld, bb, z2, y2, w2, oz, oy, ox, z_o, y_o, x_o, ch);
+    __stcs(reinterpret_cast<float4*>(
+               y + ((((long long)bb * oz + z_o) * oy + y_o) * ox + x_o) * y_ld + ch * 4),
+           make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w));
+  }
+}
+
 __global__ void copy_channels_kernel(const float* __restrict__ x, int x_ld, float* __restrict__ y,
                                      int y_ld, long long pixels, int c4) {
   long long total = pixels * c4;
@@ -373,6 +422,17 @@ PW_API int pw_upsample_trilinear(const float* x, int x_ld, float* y, int y_ld, i
   PW_REQUIRE(x && y && (c & 3) == 0 && (x_ld & 3) == 0 && (y_ld & 3) == 0);
   upsample_trilinear_kernel<<<grid_for((long long)b * oz * oy * ox * (c / 4)), TPB, 0, ST>>>(
       x, x_ld, y, y_ld, b, z, yy, xx, c / 4, oz, oy, ox);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+PW_API int pw_upsample_trilinear2(const float* x1, int x1_ld, int z1, int y1, int w1,
+                                  const float* x2, int x2_ld, int z2, int y2, int w2, float* y,
+                                  int y_ld, int b, int c, int oz, int oy, int ox, void* stream) {
+  PW_REQUIRE(x1 && x2 && y && (c & 3) == 0 && (x1_ld & 3) == 0 && (x2_ld & 3) == 0 &&
+             (y_ld & 3) == 0);
+  upsample_trilinear2_kernel<<<grid_for((long long)b * oz * oy * ox * (c / 4)), TPB, 0, ST>>>(
+      x1, x1_ld, z1, y1, w1, x2, x2_ld, z2, y2, w2, y, y_ld, b, c / 4, oz, oy, ox);
   PW_LAUNCH_CHECK(); pw_count_launch(1);
   return 0;
 }

@@ -438,6 +438,19 @@ def upsample_trilinear_(out, x):
     return out
 
 
+def upsample_trilinear2(x1, x2, out_spatial):
+    """up(x1) + up(x2) -> [B,OZ,OY,OX,C] (trilinear, align_corners)."""
+    b, z1, y1, w1, c = x1.shape
+    _, z2, y2, w2, c2 = x2.shape
+    assert c == c2 and x2.shape[0] == b
+    oz, oy, ox = out_spatial
+    out = torch.empty((b, oz, oy, ox, c), device=x1.device, dtype=torch.float32)
+    check(_lib.lib().pw_upsample_trilinear2(
+        _ptr(x1), cl_ld(x1), z1, y1, w1, _ptr(x2), cl_ld(x2), z2, y2, w2,
+        _ptr(out), c, b, c, oz, oy, ox, _stream()), 'pw_upsample_trilinear2')
+    return out
+
+
 def copy_channels_(out, x):
     c = x.shape[-1]
     pixels = x[..., 0].numel()

@@ -125,17 +125,35 @@ class LSSFPN3D(BaseModule):
         self.with_cp = with_cp
 
     def _build_packs(self):
-        return self.conv.pack()
+        return {}
+
+    def _split_packs(self, c8, c16, c32):
+        """The 1x1x1 conv is linear and so is the interpolation, and BN's
+        per-channel scale commutes with both:
+            relu(bn(W [a; up(b); up(c)])) = relu(s*(Wa a) + up(s*Wb b)
+                                                 + up(s*Wc c) + t)
+        so Wb, Wc run at the COARSE resolutions and the [B,224,16,200,200]
+        concatenation (573 MB) of lss_fpn.py:139-147 never exists."""
+        P = self.packs()
+        key = (c8, c16, c32)
+        if key not in P:
+            w = self.conv.conv.weight
+            bn = self.conv.bn
+            assert w.shape[1] == c8 + c16 + c32
+            zero = torch.zeros_like(bn.bias)
+            scale_only = (bn.weight, zero, zero, bn.running_var, bn.eps)
+            full = (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+            with torch.no_grad():
+                P[key] = (
+                    ops.PackedConv(w[:, :c8], None, full),
+                    ops.PackedConv(w[:, c8:c8 + c16], None, scale_only),
+                    ops.PackedConv(w[:, c8 + c16:], None, scale_only))
+        return P[key]
 
     def forward(self, feats):
         x8, x16, x32 = [ops.from_logical(f) for f in feats]
-        pc = self.packs()
-        b, z, y, x, c8 = x8.shape
-        c16, c32 = x16.shape[-1], x32.shape[-1]
-        assert c8 + c16 + c32 == pc.cin
-        cat = torch.empty((b, z, y, x, pc.cin), device=x8.device,
-                          dtype=torch.float32)
-        ops.copy_channels_(cat[..., :c8], x8)
-        ops.upsample_trilinear_(cat[..., c8:c8 + c16], x16)
-        ops.upsample_trilinear_(cat[..., c8 + c16:], x32)
-        return ops.to_logical(ops.conv(cat, pc, 'relu'))
+        pa, pb, pc = self._split_packs(x8.shape[-1], x16.shape[-1],
+                                       x32.shape[-1])
+        r = ops.upsample_trilinear2(ops.conv(x16, pb), ops.conv(x32, pc),
+                                    tuple(x8.shape[1:4]))
+        return ops.to_logical(ops.conv(x8, pa, 'relu', residual=r))
