@@ -337,7 +337,10 @@ def main():
     ms_max = t.item()
 
     # ---- end-to-end timing (host buffers, H2D + D2H inside) ----------------
-    for i in range(2):
+    # the public call replays the forward as one CUDA graph (one capture per
+    # input shape, done by the first untimed call below)
+    model.enable_cuda_graph()
+    for i in range(3):
         step_e2e(i)
     barrier()
     t0 = time.perf_counter()
@@ -436,7 +439,8 @@ def main():
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / args.steps,
                 'api': 'model(return_loss=False, img_inputs=[...]) with '
-                       'pinned host tensors'},
+                       'pinned host tensors, model.enable_cuda_graph() '
+                       '(forward replayed as one CUDA graph)'},
         'gpu_launches': int(launches),
         'clocks': clk, 'roofline': roof, 'cpu_baseline': cpu,
         'kernels': kernels,

@@ -236,3 +236,31 @@ def test_full_size_finetune_matches_reference(golden_dir):
     assert lifted.shape == (1, 32, 16, 200, 200)
     nz = (lifted.abs().sum(1) > 0).float().mean().item()
     assert 0.15 < nz < 0.35                   # ~142k of 640k voxels non-empty
+
+
+@pytest.mark.parametrize('name', ['tiny_finetune', 'tiny_pretrain'])
+def test_cuda_graph_replay_equals_eager(name):
+    """enable_cuda_graph(): the captured graph replays the same launches, so
+    the occupancy grids are identical to the eager path -- also for a second
+    sample fed through the same captured graph."""
+    case = CASES[name]
+    model = _model(case).cuda()
+    samples = [build_case_inputs(case)[0],
+               build_case_inputs(dict(case,
+                                      input_seed=case['input_seed'] + 7))[0]]
+    eager = []
+    with torch.no_grad():
+        for s in samples:
+            out = model(return_loss=False,
+                        img_inputs=[tuple(t.cuda() for t in s)], img_metas=[None])
+            eager.append((out['semantic_occ'][0], out['geo_occ'][0]))
+    model.enable_cuda_graph()
+    with torch.no_grad():
+        for rep in range(2):
+            for s, want in zip(samples, eager):
+                out = model(return_loss=False,
+                            img_inputs=[tuple(t.cuda() for t in s)],
+                            img_metas=[None])
+                assert np.array_equal(out['semantic_occ'][0], want[0])
+                assert np.array_equal(out['geo_occ'][0], want[1])
+    assert len(model._graph_cache) == 1
