@@ -258,10 +258,15 @@ class BEVStereo4DOCC(BaseModule):
         post_trans = [to_dev(t) for t in post_trans]
         curr2adjsensor = [to_dev(t) for t in curr2adjsensor]
         bda = to_dev(bda)
+        vt = self.img_view_transformer
+        shard = getattr(self, 'camera_shard', None)
+        if shard is not None and shard.world > 1:
+            return self._extract_img_feat_sharded(
+                shard, imgs, sensor2keyegos, ego2globals, intrins, post_rots,
+                post_trans, bda, curr2adjsensor)
         bev_feat_list = []
         depth_key_frame = None
         feat_prev_iv = None
-        vt = self.img_view_transformer
         enc = self.encode_frames(imgs)
         for fid in range(self.num_frame - 1, -1, -1):
             key_frame = fid == 0
@@ -279,6 +284,78 @@ class BEVStereo4DOCC(BaseModule):
             if not extra_ref_frame:
                 bev_feat_list.append(bev_feat)
             feat_prev_iv = feat_curr_iv
+        return self._fuse_frames(bev_feat_list, dev), depth_key_frame
+
+    def set_camera_shard(self, shard):
+        """Within-sample camera sharding over the ranks of ``shard``
+        (preworld_b200.parallel.CameraShard); None = off."""
+        self.camera_shard = shard
+        return self
+
+    def _extract_img_feat_sharded(self, shard, imgs, sensor2keyegos,
+                                  ego2globals, intrins, post_rots, post_trans,
+                                  bda, curr2adjsensor):
+        """This rank encodes its block of cameras for every frame, ONE
+        all-gather exchanges depth + context features, then every rank lifts
+        all cameras (same deterministic kernel -> identical voxel features)."""
+        vt = self.img_view_transformer
+        dev = imgs[0].device
+        nf = self.num_frame
+        B, N = imgs[0].shape[:2]
+        c0, cn = shard.local_range(N)
+        sl = slice(c0, c0 + cn)
+        lifted = [f for f in range(nf - 1, -1, -1)
+                  if f != nf - self.extra_ref_frames]      # [adjacent.., key]
+        D, C = vt.D, vt.out_channels
+        h, w = [int(v) for v in vt.frustum.shape[1:3]]
+        per_frame = D * h * w + h * w * C
+        local = torch.empty((B, cn, per_frame * len(lifted)), device=dev,
+                            dtype=torch.float32)
+        if cn > 0:
+            enc = self.encode_frames([im[:, sl] for im in imgs])
+            feat_prev = None
+            k = 0
+            for fid in range(nf - 1, -1, -1):
+                x, stereo = enc[0][fid], enc[1][fid]
+                if fid in lifted:
+                    mlp_input = vt.get_mlp_input(
+                        sensor2keyegos[0][:, sl], ego2globals[0][:, sl],
+                        intrins[fid][:, sl], post_rots[fid][:, sl],
+                        post_trans[fid][:, sl], bda)
+                    metas = dict(k2s_sensor=curr2adjsensor[fid][:, sl],
+                                 intrins=intrins[fid][:, sl],
+                                 post_rots=post_rots[fid][:, sl],
+                                 post_trans=post_trans[fid][:, sl],
+                                 frustum=vt.cv_frustum, cv_downsample=4,
+                                 downsample=vt.downsample,
+                                 grid_config=vt.grid_config,
+                                 cv_feat_list=[feat_prev, stereo])
+                    depth, tran = vt.depth_stage(x, mlp_input, metas)
+                    o = k * per_frame
+                    local[:, :, o:o + D * h * w] = depth.reshape(B, cn, -1)
+                    local[:, :, o + D * h * w:o + per_frame] = \
+                        tran.reshape(B, cn, -1)
+                    k += 1
+                feat_prev = stereo
+        full = shard.all_gather_cams(local, N)                 # [B, N, F]
+        bev_feat_list = []
+        depth_key_frame = None
+        for k, fid in enumerate(lifted):
+            o = k * per_frame
+            depth = full[:, :, o:o + D * h * w].reshape(B * N, D, h, w) \
+                .contiguous()
+            tran = full[:, :, o + D * h * w:o + per_frame] \
+                .reshape(B * N, h, w, C).contiguous()
+            bev = vt.lift_stage(depth, tran, sensor2keyegos[fid], intrins[fid],
+                                post_rots[fid], post_trans[fid], bda, B, N)
+            if self.pre_process:
+                bev = self.pre_process_net(bev)[0]
+            bev_feat_list.append(bev)
+            if fid == 0:
+                depth_key_frame = depth
+        return self._fuse_frames(bev_feat_list, dev), depth_key_frame
+
+    def _fuse_frames(self, bev_feat_list, dev):
         # torch.cat(bev_feat_list, dim=1): [adjacent, key] order (:240,266)
         parts = [ops.from_logical(f) for f in bev_feat_list]
         ctot = sum(p.shape[-1] for p in parts)
@@ -288,8 +365,7 @@ class BEVStereo4DOCC(BaseModule):
         for p in parts:
             ops.copy_channels_(cat[..., c0:c0 + p.shape[-1]], p)
             c0 += p.shape[-1]
-        x = self.bev_encoder(ops.to_logical(cat))
-        return [x], depth_key_frame
+        return [self.bev_encoder(ops.to_logical(cat))]
 
     def _build_packs(self):
         return dict(final=self.final_conv.pack())

@@ -311,23 +311,37 @@ class LSSViewTransformerBEVStereo(BaseModule):
         return out
 
     # -- forward (view_transformer.py:791-804) --------------------------------
-    def forward(self, input, stereo_metas=None, depth_gt=None):
-        (x, sensor2keyego, ego2global, intrin, post_rot, post_tran, bda,
-         mlp_input) = input[:8]
+    def depth_stage(self, x, mlp_input, stereo_metas):
+        """DepthNet + softmax over D for the cameras in ``x`` [B,n,C,H,W]
+        (per-camera work: this is what a camera shard runs locally).
+        -> depth [B*n,D,H,W], context features cl [B*n,H,W,C_out] (a channel
+        slice of the DepthNet output)."""
         P = self.packs()
         B, N, C, H, W = x.shape
-        x_cl = ops.from_logical(x.reshape(B * N, C, H, W)
-                                if x.dim() == 5 else x)
+        x_cl = ops.from_logical(x.reshape(B * N, C, H, W))
         feat = self._depth_net(P, x_cl, mlp_input, stereo_metas)
         depth = ops.softmax_depth(feat, self.D)          # [B*N, D, H, W]
-        dev = feat.device
+        return depth, feat[..., self.D:self.D + self.out_channels]
+
+    def lift_stage(self, depth, tran_feat, sensor2keyego, intrin, post_rot,
+                   post_tran, bda, B, N):
+        """Voxel lift of ALL cameras (view_transformer.py:114-153,176-261)."""
+        dev = depth.device
         cam = ops.lift_camera_params(sensor2keyego, intrin, post_rot,
                                      post_tran)
         xs, ys, ds = self._frustum_axes(self.frustum, dev)
         grid = tuple(int(g) for g in self.grid_size)
         bev = ops.lift_fused(
-            depth, feat[..., self.D:self.D + self.out_channels], cam,
-            bda.reshape(B, 9).contiguous().float(), xs, ys, ds,
-            self.grid_lower_bound.tolist(), self.grid_interval.tolist(), B, N,
-            grid)
-        return ops.to_logical(bev), depth
+            depth, tran_feat, cam, bda.reshape(B, 9).contiguous().float(),
+            xs, ys, ds, self.grid_lower_bound.tolist(),
+            self.grid_interval.tolist(), B, N, grid)
+        return ops.to_logical(bev)
+
+    def forward(self, input, stereo_metas=None, depth_gt=None):
+        (x, sensor2keyego, ego2global, intrin, post_rot, post_tran, bda,
+         mlp_input) = input[:8]
+        B, N = x.shape[:2]
+        depth, tran_feat = self.depth_stage(x, mlp_input, stereo_metas)
+        bev = self.lift_stage(depth, tran_feat, sensor2keyego, intrin,
+                              post_rot, post_tran, bda, B, N)
+        return bev, depth
