@@ -159,7 +159,22 @@ int pw_bev_pool_v2(int c, int n_intervals, const float* depth, const float* feat
                    const int* ranks_bev, const int* interval_starts,
                    const int* interval_lengths, float* out, void* stream);
 
-/* Fused B200-native lift: geometry -> voxel rank -> per-voxel point lists ->
+/* Backward of bev_pool_v2: drop-in for the reference FFI  bev_pool_v2_grad(c,
+ * n_intervals, out_grad, depth, feat, ranks_depth, ranks_feat, ranks_bev,
+ * interval_starts, interval_lengths, depth_grad, feat_grad)
+ * (src/bev_pool.cpp:16-28,74-111; kernel src/bev_pool_cuda.cu:67-121).  As in
+ * the reference the point lists are sorted by ranks_FEAT and the intervals
+ * are runs of equal ranks_feat (bev_pool.py:47-57); depth_grad / feat_grad are
+ * zero-initialised by the caller (bev_pool.py:67-68). */
+int pw_bev_pool_v2_grad(int c, int n_intervals, const float* out_grad,
+                        const float* depth, const float* feat,
+                        const int* ranks_depth, const int* ranks_feat,
+                        const int* ranks_bev, const int* interval_starts,
+                        const int* interval_lengths, float* depth_grad,
+                        float* feat_grad, void* stream);
+
+/* Fused B200-native lift (ONE persistent kernel with grid barriers): geometry
+ * -> voxel rank -> per-voxel point lists ->
  * dense pooled volume, replacing get_lidar_coor + voxel_pooling_prepare_v2 +
  * bev_pool_v2 + the zero-fill and the permute copy (view_transformer.py:
  * 114-153,176-261; bev_pool.py:27,91).
@@ -276,7 +291,22 @@ typedef struct pw_render_desc {
   int world_len;
   int gx, gy, gz;
   int n_sem;
-  long long vs_x, vs_y, vs_z; /* voxel strides (in voxels) of the volumes:
+  long long vs_x, vs_y, vs_z; /* render_utils_cuda.raw2alpha_backward(exp_d, grad_back, interval) -> grad
+ * (nerf/cuda/render_utils_kernel.cu:507-537, render_utils.cpp:54-60). */
+int pw_raw2alpha_backward(const float* exp_d, const float* grad_back,
+                          float interval, long long n, float* grad,
+                          void* stream);
+/* render_utils_cuda.alpha2weight_backward(alpha, weight, T, alphainv_last,
+ * i_start, i_end, n_rays, grad_weights, grad_last) -> grad
+ * (render_utils_kernel.cu:654-707); `grad` [n_pts] zero-initialised by the
+ * caller (torch::zeros_like, :682). */
+int pw_alpha2weight_backward(const float* alpha, const float* weight,
+                             const float* T, const float* alphainv_last,
+                             const long long* i_start, const long long* i_end,
+                             int n_rays, const float* grad_weights,
+                             const float* grad_last, float* grad, void* stream);
+
+/* voxel strides (in voxels) of the volumes:
                                  library order [Z,Y,X] -> (1, gx, gx*gy);
                                  reference order [X,Y,Z] -> (gy*gz, gz, 1) */
 } pw_render_desc;

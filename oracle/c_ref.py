@@ -50,7 +50,12 @@ def lib():
         L.pw_ref_alpha2weight.argtypes = [
             _int, _int, _f32p, _i64p, _f32p, _f32p, _f32p, _i64p, _i64p]
         L.pw_ref_cumdist_thres.argtypes = [_int, _int, _f32p, _flt, _u8p]
+        L.pw_ref_raw2alpha_bwd.argtypes = [_int, _f32p, _f32p, _flt, _f32p]
+        L.pw_ref_alpha2weight_bwd.argtypes = [
+            _int, _f32p, _f32p, _f32p, _f32p, _i64p, _i64p, _f32p, _f32p,
+            _f32p]
         for f in ('pw_ref_bev_pool_v2_fwd', 'pw_ref_bev_pool_v2_bwd',
+                  'pw_ref_raw2alpha_bwd', 'pw_ref_alpha2weight_bwd',
                   'pw_ref_lift_camera_params', 'pw_ref_lift_ranks',
                   'pw_ref_raw2alpha', 'pw_ref_alpha2weight',
                   'pw_ref_cumdist_thres'):
@@ -135,6 +140,26 @@ def alpha2weight(alpha, ray_id, n_rays, full=False):
     if full:
         return w, T, last, i_s, i_e
     return w, last
+
+
+def raw2alpha_bwd(exp_d, grad_back, interval):
+    e = _f32(exp_d).ravel()
+    g = np.empty_like(e)
+    lib().pw_ref_raw2alpha_bwd(len(e), e, _f32(grad_back).ravel(), interval, g)
+    return g
+
+
+def alpha2weight_bwd(alpha, weight, T, alphainv_last, i_start, i_end,
+                     grad_weights, grad_last):
+    a = _f32(alpha).ravel()
+    g = np.zeros_like(a)
+    lib().pw_ref_alpha2weight_bwd(
+        len(alphainv_last), a, _f32(weight).ravel(), _f32(T).ravel(),
+        _f32(alphainv_last).ravel(),
+        np.ascontiguousarray(i_start, dtype=np.int64),
+        np.ascontiguousarray(i_end, dtype=np.int64),
+        _f32(grad_weights).ravel(), _f32(grad_last).ravel(), g)
+    return g
 
 
 def cumdist_thres(dist, thres):

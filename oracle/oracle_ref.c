@@ -205,6 +205,38 @@ void pw_ref_alpha2weight(int n_pts, int n_rays, const float *alpha,
   }
 }
 
+/* mmdet3d/models/nerf/cuda/render_utils_kernel.cu:507-517 (scalar_t = float):
+ * `min(exp_d, 1e10)` promotes to double, `pow(1+exp_d, -interval-1)` is the
+ * float overload, the product chain is evaluated left to right in double and
+ * rounded once on the store. */
+void pw_ref_raw2alpha_bwd(int n, const float *exp_d, const float *grad_back,
+                          float interval, float *grad) {
+  for (int i = 0; i < n; ++i) {
+    double m = (double)exp_d[i] < 1e10 ? (double)exp_d[i] : 1e10;
+    float pw = powf(1 + exp_d[i], -interval - 1);
+    grad[i] = (float)(m * (double)pw * (double)interval * (double)grad_back[i]);
+  }
+}
+
+/* mmdet3d/models/nerf/cuda/render_utils_kernel.cu:654-676; `grad` must be
+ * zero-initialised by the caller (torch::zeros_like, :682).  back_cum is a
+ * float; `1-alpha+1e-10` and the division / subtraction are double. */
+void pw_ref_alpha2weight_bwd(int n_rays, const float *alpha, const float *weight,
+                             const float *T, const float *alphainv_last,
+                             const int64_t *i_start, const int64_t *i_end,
+                             const float *grad_weights, const float *grad_last,
+                             float *grad) {
+  for (int r = 0; r < n_rays; ++r) {
+    int i_s = (int)i_start[r], i_e = (int)i_end[r];
+    float back_cum = grad_last[r] * alphainv_last[r];
+    for (int i = i_e - 1; i >= i_s; --i) {
+      float gt = grad_weights[i] * T[i];
+      grad[i] = (float)((double)gt - (double)back_cum / ((double)(1 - alpha[i]) + 1e-10));
+      back_cum += grad_weights[i] * weight[i];
+    }
+  }
+}
+
 /* mmdet3d/models/nerf/cuda/ub360_utils_kernel.cu:12-32 */
 void pw_ref_cumdist_thres(int n_rays, int n_pts, const float *dist, float thres,
                           uint8_t *mask) {

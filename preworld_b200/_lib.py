@@ -65,6 +65,11 @@ SIGNATURES = {
                        c_int, c_int, c_int, c_f, c_int, c_int, c_p],
     'pw_bev_pool_v2': [c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
                        c_p],
+    'pw_bev_pool_v2_grad': [c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
+                            c_p, c_p, c_p],
+    'pw_raw2alpha_backward': [c_p, c_p, c_f, c_ll, c_p, c_p],
+    'pw_alpha2weight_backward': [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_p, c_p,
+                                 c_p, c_p],
     'pw_lift_camera_params': [c_int, c_p, c_p, c_p, c_p, c_p, c_p],
     'pw_cv_camera_params': [c_int, c_p, c_p, c_p, c_p, c_p, c_p],
     'pw_lift_workspace_bytes': [c_int] * 8,

@@ -363,6 +363,21 @@ def bev_pool_v2_(depth, feat, ranks_depth, ranks_feat, ranks_bev,
     return out
 
 
+def bev_pool_v2_grad_(out_grad, depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                      interval_starts, interval_lengths, depth_grad, feat_grad):
+    """In-place drop-in of bev_pool_v2_ext.bev_pool_v2_backward: lists sorted by
+    ranks_feat, intervals = runs of equal ranks_feat, zero-initialised grads
+    (bev_pool.py:43-83)."""
+    _require_cuda(out_grad, depth, feat, depth_grad, feat_grad)
+    c = feat.shape[-1]
+    check(_lib.lib().pw_bev_pool_v2_grad(
+        c, int(interval_starts.numel()), _ptr(out_grad), _ptr(depth), _ptr(feat),
+        _ptr(ranks_depth), _ptr(ranks_feat), _ptr(ranks_bev),
+        _ptr(interval_starts), _ptr(interval_lengths), _ptr(depth_grad),
+        _ptr(feat_grad), _stream()), 'pw_bev_pool_v2_grad')
+    return depth_grad, feat_grad
+
+
 def _cam_params(fn_name, floats, pose44, intrin, post_rot, post_tran):
     _require_cuda(pose44, intrin, post_rot, post_tran)
     n = pose44.numel() // 16
@@ -522,6 +537,31 @@ def alpha2weight(alpha, ray_id, n_rays):
                                      _ptr(i_s), _ptr(i_e), _stream()),
           'pw_alpha2weight')
     return weight, T, last, i_s, i_e
+
+
+def raw2alpha_backward(exp_d, grad_back, interval):
+    _require_cuda(exp_d, grad_back)
+    exp_d, grad_back = exp_d.contiguous(), grad_back.contiguous()
+    grad = torch.empty_like(exp_d)
+    check(_lib.lib().pw_raw2alpha_backward(_ptr(exp_d), _ptr(grad_back),
+                                           float(interval), exp_d.numel(),
+                                           _ptr(grad), _stream()),
+          'pw_raw2alpha_backward')
+    return grad
+
+
+def alpha2weight_backward(alpha, weight, T, alphainv_last, i_start, i_end,
+                          grad_weights, grad_last):
+    _require_cuda(alpha, weight, T, grad_weights)
+    grad = torch.zeros_like(alpha)
+    check(_lib.lib().pw_alpha2weight_backward(
+        _ptr(alpha.contiguous()), _ptr(weight.contiguous()),
+        _ptr(T.contiguous()), _ptr(alphainv_last.contiguous()),
+        _ptr(i_start.contiguous()), _ptr(i_end.contiguous()),
+        int(alphainv_last.numel()), _ptr(grad_weights.contiguous()),
+        _ptr(grad_last.contiguous()), _ptr(grad), _stream()),
+        'pw_alpha2weight_backward')
+    return grad
 
 
 def cumdist_thres(dist, thres):

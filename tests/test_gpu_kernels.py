@@ -205,6 +205,74 @@ def test_bev_pool_v2_drop_in_kat():
                      out)                      # empty: no-op
 
 
+def test_bev_pool_v2_grad_kat_and_oracle():
+    """Backward drop-in (bev_pool.py:43-83, src/bev_pool_cuda.cu:67-121): the
+    reference's own gradient KAT (bev_pool.py:170-176) through the C ABI, then
+    a random case bit-exact against the C oracle."""
+    def intervals(rf):
+        kept = np.ones(len(rf), bool)
+        kept[1:] = rf[1:] != rf[:-1]
+        st = np.where(kept)[0].astype(np.int32)
+        return st, np.diff(np.append(st, len(rf))).astype(np.int32)
+
+    def run(out_grad, depth, feat, rd, rf, rb):
+        order = np.argsort(rf, kind='stable')
+        rd, rf, rb = rd[order], rf[order], rb[order]
+        st, ln = intervals(rf)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+        dg = torch.zeros(depth.size, device=DEV)
+        fg = torch.zeros(feat.shape, device=DEV)
+        ops.bev_pool_v2_grad_(t(out_grad), t(depth), t(feat), t(rd), t(rf),
+                              t(rb), t(st), t(ln), dg, fg)
+        want = c_ref.bev_pool_v2_bwd(out_grad, depth, feat, rd, rf, rb, st, ln)
+        return dg.cpu().numpy(), fg.cpu().numpy(), want
+
+    depth = np.array([0.3, 0.4, 0.2, 0.1, 0.7, 0.6, 0.8, 0.9], np.float32)
+    dg, fg, _ = run(np.ones((4, 2), np.float32), depth, np.ones((4, 2), np.float32),
+                    np.array([0, 4, 1, 6], np.int32), np.array([0, 0, 1, 2], np.int32),
+                    np.array([0, 0, 1, 1], np.int32))
+    np.testing.assert_allclose(dg, [2, 2, 0, 0, 2, 0, 2, 0], atol=1e-6)
+    np.testing.assert_allclose(fg.ravel(), [1, 1, .4, .4, .8, .8, 0, 0], atol=1e-6)
+
+    rng = np.random.default_rng(0)
+    n_pts, n_depth, n_feat, n_bev, c = 20000, 30000, 900, 5000, 80
+    rd = rng.choice(n_depth, n_pts, replace=False).astype(np.int32)
+    rf = rng.integers(0, n_feat, n_pts).astype(np.int32)
+    rb = rng.integers(0, n_bev, n_pts).astype(np.int32)
+    dg, fg, (wdg, wfg) = run(rng.standard_normal((n_bev, c)).astype(np.float32),
+                             rng.random(n_depth).astype(np.float32),
+                             rng.standard_normal((n_feat, c)).astype(np.float32),
+                             rd, rf, rb)
+    assert np.array_equal(dg, wdg)           # same sequential fmaf chains
+    assert np.array_equal(fg, wfg)
+
+
+def test_render_backward_primitives_match_c_oracle():
+    """raw2alpha_backward / alpha2weight_backward (render_utils_kernel.cu:
+    507-517, 654-676) against the C restatements."""
+    g = torch.Generator().manual_seed(5)
+    dens = torch.rand(6000, generator=g) * 40 - 5
+    gb = torch.randn(6000, generator=g)
+    e, a = ops.raw2alpha(dens.to(DEV), -13.8155, 0.5)
+    got = ops.raw2alpha_backward(e, gb.to(DEV), 0.5).cpu().numpy()
+    want = c_ref.raw2alpha_bwd(e.cpu().numpy(), gb.numpy(), 0.5)
+    np.testing.assert_allclose(got, want, rtol=3e-6, atol=1e-12)   # powf ulp
+    n_rays = 500
+    counts = torch.randint(0, 60, (n_rays,), generator=g)
+    counts[::13] = 0
+    ray_id = torch.repeat_interleave(torch.arange(n_rays), counts)
+    alpha = torch.rand(len(ray_id), generator=g) ** 2
+    w, T, last, i_s, i_e = ops.alpha2weight(alpha.to(DEV), ray_id.to(DEV), n_rays)
+    gw = torch.randn(len(ray_id), generator=g)
+    gl = torch.randn(n_rays, generator=g)
+    got = ops.alpha2weight_backward(alpha.to(DEV), w, T, last, i_s, i_e,
+                                    gw.to(DEV), gl.to(DEV)).cpu().numpy()
+    want = c_ref.alpha2weight_bwd(alpha.numpy(), w.cpu().numpy(), T.cpu().numpy(),
+                                  last.cpu().numpy(), i_s.cpu().numpy(),
+                                  i_e.cpu().numpy(), gw.numpy(), gl.numpy())
+    assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize('batch', [1, 2])
 def test_lift_matches_oracle_bit_exact(batch):
     geo, s2k, intr, pr, pt, bda = _lift_setup(batch, seed=3)
