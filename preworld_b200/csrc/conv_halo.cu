@@ -420,33 +420,48 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
         }
         const int a_ = (cbase < act_end) ? p.act : PW_ACT_NONE;     // act_end % 4 == 0
         const bool vec = vec_ok && cbase + 4 <= p.cout;
+        const float* yb = p.y + cbase;
+        if (vec && (a_ == PW_ACT_NONE || a_ == PW_ACT_RELU)) {
+          // fast path (every hot layer): branch-free, fully unrolled, residual
+          // already in registers
+          const bool relu = a_ == PW_ACT_RELU;
+          const int ldo = p.out_ld;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + (lane >> 3);
-          const int pixi = m == 0 ? rowpix[0][i] : rowpix[1][i];
-          if (pixi < 0) continue;
-          const float4 v4 = lds128(stage + (uint32_t)((r * 8 + (ch4 ^ (r & 7))) << 4));
-          float va = fmaf(v4.x, sc[0], bi[0]), vb = fmaf(v4.y, sc[1], bi[1]);
-          float vc = fmaf(v4.z, sc[2], bi[2]), vd = fmaf(v4.w, sc[3], bi[3]);
-          float* yrow = p.y + (size_t)pixi * p.out_ld + cbase;
-          const float* rrow = p.res ? p.res + (size_t)pixi * p.res_ld + cbase : nullptr;
-          if (vec) {
-            va += rr[i].x; vb += rr[i].y; vc += rr[i].z; vd += rr[i].w;   // zeros if no residual
-          } else if (rrow) {
-            va += __ldg(rrow);
-            if (cbase + 1 < p.cout) vb += __ldg(rrow + 1);
-            if (cbase + 2 < p.cout) vc += __ldg(rrow + 2);
-            if (cbase + 3 < p.cout) vd += __ldg(rrow + 3);
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3);
+            const int pixi = m == 0 ? rowpix[0][i] : rowpix[1][i];
+            const float4 v4 = lds128(stage + (uint32_t)((r * 8 + (ch4 ^ (r & 7))) << 4));
+            float4 o;
+            o.x = fmaf(v4.x, sc[0], bi[0]) + rr[i].x;
+            o.y = fmaf(v4.y, sc[1], bi[1]) + rr[i].y;
+            o.z = fmaf(v4.z, sc[2], bi[2]) + rr[i].z;
+            o.w = fmaf(v4.w, sc[3], bi[3]) + rr[i].w;
+            o.x = relu ? fmaxf(o.x, 0.f) : o.x;
+            o.y = relu ? fmaxf(o.y, 0.f) : o.y;
+            o.z = relu ? fmaxf(o.z, 0.f) : o.z;
+            o.w = relu ? fmaxf(o.w, 0.f) : o.w;
+            if (pixi >= 0)
+              *reinterpret_cast<float4*>(const_cast<float*>(yb) + (size_t)pixi * ldo) = o;
           }
-          if (a_ == PW_ACT_RELU) {
-            va = fmaxf(va, 0.f); vb = fmaxf(vb, 0.f); vc = fmaxf(vc, 0.f); vd = fmaxf(vd, 0.f);
-          } else if (a_ != PW_ACT_NONE) {
+        } else {
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3);
+            const int pixi = m == 0 ? rowpix[0][i] : rowpix[1][i];
+            if (pixi < 0) continue;
+            const float4 v4 = lds128(stage + (uint32_t)((r * 8 + (ch4 ^ (r & 7))) << 4));
+            float va = fmaf(v4.x, sc[0], bi[0]), vb = fmaf(v4.y, sc[1], bi[1]);
+            float vc = fmaf(v4.z, sc[2], bi[2]), vd = fmaf(v4.w, sc[3], bi[3]);
+            float* yrow = p.y + (size_t)pixi * p.out_ld + cbase;
+            const float* rrow = p.res ? p.res + (size_t)pixi * p.res_ld + cbase : nullptr;
+            if (rrow) {
+              va += __ldg(rrow);
+              if (cbase + 1 < p.cout) vb += __ldg(rrow + 1);
+              if (cbase + 2 < p.cout) vc += __ldg(rrow + 2);
+              if (cbase + 3 < p.cout) vd += __ldg(rrow + 3);
+            }
             va = pw_activate_slow(va, a_); vb = pw_activate_slow(vb, a_);
             vc = pw_activate_slow(vc, a_); vd = pw_activate_slow(vd, a_);
-          }
-          if (vec) {
-            *reinterpret_cast<float4*>(yrow) = make_float4(va, vb, vc, vd);
-          } else {
             yrow[0] = va;
             if (cbase + 1 < p.cout) yrow[1] = vb;
             if (cbase + 2 < p.cout) yrow[2] = vc;
