@@ -217,6 +217,8 @@ class BEVStereo4DOCC(BaseModule):
             stereo.append(ops.to_logical(l1[f * bn:(f + 1) * bn]))
             feats.append(x[f * bn:(f + 1) * bn].view(B, N, cdim, oh, ow)
                          if f < n_full else None)
+        # the frame-major batches themselves (for the batched DepthNet pass)
+        self._enc_batches = (l1, x, n_full)
         return feats, stereo
 
     def prepare_bev_feat(self, img, sensor2keyego, ego2global, intrin,
@@ -268,6 +270,11 @@ class BEVStereo4DOCC(BaseModule):
         depth_key_frame = None
         feat_prev_iv = None
         enc = self.encode_frames(imgs)
+        if enc is not None and self.extra_ref_frames == 1 and \
+                self.num_frame >= 2 and not kwargs:
+            return self._lift_frames_batched(
+                imgs, sensor2keyegos, ego2globals, intrins, post_rots,
+                post_trans, bda, curr2adjsensor)
         for fid in range(self.num_frame - 1, -1, -1):
             key_frame = fid == 0
             extra_ref_frame = fid == self.num_frame - self.extra_ref_frames
@@ -284,6 +291,50 @@ class BEVStereo4DOCC(BaseModule):
             if not extra_ref_frame:
                 bev_feat_list.append(bev_feat)
             feat_prev_iv = feat_curr_iv
+        return self._fuse_frames(bev_feat_list, dev), depth_key_frame
+
+    def _lift_frames_batched(self, imgs, sensor2keyegos, ego2globals, intrins,
+                             post_rots, post_trans, bda, curr2adjsensor):
+        """DepthNet + cost volume of ALL lifted frames in one batched pass
+        (frame f is a virtual sample: batch = frames x B), then the lift and
+        pre_process_net per frame.  Same kernels on the same per-image data as
+        the frame-by-frame loop of bevdet_occ.py:219-240."""
+        vt = self.img_view_transformer
+        dev = imgs[0].device
+        B, N = imgs[0].shape[:2]
+        bn = B * N
+        l1, x, n_full = self._enc_batches
+        frames = list(range(n_full))                     # 0 = key, 1.. adjacent
+        cat0 = lambda ts: torch.cat([ts[f] for f in frames], dim=0)
+        mlp_input = torch.cat([vt.get_mlp_input(
+            sensor2keyegos[0], ego2globals[0], intrins[f], post_rots[f],
+            post_trans[f], bda) for f in frames], dim=0)
+        # cost volume of frame f: current = layer1 of frame f, previous = frame f+1
+        metas = dict(k2s_sensor=cat0(curr2adjsensor), intrins=cat0(intrins),
+                     post_rots=cat0(post_rots), post_trans=cat0(post_trans),
+                     frustum=vt.cv_frustum, cv_downsample=4,
+                     downsample=vt.downsample, grid_config=vt.grid_config,
+                     cv_feat_list=[ops.to_logical(l1[bn:(n_full + 1) * bn]),
+                                   ops.to_logical(l1[:n_full * bn])])
+        _, cdim, oh, ow = x.shape
+        depth, tran = vt.depth_stage(x.view(n_full * B, N, cdim, oh, ow),
+                                     mlp_input, metas)
+        bev_feat_list = []
+        depth_key_frame = None
+        for fid in reversed(frames):                     # [adjacent.., key]
+            d_f = depth[fid * bn:(fid + 1) * bn]
+            bev = vt.lift_stage(d_f, tran[fid * bn:(fid + 1) * bn],
+                                sensor2keyegos[fid], intrins[fid],
+                                post_rots[fid], post_trans[fid], bda, B, N)
+            # forward hooks registered on the view transformer still see one
+            # (bev_feat, depth) result per lifted frame, in the reference's order
+            for hook in list(vt._forward_hooks.values()):
+                hook(vt, None, (bev, d_f))
+            if self.pre_process:
+                bev = self.pre_process_net(bev)[0]
+            bev_feat_list.append(bev)
+            if fid == 0:
+                depth_key_frame = d_f
         return self._fuse_frames(bev_feat_list, dev), depth_key_frame
 
     def set_camera_shard(self, shard):
