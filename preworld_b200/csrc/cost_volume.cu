@@ -18,7 +18,7 @@ __device__ __forceinline__ float dot3(const float* m, float x, float y, float z)
 }
 
 template <int Q>   // float4 chunks per lane: C == 128*Q
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, Q <= 2 ? 3 : 1)
 cost_volume_kernel(const float* __restrict__ curr, const float* __restrict__ prev,
                    const float* __restrict__ cam, const float* __restrict__ xs,
                    const float* __restrict__ ys, const float* __restrict__ ds,
