@@ -73,10 +73,19 @@ struct HaloParams {
   float* y;
 };
 
-#define PW_TS(k) do { if (p.ts) p.ts[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (k)] = clock64(); } while (0)
+// Timing instrumentation / knock-out experiments (PW_HALO_TS, PW_HALO_DBG) are
+// compiled in only with -DPW_HALO_DEBUG: in the product build they are constant
+// false, so the hot loops carry none of their loads and branches.
+#ifdef PW_HALO_DEBUG
+#define PW_TSON (p.ts != nullptr)
+#define PW_DBG(bit) ((p.dbg & (bit)) != 0)
+#else
+#define PW_TSON false
+#define PW_DBG(bit) false
+#endif
+#define PW_TS(k) do { if (PW_TSON) p.ts[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (k)] = clock64(); } while (0)
 
-template <int MIN_CTAS>   // 2: register-capped variant so two CTAs fit one SM
-__global__ void __launch_bounds__(NUM_THREADS, MIN_CTAS)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
                  const __grid_constant__ CUtensorMap map_bh,
                  const __grid_constant__ CUtensorMap map_bl, const HaloParams p) {
@@ -191,15 +200,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     uint32_t accumulate = 0;                                   // first k-steps overwrite
     long long cyc_b = 0, cyc_a = 0, cyc_i = 0, tq = 0;
     for (int ct = 0; ct < total_ct; ++ct) {
-      if (p.ts) tq = clock64();
+      if (PW_TSON) tq = clock64();
       mbar_wait(b_full + 8 * r, ph);
-      if (p.ts) { cyc_b += clock64() - tq; }
+      if (PW_TSON) { cyc_b += clock64() - tq; }
       const uint64_t bdesc = desc0 + (uint64_t)(desc_stage * (uint32_t)r);
       for (int m = 0; m < p.mt; ++m) {
-        if (p.ts) tq = clock64();
+        if (PW_TSON) tq = clock64();
         mbar_wait(a_full + 8 * (r * p.mt + m), ph);
         tc_fence_after();
-        if (p.ts) { cyc_a += clock64() - tq; tq = clock64(); }
+        if (PW_TSON) { cyc_a += clock64() - tq; tq = clock64(); }
         const uint32_t a_hi = tbase + a_ring_col + (uint32_t)((r * p.mt + m) * A_SLOT_COLS);
         const uint32_t acc = tbase + (uint32_t)(m * tile_cols);
         if (leader) {
@@ -215,7 +224,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
           }
         }
         __syncwarp();
-        if (p.ts) cyc_i += clock64() - tq;
+        if (PW_TSON) cyc_i += clock64() - tq;
       }
       accumulate = 1;
       if (leader) umma_commit(ring_empty + 8 * r);   // weight stage + A slots free on retire
@@ -224,7 +233,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     }
     if (leader) umma_commit(accum_bar);
     __syncwarp();
-    if (p.ts && leader) {
+    if (PW_TSON && leader) {
       long long* t = p.ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
       t[6] = clock64(); t[12] = t[0] + cyc_b; t[13] = t[0] + cyc_a; t[14] = t[0] + cyc_i;
     }
@@ -242,88 +251,105 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     const uint32_t a_ring = tmem_base + lane_field + a_ring_col;
     const uint32_t smem_base_u32 = smem_u32(smem);
 
-    // Iteration state, advanced incrementally (no divisions in the loop):
-    // it = (c*T + t)*mt + m; this set takes it = set, set+SETS, ...
-    struct It { int c, kx, ky, kz, m, r, hs; uint32_t eph, hph; };
-    auto advance = [&](It& s, int steps) {
-      for (int i = 0; i < steps; ++i) {
-        if (++s.m < p.mt) continue;
-        s.m = 0;
-        if (++s.r == p.nb) { s.r = 0; s.eph ^= 1; }
-        if (++s.kx < p.kw) continue;
-        s.kx = 0;
-        if (++s.ky < p.kh) continue;
-        s.ky = 0;
-        if (++s.kz * p.kh * p.kw < T) continue;
-        s.kz = 0;
-        ++s.c;
-        if (++s.hs == p.nh) { s.hs = 0; s.hph ^= 1; }
-      }
+    // This set builds the A tiles of M tile `m_set` for taps tap0, tap0+tstep, ...
+    // of every chunk (it = (c*T + t)*mt + m; sets take it = set, set+SETS, ...;
+    // mt divides SPLIT_SETS).  All state advances incrementally -- the loop body
+    // is the critical instruction stream of the kernel (8 warps on 4 schedulers).
+    const int m_set = set % p.mt;
+    const int tstep = SPLIT_SETS / p.mt;
+    const int thread_row = row_base + m_set * p.mt_halo_off;
+    int c = 0, kx = 0, ky = 0, kz = 0, r = 0, hs = 0;
+    uint32_t eph = 1u, hph = 0u;                         // parities: ring_empty, halo_full
+    auto step_tap = [&]() {                              // advance (c, tap, ring entry) by one tap
+      if (++r == p.nb) { r = 0; eph ^= 1u; }
+      if (++kx < p.kw) return;
+      kx = 0;
+      if (++ky < p.kh) return;
+      ky = 0;
+      if ((++kz) * p.kh * p.kw < T) return;
+      kz = 0;
+      ++c;
+      if (++hs == p.nh) { hs = 0; hph ^= 1u; }
     };
-    auto load_row = [&](const It& s, float4 (&raw)[8]) {
-      const int hrow = row_base + s.m * p.mt_halo_off +
-                       ((s.kz * p.dd) * p.hy + s.ky * p.dh) * p.hx + s.kx * p.dw;
-      const uint32_t src = smem_base_u32 + (uint32_t)(s.hs * p.halo_stride + hrow * ROW_BYTES);
-      const int swz = hrow & 7;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) raw[j] = lds128(src + ((j ^ swz) << 4));
-    };
-
-    It cur{0, 0, 0, 0, 0, 0, 0, 1u, 0u};               // eph = parity to wait on ring_empty
-    advance(cur, set);
-    int released = 0;                                    // halo chunks this warp has released
     float4 raw[8];
-    if (cur.c < p.chunks) {
-      mbar_wait(halo_full + 8 * cur.hs, cur.hph);
+    auto load_row = [&]() {
+      const int hrow = thread_row + ((kz * p.dd) * p.hy + ky * p.dh) * p.hx + kx * p.dw;
+      // 16-byte chunk j of row hrow sits at ((j ^ (hrow & 7)) << 4) (TMA 128B swizzle)
+      const uint32_t b2 = (smem_base_u32 + (uint32_t)(hs * p.halo_stride + hrow * ROW_BYTES)) ^
+                          (uint32_t)((hrow & 7) << 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) raw[j] = lds128(b2 ^ (uint32_t)(j << 4));
+    };
+    for (int q = 0; q < set / p.mt; ++q) step_tap();     // first tap of this set
+    int released = 0;                                    // halo chunks this warp has released
+    int pending = -1;                                    // A slot stored but not yet published
+    long long sp_wait = 0, sp_busy = 0, sp_t0 = 0;       // PW_HALO_TS: cycles waiting / storing
+    if (c < p.chunks) {
+      mbar_wait(halo_full + 8 * hs, hph);
       if (sw_id == 0 && lane == 0) PW_TS(3);
-      load_row(cur, raw);
+      load_row();
     }
-    bool first_it = true;
-    while (cur.c < p.chunks) {
-      const int slot = cur.r * p.mt + cur.m;
+    while (c < p.chunks) {
+      const int slot = r * p.mt + m_set;
       const uint32_t a_col = a_ring + (uint32_t)(slot * A_SLOT_COLS);
-      uint32_t hi[16], lo[16];
+      const int ring_r = r;
+      const uint32_t ring_ph = eph;
+      // hi (columns 0..31) and lo (32..63) of this row, stored by ONE tcgen05.st
+      uint32_t hl[64];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      for (int j = 0; j < 8; ++j) {
+        const float4 v = raw[j];
+        const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 v = raw[half * 4 + j];
-          const float f[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;
-            hi[j * 4 + e] = h;
-            lo[j * 4 + e] = __float_as_uint(f[e] - __uint_as_float(h));
-          }
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;
+          hl[j * 4 + e] = h;
+          hl[BLOCK_K + j * 4 + e] = __float_as_uint(f[e] - __uint_as_float(h));
         }
-        if (half == 0) {
-          mbar_wait(ring_empty + 8 * cur.r, cur.eph);    // MMAs reading this slot retired
-          tc_fence_after();
-        }
-        tmem_st16(a_col + half * 16, hi);
-        tmem_st16(a_col + BLOCK_K + half * 16, lo);
       }
-      // raw[] is consumed: prefetch the next row of this set while the stores drain
-      It nxt = cur;
-      advance(nxt, SPLIT_SETS);
-      const int upto = nxt.c < p.chunks ? nxt.c : p.chunks;
-      while (released < upto) {                          // chunks this warp is done reading
+      // the PREVIOUS row's store is published only now: its completion latency
+      // ran under this row's hi/lo split
+      if (pending >= 0) {
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(halo_empty + 8 * (released % p.nh));
-        ++released;
+        if (lane == 0) mbar_arrive(a_full + 8 * pending);
+        if (PW_TSON) sp_busy += clock64() - sp_t0;
       }
-      if (nxt.c < p.chunks) {
-        mbar_wait(halo_full + 8 * nxt.hs, nxt.hph);
-        load_row(nxt, raw);
+      {
+        long long tw = 0;
+        if (PW_TSON) tw = clock64();
+        mbar_wait(ring_empty + 8 * ring_r, ring_ph);     // MMAs reading this slot retired
+        tc_fence_after();
+        if (PW_TSON) { sp_wait += clock64() - tw; sp_t0 = clock64(); }
       }
+      if (PW_DBG(1024)) tmem_st32(a_col, hl);            // (timing experiment: half the bytes)
+      else if (!PW_DBG(2048)) tmem_st64(a_col, hl);    // (2048: no store at all)
+      pending = slot;
+      // hl[] is handed to the store: only now fetch this set's next row (keeps
+      // raw[] and hl[] from being live together: 4 sets = 608 threads = 104 regs)
+      const int c_prev = c;
+#pragma unroll 1
+      for (int q = 0; q < tstep; ++q) step_tap();
+      if (c != c_prev) {                                 // chunk boundary (rare)
+        const int upto = c < p.chunks ? c : p.chunks;
+#pragma unroll 1
+        while (released < upto) {                        // chunks this warp is done reading
+          __syncwarp();
+          if (lane == 0) mbar_arrive(halo_empty + 8 * (released % p.nh));
+          ++released;
+        }
+        if (c < p.chunks) mbar_wait(halo_full + 8 * hs, hph);
+      }
+      if (c < p.chunks) load_row();
+    }
+    if (pending >= 0) {
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_full + 8 * slot);
-      if (first_it && sw_id == 0 && lane == 0) PW_TS(4);
-      first_it = false;
-      cur = nxt;
+      if (lane == 0) mbar_arrive(a_full + 8 * pending);
     }
+#pragma unroll 1
     while (released < p.chunks) {                        // a set with no work in the last chunks
       __syncwarp();
       if (lane == 0) mbar_arrive(halo_empty + 8 * (released % p.nh));
@@ -334,6 +360,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     //      affine / residual / activation / store (kept small: it is straight-line
     //      code after the main loop and must not thrash the instruction cache) ----
     if (sw_id == 0 && lane == 0) PW_TS(11);
+    if (PW_TSON && sw_id == 0 && lane == 0) {
+      long long* t = p.ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
+      t[15] = t[0] + sp_wait; t[4] = t[0] + sp_busy;
+    }
     const uint32_t stage = smem_base_u32 + (uint32_t)(sw_id * STAGE_BYTES_PER_WARP);
     const int ncg = (p.n_tile + 31) >> 5;
     const int items = p.mt * ncg;
@@ -560,7 +590,7 @@ HaloPlan make_plan(const pw_conv_desc& in) {
           // halo ring
           int nh = min(chunks, 2);
           auto smem_need = [&](int nh_, int nb_) {
-            return (long long)max(nh_ * halo_stride, 8 * STAGE_BYTES_PER_WARP) +
+            return (long long)max(nh_ * halo_stride, 4 * SPLIT_SETS * STAGE_BYTES_PER_WARP) +
                    (long long)nb_ * b_stage + SMEM_SLACK;
           };
           while (nb > 2 && smem_need(nh, nb) > SMEM_LIMIT) --nb;
@@ -585,12 +615,9 @@ HaloPlan make_plan(const pw_conv_desc& in) {
           while (tcols < cols_need) tcols <<= 1;
           const long long smem_cta = smem_need(nh, nb);
           int cps = min(512 / tcols, (int)((228 * 1024 - 1024) / (smem_cta + 1024)));
-          // measured: the register-capped two-CTA variant spills in the split loop and
-          // loses more than the overlap gains; opt-in only (PW_HALO_CPS=2)
-          {
-            const char* e = getenv("PW_HALO_CPS");
-            cps = max(1, min(cps, e ? atoi(e) : 1));
-          }
+          // measured: a register-capped two-CTA-per-SM variant spills in the split
+          // loop and loses more than the overlap gains -> one CTA per SM
+          cps = 1;
           const double waves = (double)((tiles + 148 * cps - 1) / (148 * cps));
           const double cost = waves * cta * (cps == 2 ? 1.3 : 1.0);
           if (best < 0 || cost < best) {
@@ -605,7 +632,7 @@ HaloPlan make_plan(const pw_conv_desc& in) {
             const int hstr[3] = {1, h[0], h[0] * h[1]};
             p.mt_halo_off = mt == 2 ? b[axis] * st[axis] * hstr[axis] : 0;
             p.halo_stride = halo_stride;
-            p.halo_region = max(nh * halo_stride, 8 * STAGE_BYTES_PER_WARP);
+            p.halo_region = max(nh * halo_stride, 4 * SPLIT_SETS * STAGE_BYTES_PER_WARP);
             p.tiles_x = pw_ceil_div(c.ow, cb[0]); p.tiles_y = pw_ceil_div(c.oh, cb[1]);
             p.tiles_z = pw_ceil_div(c.od, cb[2]);
             p.n_tile = n_tile; p.nh = nh; p.nb = nb; p.nacc = nacc;
@@ -690,11 +717,8 @@ PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* 
 
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<1>,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SMEM_LIMIT / 2);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
@@ -704,10 +728,7 @@ PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* 
     cudaMalloc(&p.ts, n_cta * 16 * sizeof(long long));
     cudaMemset(p.ts, 0, n_cta * 16 * sizeof(long long));
   }
-  if (p.cps == 2)
-    conv_halo_kernel<2><<<plan.grid, NUM_THREADS, plan.smem, st>>>(ma, mbh, mbl, p);
-  else
-    conv_halo_kernel<1><<<plan.grid, NUM_THREADS, plan.smem, st>>>(ma, mbh, mbl, p);
+  conv_halo_kernel<<<plan.grid, NUM_THREADS, plan.smem, st>>>(ma, mbh, mbl, p);
   PW_LAUNCH_CHECK();
   if (want_ts) {
     cudaStreamSynchronize(st);
@@ -719,7 +740,7 @@ PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* 
     fprintf(stderr, "[halo ts] grid %u x %u mt %d n_tile %d nh %d nb %d nacc %d box %dx%dx%d halo %dx%dx%d smem %zu tmem %d cps %d:",
             plan.grid.x, plan.grid.y, p.mt, p.n_tile, p.nh, p.nb, p.nacc, p.cbx, p.cby, p.cbz,
             p.hx, p.hy, p.hz, plan.smem, p.tmem_cols, p.cps);
-    for (int k = 0; k < 15; ++k) fprintf(stderr, " t%d=%.0f", k, sum[k] / n_cta);
+    for (int k = 0; k < 16; ++k) fprintf(stderr, " t%d=%.0f", k, sum[k] / n_cta);
     fprintf(stderr, "\n");
     free(h);
     cudaFree(p.ts);
