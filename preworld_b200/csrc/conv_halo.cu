@@ -252,12 +252,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     const uint32_t smem_base_u32 = smem_u32(smem);
 
     // This set builds the A tiles of M tile `m_set` for taps tap0, tap0+tstep, ...
-    // of every chunk (it = (c*T + t)*mt + m; sets take it = set, set+SETS, ...;
-    // mt divides SPLIT_SETS).  All state advances incrementally -- the loop body
+    // of every chunk (it = (c*T + t)*mt + m; sets take it = set, set+SETS, ...).  All state advances incrementally -- the loop body
     // is the critical instruction stream of the kernel (8 warps on 4 schedulers).
-    const int m_set = set % p.mt;
-    const int tstep = SPLIT_SETS / p.mt;
-    const int thread_row = row_base + m_set * p.mt_halo_off;
+    int m_cur = set % p.mt;                              // M tile of the current iteration
     int c = 0, kx = 0, ky = 0, kz = 0, r = 0, hs = 0;
     uint32_t eph = 1u, hph = 0u;                         // parities: ring_empty, halo_full
     auto step_tap = [&]() {                              // advance (c, tap, ring entry) by one tap
@@ -273,7 +270,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     };
     float4 raw[8];
     auto load_row = [&]() {
-      const int hrow = thread_row + ((kz * p.dd) * p.hy + ky * p.dh) * p.hx + kx * p.dw;
+      const int hrow = row_base + m_cur * p.mt_halo_off +
+                       ((kz * p.dd) * p.hy + ky * p.dh) * p.hx + kx * p.dw;
       // 16-byte chunk j of row hrow sits at ((j ^ (hrow & 7)) << 4) (TMA 128B swizzle)
       const uint32_t b2 = (smem_base_u32 + (uint32_t)(hs * p.halo_stride + hrow * ROW_BYTES)) ^
                           (uint32_t)((hrow & 7) << 4);
@@ -290,7 +288,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       load_row();
     }
     while (c < p.chunks) {
-      const int slot = r * p.mt + m_set;
+      const int slot = r * p.mt + m_cur;
       const uint32_t a_col = a_ring + (uint32_t)(slot * A_SLOT_COLS);
       const int ring_r = r;
       const uint32_t ring_ph = eph;
@@ -329,8 +327,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       // hl[] is handed to the store: only now fetch this set's next row (keeps
       // raw[] and hl[] from being live together: 4 sets = 608 threads = 104 regs)
       const int c_prev = c;
+      {                                                  // it += SPLIT_SETS in (tap, m) space
+        const int mm = m_cur + SPLIT_SETS;
+        const int taps = mm / p.mt;                      // mt is 1 or 2
+        m_cur = mm - taps * p.mt;
 #pragma unroll 1
-      for (int q = 0; q < tstep; ++q) step_tap();
+        for (int q = 0; q < taps; ++q) step_tap();
+      }
       if (c != c_prev) {                                 // chunk boundary (rare)
         const int upto = c < p.chunks ? c : p.chunks;
 #pragma unroll 1
