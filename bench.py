@@ -31,6 +31,12 @@ METRIC = 'frames/sec (7-frame, 6-cam 256x704->200x200x16)'
 UNIT = 'frames/s'
 WORKLOAD = ('preworld-7frame-finetune, derived ResNet-50 @ 6x3x256x704 -> '
             '200x200x16, bs=1/GPU, forward-only')
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full
+# (profiles/r01i_hot_kernels.md), for the layer shapes that can lead the step
+NCU_TRAFFIC = {
+    'conv_halo 1x16x200x200x32->32 k333 s1 d1': 242.9e6,
+    'conv_halo 1x16x200x200x32->64 k333 s1 d1': 207.9e6,
+}
 FALLBACK_PEAKS = dict(hbm_gbs=6650.0, bf16_tflops=1590.0,
                       bf16_tflops_sustained=1400.0)
 
@@ -382,16 +388,30 @@ def main():
                      'split, TMA)') if top == 'pw_conv_halo_fwd' else (
                      'conv_umma_kernel (pw_conv_umma_fwd: tcgen05 kind::tf32 '
                      'implicit GEMM, 3xTF32 split, TMA)')
-            roof = {'kernel': kname,
-                    'bound': 'tensor', 'achieved': k['tflops'],
+            # the roofline line is quoted on the kernel's heaviest LAYER SHAPE
+            # (per-launch figures); the whole family is reported next to it
+            fam = top[3:-4] + ' '
+            lname, lay = max(((n, v) for n, v in prof.layers.items()
+                              if n.startswith(fam)),
+                             key=lambda kv: kv[1]['ms_per_step'])
+            roof = {'kernel': kname, 'layer': lname,
+                    'bound': 'tensor', 'achieved': lay['tflops'],
                     'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                    'frac': k['tflops'] / peaks['bf16_tflops_sustained'],
-                    'traffic': None, 'peak_source': peak_src,
+                    'frac': lay['tflops'] / peaks['bf16_tflops_sustained'],
+                    'traffic': NCU_TRAFFIC.get(lname), 'peak_source': peak_src,
+                    'launch_us': 1e3 * lay['ms_per_step'] / lay['launches_per_step'],
                     'share_of_step': k['ms_per_step'] / (ms / args.steps),
-                    'note': 'achieved = ALGORITHMIC fp32 conv FLOPs / time; '
-                            'the kernel executes 3 tf32 MMAs per algorithmic '
-                            'MMA (tf32 dense peak is half the bf16 peak), so '
-                            'the executed-tensor-work fraction is 6x this'}
+                    'family': {'launches_per_step': k['launches_per_step'],
+                               'ms_per_step': k['ms_per_step'],
+                               'achieved': k['tflops'],
+                               'frac': k['tflops'] / peaks['bf16_tflops_sustained']},
+                    'note': 'achieved = ALGORITHMIC fp32 conv FLOPs of one launch '
+                            '/ its average duration (CUDA events); the kernel '
+                            'executes 3 tf32 MMAs per algorithmic MMA (tf32 dense '
+                            'peak is half the bf16 peak), so the executed-tensor-'
+                            'work fraction is 6x this; traffic = ncu dram bytes '
+                            'read+write of one launch of this layer shape '
+                            '(profiles/r01i_hot_kernels.md)'}
         elif top == 'pw_conv_fwd':
             roof = {'kernel': 'conv_igemm_kernel (pw_conv_fwd, fp32 SIMT '
                               'implicit GEMM; all conv/linear layers)',
