@@ -298,12 +298,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       for (int j = 0; j < 8; ++j) {
         const float4 v = raw[j];
         const float f[4] = {v.x, v.y, v.z, v.w};
+        float lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;
-          hl[j * 4 + e] = h;
-          hl[BLOCK_K + j * 4 + e] = __float_as_uint(f[e] - __uint_as_float(h));
-        }
+        for (int e = 0; e < 4; ++e) hl[j * 4 + e] = __float_as_uint(f[e]) & 0xFFFFE000u;
+        // lo = x - hi, two elements per FADD2 (exact either way: no rounding occurs)
+        sub2(f[0], f[1], __uint_as_float(hl[j * 4]), __uint_as_float(hl[j * 4 + 1]), lo[0], lo[1]);
+        sub2(f[2], f[3], __uint_as_float(hl[j * 4 + 2]), __uint_as_float(hl[j * 4 + 3]), lo[2],
+             lo[3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) hl[BLOCK_K + j * 4 + e] = __float_as_uint(lo[e]);
       }
       // the PREVIOUS row's store is published only now: its completion latency
       // ran under this row's hi/lo split

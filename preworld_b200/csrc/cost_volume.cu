@@ -17,6 +17,26 @@ __device__ __forceinline__ float dot3(const float* m, float x, float y, float z)
   return fmaf(m[2], z, acc);
 }
 
+__device__ __forceinline__ unsigned long long pack2(float x, float y) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b,
+                                                   unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 template <int Q>   // float4 chunks per lane: C == 128*Q
 __global__ void __launch_bounds__(256, Q <= 2 ? 3 : 1)
 cost_volume_kernel(const float* __restrict__ curr, const float* __restrict__ prev,
@@ -127,19 +147,25 @@ cost_volume_kernel(const float* __restrict__ curr, const float* __restrict__ pre
       }
       float part = 0.f;
       bool zero_flag = false;
+      // packed fp32x2 arithmetic (FMUL2 / FFMA2 / FADD2): two channels per instruction
+      const unsigned long long w2nw = pack2(wnw, wnw), w2ne = pack2(wne, wne),
+                               w2sw = pack2(wsw, wsw), w2se = pack2(wse, wse);
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
-        float4 acc;
-        acc.x = c00[q].x * wnw; acc.y = c00[q].y * wnw; acc.z = c00[q].z * wnw; acc.w = c00[q].w * wnw;
-        acc.x = fmaf(c01[q].x, wne, acc.x); acc.y = fmaf(c01[q].y, wne, acc.y);
-        acc.z = fmaf(c01[q].z, wne, acc.z); acc.w = fmaf(c01[q].w, wne, acc.w);
-        acc.x = fmaf(c10[q].x, wsw, acc.x); acc.y = fmaf(c10[q].y, wsw, acc.y);
-        acc.z = fmaf(c10[q].z, wsw, acc.z); acc.w = fmaf(c10[q].w, wsw, acc.w);
-        acc.x = fmaf(c11[q].x, wse, acc.x); acc.y = fmaf(c11[q].y, wse, acc.y);
-        acc.z = fmaf(c11[q].z, wse, acc.z); acc.w = fmaf(c11[q].w, wse, acc.w);
-        part += ((fabsf(cur[q].x - acc.x) + fabsf(cur[q].y - acc.y)) + fabsf(cur[q].z - acc.z)) +
-                fabsf(cur[q].w - acc.w);
-        if (q == own_q && lane == own_lane) zero_flag = (acc.x == 0.f);
+        unsigned long long a01 = mul2(pack2(c00[q].x, c00[q].y), w2nw);
+        unsigned long long a23 = mul2(pack2(c00[q].z, c00[q].w), w2nw);
+        a01 = fma2(pack2(c01[q].x, c01[q].y), w2ne, a01);
+        a23 = fma2(pack2(c01[q].z, c01[q].w), w2ne, a23);
+        a01 = fma2(pack2(c10[q].x, c10[q].y), w2sw, a01);
+        a23 = fma2(pack2(c10[q].z, c10[q].w), w2sw, a23);
+        a01 = fma2(pack2(c11[q].x, c11[q].y), w2se, a01);
+        a23 = fma2(pack2(c11[q].z, c11[q].w), w2se, a23);
+        float ax, ay, az, aw;
+        unpack2(a01, ax, ay);
+        unpack2(a23, az, aw);
+        part += ((fabsf(cur[q].x - ax) + fabsf(cur[q].y - ay)) + fabsf(cur[q].z - az)) +
+                fabsf(cur[q].w - aw);
+        if (q == own_q && lane == own_lane) zero_flag = (ax == 0.f);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);

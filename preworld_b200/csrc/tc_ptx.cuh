@@ -25,6 +25,15 @@ __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
                ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// packed fp32x2 subtract (one FADD2 for two lanes' worth of work): {a.x-b.x, a.y-b.y}
+__device__ __forceinline__ void sub2(float ax, float ay, float bx, float by, float& rx, float& ry) {
+  unsigned long long a, b, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(ax), "f"(ay));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(bx), "f"(by));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(rx), "=f"(ry) : "l"(r));
+}
+
 // ---- mbarrier ----------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
