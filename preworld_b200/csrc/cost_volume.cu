@@ -38,7 +38,7 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 }
 
 template <int Q>   // float4 chunks per lane: C == 128*Q
-__global__ void __launch_bounds__(256, Q <= 2 ? 3 : 1)
+__global__ void __launch_bounds__(256, Q <= 2 ? 2 : 1)
 cost_volume_kernel(const float* __restrict__ curr, const float* __restrict__ prev,
                    const float* __restrict__ cam, const float* __restrict__ xs,
                    const float* __restrict__ ys, const float* __restrict__ ds,
