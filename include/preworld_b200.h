@@ -317,6 +317,19 @@ int pw_render_rays(const pw_render_desc* desc, const float* rays, int n_rays,
                    int col_ld, float* out_depth, float* out_sem, float* out_col,
                    float* out_last, unsigned char* out_valid, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Evaluation: confusion matrices of Metric_mIoU.add_batch,
+ * mmdet3d/datasets/occ_metrics.py:93-157, accumulated on the device.
+ *   pred, gt: uint8 class grids (any order, n voxels); mask: uint8/bool or NULL
+ *   (mask_camera / mask_lidar); hist [n_cl*n_cl] int64: hist[gt*n_cl+pred] += 1
+ *   for masked voxels with gt < n_cl; occ_hist [4] int64: (gt != free)*2 +
+ *   (pred != free) over all masked voxels.  Both accumulate (zero them once).
+ * ---------------------------------------------------------------------- */
+int pw_occ_confusion(const unsigned char* pred, const unsigned char* gt,
+                     const unsigned char* mask, long long n, int n_cl,
+                     int free_idx, long long* hist, long long* occ_hist,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,47 @@
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): numpy restatement of
+Metric_mIoU (mmdet3d/datasets/occ_metrics.py:93-185) used to check
+preworld_b200.metrics / pw_occ_confusion.  Parity pin: the reference ships no
+test for it; the restatement follows the reference line by line and is
+checked against a brute-force loop in tests/test_oracle.py."""
+import numpy as np
+
+
+def hist_info(n_cl, pred, gt):                   # occ_metrics.py:93-113
+    k = (gt >= 0) & (gt < n_cl)
+    return np.bincount(n_cl * gt[k].astype(int) + pred[k].astype(int),
+                       minlength=n_cl ** 2).reshape(n_cl, n_cl)
+
+
+def per_class_iu(hist):                          # occ_metrics.py:115-117
+    with np.errstate(divide='ignore', invalid='ignore'):
+        return np.diag(hist) / (hist.sum(1) + hist.sum(0) - np.diag(hist))
+
+
+class MetricRef:
+    def __init__(self, num_classes=18, use_lidar_mask=False,
+                 use_image_mask=False):
+        self.num_classes = num_classes
+        self.use_lidar_mask, self.use_image_mask = use_lidar_mask, use_image_mask
+        self.hist = np.zeros((num_classes, num_classes))
+        self.occ_hist = np.zeros((2, 2))
+        self.cnt = 0
+
+    def add_batch(self, pred, gt, mask_lidar=None, mask_camera=None):
+        self.cnt += 1                            # occ_metrics.py:133-157
+        if self.use_image_mask:
+            gt, pred = gt[mask_camera], pred[mask_camera]
+        elif self.use_lidar_mask:
+            gt, pred = gt[mask_lidar], pred[mask_lidar]
+        self.hist += hist_info(self.num_classes, pred.flatten(), gt.flatten())
+        free = 17
+        occ_pred = np.zeros_like(pred); occ_pred[pred != free] = 1
+        occ_gt = np.zeros_like(gt); occ_gt[gt != free] = 1
+        self.occ_hist += hist_info(2, occ_pred.flatten(), occ_gt.flatten())
+
+    def count_miou(self):
+        m = per_class_iu(self.hist)
+        return m, round(np.nanmean(m[:self.num_classes - 1]) * 100, 2)
+
+    def count_iou(self):
+        i = per_class_iu(self.occ_hist)
+        return i, round(i[-1] * 100, 2)

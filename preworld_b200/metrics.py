@@ -1,0 +1,90 @@
+"""Occupancy metrics accumulated on the device.
+
+``Metric_mIoU`` mirrors mmdet3d/datasets/occ_metrics.py:52-185 (same
+constructor flags, ``add_batch`` / ``count_miou`` / ``count_iou``), but takes
+the uint8 occupancy grids as CUDA tensors and keeps the 18x18 and 2x2 confusion
+matrices on the GPU (``pw_occ_confusion``): the eval loop of
+mmdet3d/apis/test.py:62-103 no longer needs a ``.cpu().numpy()`` per sample;
+only ``count_*`` reads 328 integers back."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+
+CLASS_NAMES = ['others', 'barrier', 'bicycle', 'bus', 'car',
+               'construction_vehicle', 'motorcycle', 'pedestrian',
+               'traffic_cone', 'trailer', 'truck', 'driveable_surface',
+               'other_flat', 'sidewalk', 'terrain', 'manmade', 'vegetation',
+               'free']
+
+
+def _u8(t, dev):
+    t = torch.as_tensor(t)
+    if t.dtype == torch.bool:
+        t = t.to(torch.uint8)
+    if t.dtype != torch.uint8:
+        raise TypeError('occupancy grids / masks are uint8 (or bool) tensors')
+    t = t.to(dev).contiguous()
+    if not t.is_cuda:
+        raise RuntimeError('preworld_b200 metrics run on CUDA tensors only')
+    return t
+
+
+class Metric_mIoU:
+    def __init__(self, save_dir='.', num_classes=18, use_lidar_mask=False,
+                 use_image_mask=False, device='cuda'):
+        self.class_names = CLASS_NAMES
+        self.occ_names = ['free', 'occupied']
+        self.num_classes = num_classes
+        self.use_lidar_mask = use_lidar_mask
+        self.use_image_mask = use_image_mask
+        self.device = torch.device(device)
+        self.hist_dev = torch.zeros(num_classes * num_classes, dtype=torch.int64,
+                                    device=self.device)
+        self.occ_hist_dev = torch.zeros(4, dtype=torch.int64, device=self.device)
+        self.cnt = 0
+
+    # occ_metrics.py:133-157
+    def add_batch(self, semantics_pred, semantics_gt, mask_lidar=None,
+                  mask_camera=None):
+        self.cnt += 1
+        pred = _u8(semantics_pred, self.device)
+        gt = _u8(semantics_gt, self.device)
+        assert pred.shape == gt.shape
+        mask = None
+        if self.use_image_mask:
+            mask = _u8(mask_camera, self.device)
+        elif self.use_lidar_mask:
+            mask = _u8(mask_lidar, self.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        check(_lib.lib().pw_occ_confusion(
+            p(pred), p(gt), p(mask), pred.numel(), self.num_classes,
+            self.num_classes - 1, p(self.hist_dev), p(self.occ_hist_dev),
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+            'pw_occ_confusion')
+
+    @property
+    def hist(self):
+        n = self.num_classes
+        return self.hist_dev.cpu().numpy().reshape(n, n).astype(np.float64)
+
+    @property
+    def occ_hist(self):
+        return self.occ_hist_dev.cpu().numpy().reshape(2, 2).astype(np.float64)
+
+    @staticmethod
+    def per_class_iu(hist):                      # occ_metrics.py:115-117
+        with np.errstate(divide='ignore', invalid='ignore'):
+            return np.diag(hist) / (hist.sum(1) + hist.sum(0) - np.diag(hist))
+
+    def count_miou(self):                        # occ_metrics.py:159-175
+        mIoU = self.per_class_iu(self.hist)
+        res = round(np.nanmean(mIoU[:self.num_classes - 1]) * 100, 2)
+        return self.class_names, mIoU, self.cnt, res
+
+    def count_iou(self):                         # occ_metrics.py:177-185
+        IoU = self.per_class_iu(self.occ_hist)
+        return self.occ_names, IoU, self.cnt, round(IoU[-1] * 100, 2)

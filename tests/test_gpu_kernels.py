@@ -452,3 +452,27 @@ def test_render_rays_matches_reference_fixture(golden_dir, library_order):
         assert err < 1e-3, (k, err)
         assert np.median(np.abs(got - fx[k])) / scale < 1e-5, k
     assert (out['render_depth'].cpu().numpy()[~mask] == 0).all()
+
+
+def test_device_miou_matches_oracle_bit_exact():
+    """preworld_b200.metrics.Metric_mIoU (pw_occ_confusion) vs the numpy
+    restatement of occ_metrics.py:93-185: integer confusion matrices identical,
+    over several samples, with and without the camera mask, 255 = unlabelled."""
+    from oracle.metrics_ref import MetricRef
+    from preworld_b200.metrics import Metric_mIoU
+    rng = np.random.default_rng(1)
+    for use_mask in (False, True):
+        ref = MetricRef(use_image_mask=use_mask)
+        dev = Metric_mIoU(use_image_mask=use_mask)
+        for _ in range(3):
+            pred = rng.integers(0, 18, (200, 200, 16)).astype(np.uint8)
+            gt = rng.integers(0, 18, (200, 200, 16)).astype(np.uint8)
+            gt[rng.random(gt.shape) < 0.05] = 255
+            mask = rng.random(gt.shape) < 0.6
+            ref.add_batch(pred, gt, None, mask)
+            dev.add_batch(torch.from_numpy(pred).to(DEV), torch.from_numpy(gt).to(DEV),
+                          None, torch.from_numpy(mask).to(DEV))
+        assert np.array_equal(dev.hist, ref.hist)
+        assert np.array_equal(dev.occ_hist, ref.occ_hist)
+        assert dev.count_miou()[3] == ref.count_miou()[1]
+        assert dev.count_iou()[3] == ref.count_iou()[1]
