@@ -201,6 +201,21 @@ int pw_lift_fused(const float* depth, const float* feat, int feat_ld,
                   const float* interval, int b, int n, int d, int h, int w,
                   int c, int gx, int gy, int gz, float* out, void* workspace,
                   void* stream);
+/* The same lift split in two for CONSTANT cameras -- the reference's
+ * LSSViewTransformer(accelerate=True) (view_transformer.py:31-33,155-174,
+ * 263-295: init_acceleration_v2 caches ranks/intervals once, every later
+ * forward only calls bev_pool_v2):
+ *   pw_lift_prepare builds the per-voxel point lists in `workspace`
+ *   (same size / zeroed-control-words contract as pw_lift_fused);
+ *   pw_lift_pool pools depth x feat with those lists: ONE pass, every output
+ *   row written exactly once.  Results are identical to pw_lift_fused. */
+int pw_lift_prepare(const float* cam, const float* bda, const float* xs,
+                    const float* ys, const float* ds, const float* lower,
+                    const float* interval, int b, int n, int d, int h, int w,
+                    int gx, int gy, int gz, void* workspace, void* stream);
+int pw_lift_pool(const float* depth, const float* feat, int feat_ld, int b,
+                 int n, int d, int h, int w, int c, int gx, int gy, int gz,
+                 float* out, void* workspace, void* stream);
 /* Per-camera constant tables (device in, device out, no host round trip):
  * the torch.inverse/matmul prologues of get_lidar_coor
  * (view_transformer.py:141-150) and DepthNet.gen_grid (:552-566).

@@ -77,6 +77,11 @@ SIGNATURES = {
                       ctypes.POINTER(c_f), ctypes.POINTER(c_f),
                       c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                       c_int, c_p, c_p, c_p],
+    'pw_lift_prepare': [c_p, c_p, c_p, c_p, c_p, ctypes.POINTER(c_f),
+                        ctypes.POINTER(c_f), c_int, c_int, c_int, c_int, c_int,
+                        c_int, c_int, c_int, c_p, c_p],
+    'pw_lift_pool': [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                     c_int, c_int, c_int, c_p, c_p, c_p],
     'pw_lift_ranks': [c_p, c_p, c_p, c_p, c_p, ctypes.POINTER(c_f),
                       ctypes.POINTER(c_f), c_int, c_int, c_int, c_int, c_int,
                       c_int, c_int, c_int, c_p, c_p],

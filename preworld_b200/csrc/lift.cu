@@ -124,7 +124,12 @@ __device__ __forceinline__ void lift_stamp(unsigned* ctrl, int k) {
   }
 }
 
-template <int CPL>   // channels per lane: C <= 32*CPL
+// MODE 0: everything (lists rebuilt every call -- the reference's default path);
+// MODE 1: phases 0-3 only (build the lists: LSSViewTransformer(accelerate=True),
+//         view_transformer.py:155-174,263-267, constant cameras);
+// MODE 2: pool with the lists left in the workspace by MODE 1 (the reference's
+//         bev_pool_v2 on pre-computed ranks, :273-287): ONE pass over the output.
+template <int CPL, int MODE>   // channels per lane: C <= 32*CPL
 __global__ void __launch_bounds__(LIFT_THREADS, 2)
 lift_fused_kernel(const LiftFused a) {
   __shared__ int s_scan[LIFT_THREADS / 32];
@@ -138,8 +143,10 @@ lift_fused_kernel(const LiftFused a) {
   const unsigned G = gridDim.x;
   const long long n4 = a.V * a.C / 4;                // host guarantees V*C % 4 == 0
   unsigned* bar = a.ctrl;
+  unsigned nbar = 0;                                   // grid barriers passed so far
 
   lift_stamp(a.ctrl, 0);
+  if (MODE != 2) {
   // ---- phase 0 -------------------------------------------------------------
   {
     int4* c4 = reinterpret_cast<int4*>(a.count);       // count[] is 256-byte aligned, padded
@@ -147,8 +154,8 @@ lift_fused_kernel(const LiftFused a) {
     for (long long i = tid; i < n; i += nthreads) c4[i] = make_int4(0, 0, 0, 0);
   }
   grid_arrive(bar);
-  zero_slice(a.out, n4, 0, 4);
-  grid_wait(bar, G);
+  if (MODE == 0) zero_slice(a.out, n4, 0, 4);
+  grid_wait(bar, ++nbar * G);
   lift_stamp(a.ctrl, 1);
 
   // ---- phase 1: rank + slot (4 points per thread in flight) -------------------
@@ -173,8 +180,8 @@ lift_fused_kernel(const LiftFused a) {
     }
   }
   grid_arrive(bar);
-  zero_slice(a.out, n4, 1, 4);
-  grid_wait(bar, 2 * G);
+  if (MODE == 0) zero_slice(a.out, n4, 1, 4);
+  grid_wait(bar, ++nbar * G);
   lift_stamp(a.ctrl, 2);
 
   // ---- phase 2: list offsets.  CTA b owns voxels [b*VB, (b+1)*VB), VB a multiple
@@ -221,8 +228,8 @@ lift_fused_kernel(const LiftFused a) {
     }
   }
   grid_arrive(bar);
-  zero_slice(a.out, n4, 2, 4);
-  grid_wait(bar, 3 * G);
+  if (MODE == 0) zero_slice(a.out, n4, 2, 4);
+  grid_wait(bar, ++nbar * G);
   lift_stamp(a.ctrl, 3);
 
   // ---- phase 3: fill the per-voxel lists ------------------------------------------
@@ -241,10 +248,13 @@ lift_fused_kernel(const LiftFused a) {
     for (int u = 0; u < 4; ++u)
       if (r[u] >= 0) a.list[dst[u]] = (int)(p0 + u * nthreads);
   }
-  zero_slice(a.out, n4, 3, 4);               // must be ordered before phase 4's overwrites
+  if (MODE == 0) zero_slice(a.out, n4, 3, 4);   // must be ordered before phase 4's overwrites
   grid_arrive(bar);
-  grid_wait(bar, 4 * G);
+  grid_wait(bar, ++nbar * G);
   lift_stamp(a.ctrl, 4);
+  }  // MODE != 2
+
+  if (MODE != 1) {
 
   // ---- phase 4: pool.  One warp per group of 32 consecutive voxels, cut into
   // batches of consecutive voxels with <= 32 points in total; lane i of a batch
@@ -319,12 +329,13 @@ lift_fused_kernel(const LiftFused a) {
     __syncwarp();
   };
 
+  const long long grp0 = gwarp;
   int cnt_n = 0, st_n = 0;                              // prefetched for the next group
-  if (gwarp < ngroups && gwarp * 32 + lane < a.V) {
-    cnt_n = __ldcg(a.count + gwarp * 32 + lane);
-    st_n = __ldcg(a.start + gwarp * 32 + lane);
+  if (grp0 < ngroups && grp0 * 32 + lane < a.V) {
+    cnt_n = __ldcg(a.count + grp0 * 32 + lane);
+    st_n = __ldcg(a.start + grp0 * 32 + lane);
   }
-  for (long long grp = gwarp; grp < ngroups; grp += nwarps) {
+  for (long long grp = grp0; grp < ngroups; grp += nwarps) {
     const long long v0 = grp * 32;
     const int cnt = cnt_n, st = st_n;
     {
@@ -334,6 +345,15 @@ lift_fused_kernel(const LiftFused a) {
       st_n = ok ? __ldcg(a.start + vn) : 0;
     }
     const unsigned nonempty = __ballot_sync(0xffffffffu, cnt > 0);
+    if (MODE == 2) {
+      // single pass: this warp also writes the zero rows of its group (non-empty
+      // rows are overwritten below / in phase 5, after these stores in program
+      // resp. barrier order)
+      const long long e0 = v0 * a.C, e1 = min(a.V, v0 + 32) * a.C;   // multiples of 4
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (long long e = e0 + lane * 4; e < e1; e += 128)
+        __stcs(reinterpret_cast<float4*>(a.out + e), z);
+    }
     if (nonempty == 0) continue;                       // rows already zero
     int incl = cnt;
 #pragma unroll
@@ -365,7 +385,7 @@ lift_fused_kernel(const LiftFused a) {
   }
   lift_stamp(a.ctrl, 5);
   grid_arrive(bar);
-  grid_wait(bar, 5 * G);
+  grid_wait(bar, ++nbar * G);
   lift_stamp(a.ctrl, 6);
 
   // ---- phase 5: one warp per queued item: a batch of a crowded group, or a
@@ -439,6 +459,7 @@ lift_fused_kernel(const LiftFused a) {
       if (ch < a.C) a.out[v * a.C + ch] = acc[qc];
     }
   }
+  }  // MODE != 1
   lift_stamp(a.ctrl, 7);
   // leave the control words zeroed for the next call: the last CTA to get here
   // knows every CTA is past its final barrier wait
@@ -510,7 +531,7 @@ inline LiftGeom make_geom(const float* cam, const float* bda, const float* xs, c
   return g;
 }
 
-template <int CPL>
+template <int CPL, int MODE>
 int launch_lift_fused(const LiftFused& a, cudaStream_t st) {
   // persistent grid: every CTA must be co-resident (grid barriers)
   static int ctas_per_sm = 0, sms = 0;
@@ -519,14 +540,14 @@ int launch_lift_fused(const LiftFused& a, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &ctas_per_sm, lift_fused_kernel<CPL>, LIFT_THREADS, 0);
+        &ctas_per_sm, lift_fused_kernel<CPL, MODE>, LIFT_THREADS, 0);
     if (e != cudaSuccess) return (int)e;
     if (ctas_per_sm < 1) return PW_ERR_INVALID_ARGUMENT;
     if (ctas_per_sm > 2) ctas_per_sm = 2;
   }
   // grid == resident capacity, so all CTAs are co-resident as soon as the SMs
   // drain (same guarantee a cooperative launch checks, without its launch cost)
-  lift_fused_kernel<CPL><<<sms * ctas_per_sm, LIFT_THREADS, 0, st>>>(a);
+  lift_fused_kernel<CPL, MODE><<<sms * ctas_per_sm, LIFT_THREADS, 0, st>>>(a);
   PW_LAUNCH_CHECK();
   return 0;
 }
@@ -569,8 +590,8 @@ PW_API int pw_lift_fused(const float* depth, const float* feat, int feat_ld, con
   a.depth = depth; a.feat = feat; a.feat_ld = feat_ld; a.C = c; a.out = out;
   a.rank = ws.rank; a.slot = ws.slot; a.count = ws.count; a.start = ws.start; a.list = ws.list;
   a.ctrl = ws.ctrl; a.P = P; a.V = V;
-  int rc = c <= 32 ? launch_lift_fused<1>(a, st)
-                   : (c <= 64 ? launch_lift_fused<2>(a, st) : launch_lift_fused<4>(a, st));
+  int rc = c <= 32 ? launch_lift_fused<1, 0>(a, st)
+                   : (c <= 64 ? launch_lift_fused<2, 0>(a, st) : launch_lift_fused<4, 0>(a, st));
   if (rc != 0) return rc;
   pw_count_launch(1);
   return 0;
@@ -590,5 +611,50 @@ PW_API int pw_bev_pool_v2(int c, int n_intervals, const float* depth, const floa
       c, n_intervals, depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,
       interval_lengths, out);
   PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+/* LSSViewTransformer(accelerate=True), view_transformer.py:155-174,263-295: the
+ * cameras are constant, so the voxel lists are built once ... */
+PW_API int pw_lift_prepare(const float* cam, const float* bda, const float* xs, const float* ys,
+                           const float* ds, const float* lower, const float* interval, int b,
+                           int n, int d, int h, int w, int gx, int gy, int gz, void* workspace,
+                           void* stream) {
+  PW_REQUIRE(cam && bda && xs && ys && ds && lower && interval && workspace);
+  long long P = (long long)b * n * d * h * w, V = (long long)b * gx * gy * gz;
+  PW_REQUIRE(P > 0 && P < (1ll << 31) && V > 0 && V < (1ll << 31));
+  LiftWs ws = carve(workspace, P, V);
+  LiftFused a{};
+  a.g = make_geom(cam, bda, xs, ys, ds, lower, interval, b, n, d, h, w, gx, gy, gz);
+  a.C = 4;
+  a.rank = ws.rank; a.slot = ws.slot; a.count = ws.count; a.start = ws.start; a.list = ws.list;
+  a.ctrl = ws.ctrl; a.P = P; a.V = V;
+  int rc = launch_lift_fused<1, 1>(a, (cudaStream_t)stream);
+  if (rc != 0) return rc;
+  pw_count_launch(1);
+  return 0;
+}
+
+/* ... and every later call only pools (the reference's bev_pool_v2 on its
+ * pre-computed ranks): one pass, every output row written exactly once. */
+PW_API int pw_lift_pool(const float* depth, const float* feat, int feat_ld, int b, int n, int d,
+                        int h, int w, int c, int gx, int gy, int gz, float* out, void* workspace,
+                        void* stream) {
+  PW_REQUIRE(depth && feat && out && workspace);
+  PW_REQUIRE(c > 0 && c <= 128 && feat_ld >= c && (c & 3) == 0);
+  long long P = (long long)b * n * d * h * w, V = (long long)b * gx * gy * gz;
+  PW_REQUIRE(P > 0 && P < (1ll << 31) && V > 0 && V < (1ll << 31));
+  PW_REQUIRE(((uintptr_t)out & 15) == 0);
+  LiftWs ws = carve(workspace, P, V);
+  LiftFused a{};
+  a.g.B = b; a.g.N = n; a.g.D = d; a.g.H = h; a.g.W = w; a.g.gx = gx; a.g.gy = gy; a.g.gz = gz;
+  a.depth = depth; a.feat = feat; a.feat_ld = feat_ld; a.C = c; a.out = out;
+  a.rank = ws.rank; a.slot = ws.slot; a.count = ws.count; a.start = ws.start; a.list = ws.list;
+  a.ctrl = ws.ctrl; a.P = P; a.V = V;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = c <= 32 ? launch_lift_fused<1, 2>(a, st)
+                   : (c <= 64 ? launch_lift_fused<2, 2>(a, st) : launch_lift_fused<4, 2>(a, st));
+  if (rc != 0) return rc;
+  pw_count_launch(1);
   return 0;
 }

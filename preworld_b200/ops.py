@@ -443,6 +443,37 @@ def lift_fused(depth, feat_cl, cam, bda, xs, ys, ds, lower, interval, b, n,
     return out
 
 
+def lift_prepare(cam, bda, xs, ys, ds, lower, interval, b, n, grid):
+    """Build the voxel point lists for constant cameras (accelerate=True);
+    returns the workspace tensor to hand to ``lift_pool``."""
+    _require_cuda(cam, bda)
+    d, h, w = ds.numel(), ys.numel(), xs.numel()
+    gx, gy, gz = grid
+    nbytes = int(_lib.lib().pw_lift_workspace_bytes(b, n, d, h, w, gx, gy, gz))
+    ws = torch.zeros(nbytes, device=cam.device, dtype=torch.uint8)
+    check(_lib.lib().pw_lift_prepare(
+        _ptr(cam), _ptr(bda), _ptr(xs), _ptr(ys), _ptr(ds), _f3(lower),
+        _f3(interval), b, n, d, h, w, gx, gy, gz, _ptr(ws), _stream()),
+        'pw_lift_prepare')
+    return ws
+
+
+def lift_pool(depth, feat_cl, ws, b, n, grid, out=None):
+    """Pool with the lists of ``lift_prepare``: one pass over the output."""
+    _require_cuda(depth, feat_cl, ws)
+    _, d, h, w = depth.shape
+    c = feat_cl.shape[-1]
+    gx, gy, gz = grid
+    assert depth.is_contiguous() and depth.shape[0] == b * n
+    if out is None:
+        out = torch.empty((b, gz, gy, gx, c), device=depth.device,
+                          dtype=torch.float32)
+    check(_lib.lib().pw_lift_pool(
+        _ptr(depth), _ptr(feat_cl), cl_ld(feat_cl), b, n, d, h, w, c, gx, gy,
+        gz, _ptr(out), _ptr(ws), _stream()), 'pw_lift_pool')
+    return out
+
+
 # ------------------------------------------------------------------ 3-D side
 def upsample_trilinear_(out, x):
     """out [B,OZ,OY,OX,C] (may be a channel slice) = trilinear(x), align_corners."""

@@ -172,10 +172,10 @@ class LSSViewTransformerBEVStereo(BaseModule):
                  collapse_z=True, loss_depth_weight=3.0, depthnet_cfg=dict(),
                  init_cfg=None):
         super().__init__(init_cfg)
-        if accelerate or sid or collapse_z:
+        if sid or collapse_z:
             raise NotImplementedError(
-                'accelerate / sid / collapse_z are off in the PreWorld '
-                'configs (bevstereo-occ.py:76-89)')
+                'sid / collapse_z are off in the PreWorld configs '
+                '(bevstereo-occ.py:76-89)')
         self.grid_config = grid_config
         self.input_size = tuple(input_size)
         self.downsample = downsample
@@ -193,6 +193,10 @@ class LSSViewTransformerBEVStereo(BaseModule):
         self.depth_net = DepthNet(in_channels, in_channels, out_channels,
                                   self.D, **depthnet_cfg)
         self._consts = {}
+        # accelerate=True (view_transformer.py:31-33,263-267): constant cameras,
+        # the voxel lists are built by the first forward and reused
+        self.initial_flag = True
+        self._accel_ws = None
 
     # -- reference-visible geometry attributes ------------------------------
     def create_grid_infos(self, x, y, z, **kwargs):
@@ -331,10 +335,19 @@ class LSSViewTransformerBEVStereo(BaseModule):
                                      post_tran)
         xs, ys, ds = self._frustum_axes(self.frustum, dev)
         grid = tuple(int(g) for g in self.grid_size)
-        bev = ops.lift_fused(
-            depth, tran_feat, cam, bda.reshape(B, 9).contiguous().float(),
-            xs, ys, ds, self.grid_lower_bound.tolist(),
-            self.grid_interval.tolist(), B, N, grid)
+        bda9 = bda.reshape(B, 9).contiguous().float()
+        if self.accelerate:
+            if self.initial_flag:                       # pre_compute(), :263-267
+                self._accel_ws = ops.lift_prepare(
+                    cam, bda9, xs, ys, ds, self.grid_lower_bound.tolist(),
+                    self.grid_interval.tolist(), B, N, grid)
+                self.initial_flag = False
+            bev = ops.lift_pool(depth, tran_feat, self._accel_ws, B, N, grid)
+        else:
+            bev = ops.lift_fused(
+                depth, tran_feat, cam, bda9, xs, ys, ds,
+                self.grid_lower_bound.tolist(), self.grid_interval.tolist(),
+                B, N, grid)
         return ops.to_logical(bev)
 
     def forward(self, input, stereo_metas=None, depth_gt=None):

@@ -343,6 +343,29 @@ def test_lift_matches_oracle_bit_exact(batch):
     assert torch.equal(got2, got * 2)
 
 
+def test_lift_prepare_pool_equals_fused():
+    """accelerate=True split (pw_lift_prepare once + pw_lift_pool per call,
+    view_transformer.py:155-174,263-295) gives the bits of pw_lift_fused, also
+    on a second depth/feature pair pooled with the same lists."""
+    geo, s2k, intr, pr, pt, bda = _lift_setup(1, seed=5)
+    B, N = s2k.shape[:2]
+    D, H, W = geo.frustum.shape[:3]
+    xs, ys, ds = geo.frustum[0, 0, :, 0], geo.frustum[0, :, 0, 1], geo.frustum[:, 0, 0, 2]
+    grid = tuple(int(v) for v in geo.grid_size)
+    cam = ops.lift_camera_params(s2k.to(DEV), intr.to(DEV), pr.to(DEV), pt.to(DEV))
+    args = (cam, bda.reshape(B, 9).to(DEV), xs.to(DEV), ys.to(DEV), ds.to(DEV),
+            geo.lower.tolist(), geo.interval.tolist(), B, N, grid)
+    ws = ops.lift_prepare(*args)
+    g = torch.Generator().manual_seed(2)
+    for _ in range(2):
+        depth = torch.rand(B * N, D, H, W, generator=g).softmax(1).to(DEV)
+        feat = torch.randn(B * N, H, W, 40, generator=g).to(DEV)[..., 4:36]
+        want = ops.lift_fused(depth, feat, *args)
+        got = ops.lift_pool(depth, feat, ws, B, N, grid)
+        assert torch.equal(got, want)
+        assert (want != 0).any()
+
+
 def test_lift_all_points_outside_grid():
     geo, s2k, intr, pr, pt, bda = _lift_setup(1)
     far = dict(geo.grid_config, x=[500, 516, 0.4])

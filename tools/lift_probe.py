@@ -37,3 +37,32 @@ print('phase stamps (us since kernel start):', [round((x - st[0]) / 1e3, 2) for 
 print('queued voxels:', int(ws[:12].view(torch.int32)[2]), 'list entries:', int(ws[:12].view(torch.int32)[1]))
 alg = 4 * (6 * 88 * 16 * 44 + 6 * 16 * 44 * 32 + 640000 * 32)
 print('algorithmic MB', alg / 1e6, 'GB/s at median', alg / sorted(ts)[len(ts) // 2] / 1e3)
+
+# accelerate=True split: lists built once, then pool only
+ws2 = ops.lift_prepare(cam, bda, xs, ys, ds, vt.grid_lower_bound.tolist(),
+                       vt.grid_interval.tolist(), 1, 6, grid)
+out2 = ops.lift_pool(depth, feat, ws2, 1, 6, grid)
+torch.cuda.synchronize()
+print('pool == fused:', bool(torch.equal(out2, out)))
+ts2 = []
+for i in range(10):
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); ops.lift_pool(depth, feat, ws2, 1, 6, grid, out=out2); e1.record()
+    torch.cuda.synchronize()
+    ts2.append(e0.elapsed_time(e1) * 1e3)
+st = ws2[32:32 + 64].view(torch.int64).cpu().tolist()
+print('pool-only us per call (L2 flushed):', [round(t, 1) for t in ts2])
+print('pool-only phase stamps:', [round((x - st[0]) / 1e3, 2) for x in st[4:8]])
+print('pool-only GB/s at median', alg / sorted(ts2)[len(ts2) // 2] / 1e3)
+# back-to-back (no host gap): 20 calls inside one event pair
+for fn, name in ((lambda: ops.lift_fused(*args, out=out), 'fused'),
+                 (lambda: ops.lift_pool(depth, feat, ws2, 1, 6, grid, out=out2), 'pool')):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(20):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / 20
+    print(f'{name}: {us:.1f} us/call back-to-back, {alg / us / 1e3:.0f} GB/s algorithmic')
