@@ -296,9 +296,11 @@ lift_fused_kernel(const LiftFused a) {
     if (lane < T) {
       // p = (bn*D + d)*HW + hw  ->  feature row bn*HW + hw
       s_row[warp][pos] = (pnt / HW / a.g.D) * HW + pnt % HW;
-      s_d[warp][pos] = __ldg(a.depth + pnt);
-      s_v[warp][pos] = vox;
+      s_v[warp][pos] = vox | (lane << 8);              // voxel | lane holding this entry
     }
+    // the depth value stays in a register (fetched by shuffle below): its load
+    // runs concurrently with the feature-row loads instead of in front of them
+    const float dv_mine = lane < T ? __ldg(a.depth + pnt) : 0.f;
     __syncwarp();
 #pragma unroll
     for (int qc = 0; qc < CPL; ++qc) {
@@ -315,13 +317,15 @@ lift_fused_kernel(const LiftFused a) {
 #pragma unroll
       for (int t = 0; t < 32; ++t) {
         if (t < T) {
-          const int vx = s_v[warp][t];
+          const int ve = s_v[warp][t];
+          const int vx = ve & 0xff;
+          const float dv = __shfl_sync(0xffffffffu, dv_mine, ve >> 8);
           if (vx != cur) {
             if (cur >= 0 && chok) a.out[(v0 + cur) * a.C + ch] = acc;
             cur = vx;
             acc = 0.f;
           }
-          acc = fmaf(f[t], s_d[warp][t], acc);
+          acc = fmaf(f[t], dv, acc);
         }
       }
       if (cur >= 0 && chok) a.out[(v0 + cur) * a.C + ch] = acc;
