@@ -27,6 +27,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "../../include/preworld_b200.h"
@@ -531,9 +535,41 @@ struct HaloPlan {
   dim3 grid;
 };
 
+// Tuning knobs for experiments (tools/umma_probe.py), read once per process.
+struct HaloKnobs {
+  int nt = 0, nacc = 0, nb = 0, mt = 0, dbg = 0;
+  bool ts = false;
+  HaloKnobs() {
+    auto geti = [](const char* k) { const char* e = getenv(k); return e ? atoi(e) : 0; };
+    nt = geti("PW_HALO_NT"); nacc = geti("PW_HALO_NACC"); nb = geti("PW_HALO_NB");
+    mt = geti("PW_HALO_MT"); dbg = geti("PW_HALO_DBG");
+    ts = getenv("PW_HALO_TS") != nullptr;
+  }
+};
+const HaloKnobs& knobs() {
+  static const HaloKnobs k;
+  return k;
+}
+
 // Picks box / M-tile count / ring depths with a small cycle model:
 // waves * (per-CTA mainloop + halo load).
-HaloPlan make_plan(const pw_conv_desc& in) {
+HaloPlan make_plan_uncached(const pw_conv_desc& in);
+
+// The plan depends only on the descriptor: cache it (a forward re-issues the
+// same ~100 layer shapes every step; the search below costs ~50 us of host time).
+const HaloPlan& make_plan(const pw_conv_desc& in) {
+  static std::mutex mu;
+  static std::unordered_map<std::string, HaloPlan> cache;
+  pw_conv_desc key = in;
+  key.act = 0; key.act_channels = 0; key.out_ld = 0; key.res_ld = 0; key.w_ld = 0;
+  std::string k(reinterpret_cast<const char*>(&key), sizeof(key));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(k);
+  if (it == cache.end()) it = cache.emplace(k, make_plan_uncached(key)).first;
+  return it->second;
+}
+
+HaloPlan make_plan_uncached(const pw_conv_desc& in) {
   HaloPlan plan;
   pw_conv_desc c = in;
   if (c.cin % BLOCK_K != 0 || c.in_ld % 4 != 0 || c.cout < 1) return plan;
@@ -561,7 +597,7 @@ HaloPlan make_plan(const pw_conv_desc& in) {
   for (int ntry = 0; ntry < 3; ++ntry) {
     const int n_tile = ntry == 0 ? n_full : (ntry == 1 ? 64 : 32);
     if (ntry > 0 && n_tile >= n_full) continue;
-    if (const char* e = getenv("PW_HALO_NT")) { if (atoi(e) != n_tile && atoi(e) < n_full) continue; }
+    if (knobs().nt && knobs().nt != n_tile && knobs().nt < n_full) continue;
     const int slabs = pw_ceil_div(c.cout, n_tile);
     const int b_stage = 2 * n_tile * ROW_BYTES;
     for (int bi = 0; bi < nboxes; ++bi) {
@@ -586,13 +622,13 @@ HaloPlan make_plan(const pw_conv_desc& in) {
           const int halo_stride = round_up(hrows * ROW_BYTES, 1024);
           // TMEM: accumulators (mt * nacc * 2n) + A ring (nb * mt * 64 columns)
           int nacc = 1;
-          if (const char* e = getenv("PW_HALO_NACC")) nacc = atoi(e) == 2 ? 2 : 1;
+          if (knobs().nacc == 2) nacc = 2;
           if (mt * nacc * 2 * n_tile + 2 * mt * A_SLOT_COLS > 512) nacc = 1;
           const int acc_cols = mt * nacc * 2 * n_tile;
           int nb = min(T * chunks, min(4, (512 - acc_cols) / (mt * A_SLOT_COLS)));
-          if (const char* e = getenv("PW_HALO_NB")) nb = min(nb, max(1, atoi(e)));
+          if (knobs().nb) nb = min(nb, max(1, knobs().nb));
           if (nb < 1 || (nb < 2 && T * chunks > 1)) continue;
-          if (const char* e = getenv("PW_HALO_MT")) { if (atoi(e) != mt) continue; }
+          if (knobs().mt && knobs().mt != mt) continue;
           // halo ring
           int nh = min(chunks, 2);
           auto smem_need = [&](int nh_, int nb_) {
@@ -686,12 +722,13 @@ PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* 
   PW_REQUIRE(d->act_channels >= 0 && (d->act_channels & 3) == 0);
   EncodeTiledFn enc = encode_tiled_fn();
   PW_REQUIRE(enc != nullptr);
-  HaloPlan plan = make_plan(*d);
+  HaloPlan plan = make_plan(*d);                 // copy: per-launch fields are filled below
   PW_REQUIRE(plan.ok);
   const pw_conv_desc& c = plan.c;
   HaloParams& p = plan.p;
+  p.out_ld = d->out_ld; p.res_ld = d->res_ld; p.act = d->act; p.act_channels = d->act_channels;
   p.scale = scale; p.bias = bias; p.res = residual; p.y = y;
-  if (const char* e = getenv("PW_HALO_DBG")) p.dbg = atoi(e);
+  p.dbg = knobs().dbg;
   cudaStream_t st = (cudaStream_t)stream;
 
   CUtensorMap ma, mbh, mbl;
@@ -728,7 +765,7 @@ PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* 
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  const bool want_ts = getenv("PW_HALO_TS") != nullptr;
+  const bool want_ts = knobs().ts;
   const size_t n_cta = (size_t)plan.grid.x * plan.grid.y;
   if (want_ts) {
     cudaMalloc(&p.ts, n_cta * 16 * sizeof(long long));

@@ -133,15 +133,16 @@ class BEVStereo4DOCC(BaseModule):
         sensor2egos = sensor2egos.view(B, self.num_frame, N, 4, 4)
         ego2globals = ego2globals.view(B, self.num_frame, N, 4, 4)
         keyego2global = ego2globals[:, 0, 0, ...].unsqueeze(1).unsqueeze(1)
-        global2keyego = torch.inverse(keyego2global.double())
+        # inv_ex == torch.inverse without the device->host sync of its error check
+        global2keyego = torch.linalg.inv_ex(keyego2global.double()).inverse
         sensor2keyegos = (global2keyego @ ego2globals.double()
                           @ sensor2egos.double()).float()
         curr2adjsensor = None
         if stereo:
             tf = self.temporal_frame
-            curr2adjsensor = torch.inverse(
+            curr2adjsensor = torch.linalg.inv_ex(
                 ego2globals[:, 1:tf + 1].double()
-                @ sensor2egos[:, 1:tf + 1].double()) \
+                @ sensor2egos[:, 1:tf + 1].double()).inverse \
                 @ ego2globals[:, :tf].double() @ sensor2egos[:, :tf].double()
             curr2adjsensor = [p.squeeze(1) for p in
                               torch.split(curr2adjsensor.float(), 1, 1)]
