@@ -99,6 +99,13 @@ int pw_conv_halo_fwd(const pw_conv_desc* desc, const float* x,
  * -> [n,h,w,c_pad] with zero padding channels. */
 int pw_nchw_to_nhwc_pad(const float* x, long long img_stride, float* y, int n,
                         int c, int h, int w, int c_pad, void* stream);
+/* Same input, space-to-depth by 2: y[n, Y, X, (dy*2+dx)*4 + c] =
+ * x[n, c, 2Y+dy, 2X+dx] (c <= 4; h, w even; channels 16..c_pad-1 zero).  The
+ * mmdet ResNet stem (7x7, stride 2, pad 3) becomes a stride-1 4x4 conv over
+ * this tensor (taps a,b in -2..1; weight[o,(dy,dx,c),a,b] = W[o,c,2a+dy+3,
+ * 2b+dx+3]), which has Cin % 32 == 0 and runs on the tensor-core kernel. */
+int pw_nchw_to_s2d_nhwc(const float* x, long long img_stride, float* y, int n,
+                        int c, int h, int w, int c_pad, void* stream);
 /* channels-last -> NCHW copy: y[n,c,p] = x[n,p,c0+c]  (API edges only). */
 int pw_nhwc_to_nchw(const float* x, int x_ld, float* y, int n, int c,
                     long long pixels, void* stream);

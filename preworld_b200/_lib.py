@@ -51,6 +51,8 @@ SIGNATURES = {
                          c_p, c_p, c_p],
     'pw_nchw_to_nhwc_pad': [c_p, c_ll, c_p, c_int, c_int, c_int, c_int, c_int,
                             c_p],
+    'pw_nchw_to_s2d_nhwc': [c_p, c_ll, c_p, c_int, c_int, c_int, c_int, c_int,
+                            c_p],
     'pw_nhwc_to_nchw': [c_p, c_int, c_p, c_int, c_int, c_ll, c_p],
     'pw_maxpool3x3s2': [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int,
                         c_p],

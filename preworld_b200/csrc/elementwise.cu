@@ -29,6 +29,33 @@ __global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, float* __re
   }
 }
 
+// ---- NCHW -> space-to-depth(2) NHWC ----------------------------------------------
+// y[n, Y, X, (dy*2+dx)*4 + c] = x[n, c, 2Y+dy, 2X+dx]  (c < 3.. <=4), remaining
+// channels up to c_pad zero.  Turns the stride-2 7x7 ResNet stem into a
+// stride-1 4x4 conv with a 32-multiple Cin, i.e. a tensor-core conv.
+__global__ void nchw_to_s2d_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int n,
+                                        int c, int h, int w, int c_pad, long long img_stride) {
+  const int oh = h >> 1, ow = w >> 1;
+  const int q4 = c_pad >> 2;                            // float4 chunks per output pixel
+  long long total = (long long)n * oh * ow * q4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % q4);
+    long long t = i / q4;
+    const int X = (int)(t % ow); t /= ow;
+    const int Y = (int)(t % oh);
+    const long long img = t / oh;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (q < 4) {                                        // chunk q = (dy, dx), lanes = channel
+      const int dy = q >> 1, dx = q & 1;
+      const float* src = x + img * img_stride + (long long)(2 * Y + dy) * w + 2 * X + dx;
+      for (int ch = 0; ch < c && ch < 4; ++ch) v[ch] = __ldg(src + (long long)ch * h * w);
+    }
+    *reinterpret_cast<float4*>(y + (((img * oh + Y) * ow + X) * (long long)c_pad) + q * 4) =
+        make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 // ---- NHWC slice -> NCHW ----------------------------------------------------
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int x_ld,
                                     float* __restrict__ y, int n, int c, long long hw) {
@@ -351,6 +378,16 @@ PW_API int pw_nchw_to_nhwc_pad(const float* x, long long img_stride, float* y, i
   long long hw = (long long)h * w;
   PW_REQUIRE(img_stride >= c * hw);
   nchw_to_nhwc_pad_kernel<<<grid_for(n * hw), TPB, 0, ST>>>(x, y, n, c, hw, c_pad, img_stride);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+PW_API int pw_nchw_to_s2d_nhwc(const float* x, long long img_stride, float* y, int n, int c,
+                               int h, int w, int c_pad, void* stream) {
+  PW_REQUIRE(x && y && n > 0 && c > 0 && c <= 4 && c_pad >= 16 && (c_pad & 3) == 0);
+  PW_REQUIRE((h & 1) == 0 && (w & 1) == 0 && img_stride >= (long long)c * h * w);
+  nchw_to_s2d_nhwc_kernel<<<grid_for((long long)n * (h / 2) * (w / 2) * (c_pad / 4)), TPB, 0, ST>>>(
+      x, y, n, c, h, w, c_pad, img_stride);
   PW_LAUNCH_CHECK(); pw_count_launch(1);
   return 0;
 }

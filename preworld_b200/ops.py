@@ -174,7 +174,8 @@ USE_UMMA = True
 USE_HALO = True
 
 
-def conv(x, pc, act=None, residual=None, out=None, act_channels=0):
+def conv(x, pc, act=None, residual=None, out=None, act_channels=0,
+         out_size=None):
     """x: cl array [N,H,W,C] or [B,Z,Y,X,C] (C >= pc.cin, extra channels
     ignored only if equal to the packed cin).  Returns / fills a cl array with
     pc.cout channels; ``out`` may be a channel slice of a wider cl array."""
@@ -185,6 +186,12 @@ def conv(x, pc, act=None, residual=None, out=None, act_channels=0):
     assert x.shape[-1] == pc.cin, (x.shape, pc.cin)
     o = tuple((sp[i] + 2 * pc.pad[i] - pc.dil[i] * (pc.k[i] - 1) - 1)
               // pc.stride[i] + 1 for i in range(3))
+    if out_size is not None:
+        # fewer outputs than the symmetric-padding formula gives == less padding
+        # at the END of each axis (the kernels take the output extent as given)
+        os_ = (1,) * (3 - len(out_size)) + tuple(out_size)
+        assert all(0 < a <= b for a, b in zip(os_, o)), (os_, o)
+        o = os_
     if out is None:
         out = torch.empty((n, *o[3 - len(spatial):], pc.cout), device=x.device,
                           dtype=torch.float32)
@@ -251,6 +258,25 @@ def nchw_to_nhwc(x, c_pad=None, out=None):
                                          h, w, c_pad, _stream()),
           'pw_nchw_to_nhwc_pad')
     return y
+
+
+def nchw_to_s2d(x, c_pad=32, out=None):
+    """x [n,c<=4,h,w] (dense CHW planes, images may be strided) ->
+    space-to-depth(2) channels-last [n,h/2,w/2,c_pad]: channel (dy*2+dx)*4+c."""
+    _require_cuda(x)
+    n, c, h, w = x.shape
+    if x.stride()[1:] != (h * w, w, 1):
+        raise ValueError(f'images must be dense CHW planes, got {x.stride()}')
+    if out is None:
+        out = torch.empty((n, h // 2, w // 2, c_pad), device=x.device,
+                          dtype=torch.float32)
+    else:
+        assert out.shape == (n, h // 2, w // 2, c_pad) and out.is_contiguous()
+    img_stride = x.stride(0) if n > 1 else c * h * w
+    check(_lib.lib().pw_nchw_to_s2d_nhwc(_ptr(x), img_stride, _ptr(out), n, c,
+                                         h, w, c_pad, _stream()),
+          'pw_nchw_to_s2d_nhwc')
+    return out
 
 
 def nhwc_to_nchw(x_cl):

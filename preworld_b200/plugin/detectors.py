@@ -199,12 +199,11 @@ class BEVStereo4DOCC(BaseModule):
         bb = self.img_backbone
         if not (hasattr(bb, 'run_stem_cl') and 0 in bb.out_indices):
             return None
-        cin = bb.packs()['stem'].cin
-        x_all = torch.empty((nf * bn, imH, imW, cin), device=imgs[0].device,
-                            dtype=torch.float32)
+        x_all = torch.empty((nf * bn, *bb.stem_input_shape(imH, imW)),
+                            device=imgs[0].device, dtype=torch.float32)
         for f in range(nf):
-            ops.nchw_to_nhwc(imgs[f].reshape(bn, C, imH, imW), cin,
-                             out=x_all[f * bn:(f + 1) * bn])
+            bb.convert_images(imgs[f].reshape(bn, C, imH, imW),
+                              out=x_all[f * bn:(f + 1) * bn])
         l1 = bb.run_layer(0, bb.run_stem_cl(x_all))          # [nf*bn,h4,w4,256]
         n_full = nf - self.extra_ref_frames                   # frames 0..n_full-1
         x = bb.run_from_layer(1, l1[:n_full * bn])

@@ -128,19 +128,68 @@ class ResNet(BaseModule):
 
     def _build_packs(self):
         return dict(stem=pack_conv(self.conv1, self.bn1),
+                    stem_s2d=self._pack_stem_s2d(),
                     layers=[[blk.pack() for blk in getattr(self, n)]
                             for n in self.res_layers])
+
+    def _pack_stem_s2d(self):
+        """The 7x7 / stride 2 / pad 3 stem as a 4x4 stride-1 conv over the
+        space-to-depth(2) image (ops.nchw_to_s2d): out[Y,X] = sum_{ky,kx}
+        W[ky,kx] x[2Y+ky-3, 2X+kx-3]; with ky-3 = 2a+dy (a in -2..1, dy in 0,1)
+        this is sum_{a,b} W'[a,b] x'[Y+a, X+b], W'[o,(dy,dx,c),a,b] =
+        W[o,c,2a+dy+3,2b+dx+3] (zero where that index leaves the 7x7 window).
+        Cin is padded to 32, so the conv runs on the tensor-core kernel."""
+        w = self.conv1.weight.detach().float()
+        co, ci, kh, kw = w.shape
+        if (kh, kw) != (7, 7) or ci > 4 or self.conv1.stride != (2, 2) or \
+                self.conv1.padding != (3, 3):
+            return None
+        w2 = torch.zeros((co, 32, 4, 4), device=w.device)
+        for a in range(-2, 2):
+            for dy in range(2):
+                ky = 2 * a + dy + 3
+                if not 0 <= ky < 7:
+                    continue
+                for b in range(-2, 2):
+                    for dx in range(2):
+                        kx = 2 * b + dx + 3
+                        if 0 <= kx < 7:
+                            c0 = (dy * 2 + dx) * 4
+                            w2[:, c0:c0 + ci, a + 2, b + 2] = w[:, :, ky, kx]
+        from .base import bn_tuple
+        return ops.PackedConv(w2, None, bn_tuple(self.bn1), stride=1, padding=2)
 
     # -- stage-level entry points (bevdet.py:577-588 runs stem + layer1 only
     #    for the stereo reference frame) ------------------------------------
     def run_stem(self, img_nchw):
         """NCHW image batch -> cl array after conv1/bn1/relu/maxpool."""
+        return self.run_stem_cl(self.convert_images(img_nchw))
+
+    def stem_input_shape(self, h, w):
+        """(H, W, C) of the channels-last stem input for h x w images."""
         p = self.packs()
-        return self.run_stem_cl(ops.nchw_to_nhwc(img_nchw, p['stem'].cin))
+        if p['stem_s2d'] is not None and h % 2 == 0 and w % 2 == 0:
+            return (h // 2, w // 2, 32)
+        return (h, w, p['stem'].cin)
+
+    def convert_images(self, img_nchw, out=None):
+        """NCHW images -> the stem's channels-last input: space-to-depth(2)
+        for the tensor-core stem, plain padded NHWC otherwise."""
+        n, c, h, w = img_nchw.shape
+        if self.stem_input_shape(h, w)[2] == 32 and \
+                self.packs()['stem_s2d'] is not None and h % 2 == 0 and w % 2 == 0:
+            return ops.nchw_to_s2d(img_nchw, 32, out=out)
+        return ops.nchw_to_nhwc(img_nchw, self.packs()['stem'].cin, out=out)
 
     def run_stem_cl(self, x_cl):
-        """channels-last (zero-padded to the packed stem cin) image batch."""
-        x = ops.conv(x_cl, self.packs()['stem'], 'relu')
+        """stem input from ``convert_images`` -> conv1/bn1/relu/maxpool."""
+        p = self.packs()
+        if p['stem_s2d'] is not None and x_cl.shape[-1] == 32 and \
+                p['stem'].cin != 32:
+            x = ops.conv(x_cl, p['stem_s2d'], 'relu',
+                         out_size=tuple(x_cl.shape[1:3]))
+        else:
+            x = ops.conv(x_cl, p['stem'], 'relu')
         return ops.maxpool3x3s2(x)
 
     def run_from_layer(self, i0, x):

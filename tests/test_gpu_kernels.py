@@ -499,3 +499,30 @@ def test_device_miou_matches_oracle_bit_exact():
         assert np.array_equal(dev.occ_hist, ref.occ_hist)
         assert dev.count_miou()[3] == ref.count_miou()[1]
         assert dev.count_iou()[3] == ref.count_iou()[1]
+
+
+def test_resnet_stem_space_to_depth_matches_conv7x7():
+    """The tensor-core stem (space-to-depth(2) image, 4x4 stride-1 conv with
+    re-indexed weights) reproduces conv1(7x7, s2, p3) + bn1 + relu + maxpool of
+    mmdet ResNet (call site detectors/bevdet.py:577-588)."""
+    from preworld_b200.plugin.image import ResNet
+    torch.manual_seed(0)
+    bb = ResNet(depth=50, out_indices=(0, 2, 3)).eval()
+    S.lively_init_(bb, 3)
+    img = torch.randn(3, 3, 64, 96)
+    with torch.no_grad():
+        want = F.max_pool2d(F.relu(bb.bn1(bb.conv1(img))), 3, 2, 1)
+    bb = bb.to(DEV)
+    assert bb.packs()['stem_s2d'] is not None
+    assert bb.stem_input_shape(64, 96) == (32, 48, 32)
+    with torch.no_grad():
+        got = ops.to_logical(bb.run_stem(img.to(DEV))).cpu()
+    assert got.shape == want.shape
+    err = (got - want).abs().max().item() / want.abs().max().item()
+    assert err < 2e-5, err
+    # odd image sizes fall back to the plain NHWC stem
+    img2 = torch.randn(1, 3, 33, 47)
+    with torch.no_grad():
+        want2 = F.max_pool2d(F.relu(bb.cpu().bn1(bb.conv1(img2))), 3, 2, 1)
+        got2 = ops.to_logical(bb.to(DEV).run_stem(img2.to(DEV))).cpu()
+    assert (got2 - want2).abs().max().item() / want2.abs().max().item() < 2e-5
