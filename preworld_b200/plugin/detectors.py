@@ -424,6 +424,10 @@ class BEVStereo4DOCC(BaseModule):
     def voxel_features_cl(self, img, **kwargs):
         """Trunk + final_conv (ReLU is ConvModule's default act) -> cl array
         [B,Z,Y,X,C] in library voxel order."""
+        if not img[0].is_cuda:                   # the loader's host batch
+            dev = next(self.parameters()).device
+            img = tuple(t.to(dev, non_blocking=True)
+                        if torch.is_tensor(t) else t for t in img)
         img_inputs = self.prepare_inputs(img, stereo=True)
         img_feats, _ = self.extract_img_feat(img_inputs, None, **kwargs)
         P = self.packs()
@@ -573,9 +577,19 @@ class PreWorld(BEVStereo4DOCC):
         return self._occ_from_density(vf_cl)
 
     def _graphed_occupancy(self, img):
+        """Host tensors (the loader's CPU batch, ideally pinned) take the short
+        route: the image batch is copied straight into the graph's static input
+        buffer, the fp64 pose chain runs on the CPU (a few hundred floats,
+        hidden under that copy) and reaches the device as ONE packed buffer the
+        static pose tables are views of.  Device tensors are copied into the
+        static buffers on the device."""
         dev = next(self.parameters()).device
-        raw = img[0] if img[0].device == dev else img[0].to(dev, non_blocking=True)
-        poses = self.prepare_inputs((raw,) + tuple(img[1:7]), stereo=True)[1:]
+        on_host = not img[0].is_cuda
+        shape_src = img[0]
+        poses = self.prepare_inputs(
+            (shape_src,) + tuple(t if t.is_cuda == shape_src.is_cuda
+                                 else t.to(shape_src.device) for t in img[1:7]),
+            stereo=True)[1:]
         flat, spec = [], []
         for item in poses:                       # lists of tensors / None, or a tensor
             if isinstance(item, (list, tuple)):
@@ -584,9 +598,9 @@ class PreWorld(BEVStereo4DOCC):
             else:
                 spec.append(-1)
                 flat.append(item)
-        flat = [t.to(dev, non_blocking=True) if t is not None else None for t in flat]
-        key = (tuple(raw.shape),) + tuple(
-            (tuple(t.shape), t.dtype) if t is not None else None for t in flat)
+        flat = [t.float() if t is not None else None for t in flat]
+        key = (tuple(img[0].shape),) + tuple(
+            tuple(t.shape) if t is not None else None for t in flat)
         entry = self._graph_cache.get(key)
 
         def unflatten(ts):
@@ -606,8 +620,18 @@ class PreWorld(BEVStereo4DOCC):
             return self._occupancy_dev(vf)
 
         if entry is None:
-            raw_s = raw.clone()
-            flat_s = [t.clone() if t is not None else None for t in flat]
+            raw_s = torch.empty(img[0].shape, device=dev, dtype=torch.float32)
+            raw_s.copy_(img[0])
+            # one packed device buffer; the static pose tables are views of it
+            sizes = [t.numel() if t is not None else 0 for t in flat]
+            packed_s = torch.empty(sum(sizes), device=dev, dtype=torch.float32)
+            packed_h = torch.empty(sum(sizes), dtype=torch.float32).pin_memory()
+            flat_s, o = [], 0
+            for t, n in zip(flat, sizes):
+                flat_s.append(packed_s[o:o + n].view(t.shape)
+                              if t is not None else None)
+                o += n
+            self._pack_poses(flat, packed_h, packed_s)
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side), torch.no_grad():
@@ -617,16 +641,25 @@ class PreWorld(BEVStereo4DOCC):
             g = torch.cuda.CUDAGraph()
             with torch.no_grad(), torch.cuda.graph(g):
                 out_s = body(raw_s, flat_s)
-            entry = self._graph_cache[key] = (g, raw_s, flat_s, out_s)
-        g, raw_s, flat_s, out_s = entry
-        raw_s.copy_(raw, non_blocking=True)
-        for s_, t in zip(flat_s, flat):
-            if t is not None:
-                s_.copy_(t, non_blocking=True)
+            entry = self._graph_cache[key] = (g, raw_s, packed_s, packed_h, out_s)
+        g, raw_s, packed_s, packed_h, out_s = entry
+        raw_s.copy_(img[0], non_blocking=True)       # H2D (pinned) or D2D
+        self._pack_poses(flat, packed_h, packed_s)
         g.replay()
         if len(out_s) == 1:
             return self._to_numpy_pair(out_s[0], None, self.num_classes - 1)
         return self._to_numpy_pair(out_s[0], out_s[1])
+
+    @staticmethod
+    def _pack_poses(flat, packed_h, packed_s):
+        ts = [t.reshape(-1) for t in flat if t is not None]
+        if ts and not ts[0].is_cuda:
+            # the previous replay has been synchronised by its D2H read, so the
+            # pinned staging buffer is free again
+            torch.cat(ts, out=packed_h)
+            packed_s.copy_(packed_h, non_blocking=True)
+        else:
+            torch.cat(ts, out=packed_s)
 
     # -- pre-training forward (preworld.py:229-256 + nerf_head.py:361-407) ---
     def render_forward(self, img, rays, **kwargs):

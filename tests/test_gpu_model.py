@@ -264,3 +264,11 @@ def test_cuda_graph_replay_equals_eager(name):
                 assert np.array_equal(out['semantic_occ'][0], want[0])
                 assert np.array_equal(out['geo_occ'][0], want[1])
     assert len(model._graph_cache) == 1
+    # host (pinned) tensors: image H2D straight into the static buffer, pose
+    # chain on the CPU -- same occupancy
+    with torch.no_grad():
+        for s, want in zip(samples, eager):
+            out = model(return_loss=False,
+                        img_inputs=[tuple(t.pin_memory() for t in s)],
+                        img_metas=[None])
+            assert np.array_equal(out['semantic_occ'][0], want[0])
