@@ -45,3 +45,26 @@ class MetricRef:
     def count_iou(self):
         i = per_class_iu(self.occ_hist)
         return i, round(i[-1] * 100, 2)
+
+
+class MetricTemporalRef:
+    """occ_metrics.py:413-596: per-horizon accumulation (idx 0, 2, 4, 6 ->
+    0s..3s, prediction index idx // 2)."""
+
+    def __init__(self, num_classes=18, use_lidar_mask=False,
+                 use_image_mask=False):
+        self.num_classes = num_classes
+        self.m = {idx: MetricRef(num_classes, use_lidar_mask, use_image_mask)
+                  for idx in (0, 2, 4, 6)}
+
+    def add_batch(self, preds, gts, mask_lidar, mask_camera):
+        for idx in gts.keys():
+            if idx in self.m:
+                self.m[idx].add_batch(preds[idx // 2], gts[idx],
+                                      mask_lidar[idx], mask_camera[idx])
+
+    def count_miou(self):
+        return [self.m[idx].count_miou()[1] for idx in (2, 4, 6)]
+
+    def count_iou(self):
+        return [self.m[idx].count_iou()[1] for idx in (2, 4, 6)]

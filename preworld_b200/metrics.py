@@ -88,3 +88,52 @@ class Metric_mIoU:
     def count_iou(self):                         # occ_metrics.py:177-185
         IoU = self.per_class_iu(self.occ_hist)
         return self.occ_names, IoU, self.cnt, round(IoU[-1] * 100, 2)
+
+
+class Metric_mIoU_Temporal:
+    """mmdet3d/datasets/occ_metrics.py:413-596 on the device: one
+    (18x18, 2x2) confusion-matrix pair per horizon 0s/1s/2s/3s; ``add_batch``
+    takes the forecast list ``semantics_pred[k]`` (k = idx // 2) and the ground
+    truth / mask dicts keyed idx = 0, 2, 4, 6 exactly as the reference."""
+
+    def __init__(self, save_dir='.', num_classes=18, use_lidar_mask=False,
+                 use_image_mask=False, device='cuda'):
+        self.class_names = CLASS_NAMES
+        self.occ_names = ['free', 'occupied']
+        self.num_classes = num_classes
+        self.cnt = 0
+        self._m = {idx: Metric_mIoU(save_dir, num_classes, use_lidar_mask,
+                                    use_image_mask, device)
+                   for idx in (0, 2, 4, 6)}
+
+    def add_batch(self, semantics_pred, semantics_gt_temp, mask_lidar_temp,
+                  mask_camera_temp):
+        self.cnt += 1
+        for idx in semantics_gt_temp.keys():
+            if idx not in self._m:
+                continue                         # the reference ignores other keys
+            self._m[idx].add_batch(
+                semantics_pred[idx // 2], semantics_gt_temp[idx],
+                mask_lidar_temp[idx] if mask_lidar_temp is not None else None,
+                mask_camera_temp[idx] if mask_camera_temp is not None else None)
+
+    def _hist(self, k):
+        return self._m[2 * k].hist
+
+    hist_0s = property(lambda self: self._hist(0))
+    hist_1s = property(lambda self: self._hist(1))
+    hist_2s = property(lambda self: self._hist(2))
+    hist_3s = property(lambda self: self._hist(3))
+    occ_hist_0s = property(lambda self: self._m[0].occ_hist)
+    occ_hist_1s = property(lambda self: self._m[2].occ_hist)
+    occ_hist_2s = property(lambda self: self._m[4].occ_hist)
+    occ_hist_3s = property(lambda self: self._m[6].occ_hist)
+
+    def count_miou(self):                        # occ_metrics.py:541-571
+        n = self.num_classes
+        per = [Metric_mIoU.per_class_iu(self._hist(k)) for k in (1, 2, 3)]
+        return per[0], [round(np.nanmean(m[:n - 1]) * 100, 2) for m in per]
+
+    def count_iou(self):                         # occ_metrics.py:573-596
+        return [round(Metric_mIoU.per_class_iu(self._m[idx].occ_hist)[-1] * 100, 2)
+                for idx in (2, 4, 6)]

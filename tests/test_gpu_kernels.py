@@ -526,3 +526,30 @@ def test_resnet_stem_space_to_depth_matches_conv7x7():
         want2 = F.max_pool2d(F.relu(bb.cpu().bn1(bb.conv1(img2))), 3, 2, 1)
         got2 = ops.to_logical(bb.to(DEV).run_stem(img2.to(DEV))).cpu()
     assert (got2 - want2).abs().max().item() / want2.abs().max().item() < 2e-5
+
+
+def test_device_temporal_miou_matches_oracle():
+    """Metric_mIoU_Temporal (occ_metrics.py:413-596): per-horizon matrices."""
+    from oracle.metrics_ref import MetricTemporalRef
+    from preworld_b200.metrics import Metric_mIoU_Temporal
+    rng = np.random.default_rng(2)
+    ref = MetricTemporalRef(use_image_mask=True)
+    dev = Metric_mIoU_Temporal(use_image_mask=True)
+    for _ in range(2):
+        preds = [rng.integers(0, 18, (40, 40, 16)).astype(np.uint8) for _ in range(4)]
+        gts, ml, mc = {}, {}, {}
+        for idx in (0, 2, 4, 6):
+            g = rng.integers(0, 18, (40, 40, 16)).astype(np.uint8)
+            g[rng.random(g.shape) < 0.05] = 255
+            gts[idx], ml[idx] = g, rng.random(g.shape) < 0.5
+            mc[idx] = rng.random(g.shape) < 0.6
+        ref.add_batch(preds, gts, ml, mc)
+        t = lambda a: torch.from_numpy(a).to(DEV)
+        dev.add_batch([t(p) for p in preds], {k: t(v) for k, v in gts.items()},
+                      {k: t(v) for k, v in ml.items()},
+                      {k: t(v) for k, v in mc.items()})
+    for k, idx in enumerate((0, 2, 4, 6)):
+        assert np.array_equal(getattr(dev, f'hist_{k}s'), ref.m[idx].hist)
+        assert np.array_equal(getattr(dev, f'occ_hist_{k}s'), ref.m[idx].occ_hist)
+    assert dev.count_miou()[1] == ref.count_miou()
+    assert dev.count_iou() == ref.count_iou()
