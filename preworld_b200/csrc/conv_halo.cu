@@ -41,6 +41,9 @@ using namespace pwtc;
 
 constexpr int BLOCK_K = 32;                  // floats = one 128-byte swizzle row
 constexpr int ROW_BYTES = 128;
+// Split-warp sets (4 warps = 4 TMEM lane quadrants each).  3 sets were measured:
+// +3 % on the 3x3x3 volume layers, -2 % on the whole step (84.1 vs 85.9 frames/s);
+// the protocol is safe for 2..4 sets (tools/halo_protocol_sim.py), 2 is shipped.
 constexpr int SPLIT_SETS = 2;
 constexpr int FIRST_SPLIT_WARP = 3;
 constexpr int NUM_WARPS = FIRST_SPLIT_WARP + 4 * SPLIT_SETS;
@@ -282,10 +285,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
       for (int j = 0; j < 8; ++j) raw[j] = lds128(b2 ^ (uint32_t)(j << 4));
     };
+    // Every split warp arrives once per chunk on halo_empty.  A chunk this warp
+    // never read (T*mt < SPLIT_SETS: the set skips it) may only be released once
+    // its load has been ISSUED -- i.e. after the previous occupant of the slot was
+    // released by everybody -- or the arrival would land in the previous phase
+    // and free the slot under a slower set: wait for its halo_full first.
+    auto release_chunk = [&](int ch) {
+      const int slot = ch % p.nh;
+      mbar_wait(halo_full + 8 * slot, (uint32_t)((ch / p.nh) & 1));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(halo_empty + 8 * slot);
+    };
     for (int q = 0; q < set / p.mt; ++q) step_tap();     // first tap of this set
     int released = 0;                                    // halo chunks this warp has released
     int pending = -1;                                    // A slot stored but not yet published
     long long sp_wait = 0, sp_busy = 0, sp_t0 = 0;       // PW_HALO_TS: cycles waiting / storing
+#pragma unroll 1
+    while (released < min(c, p.chunks)) {                // chunks before this set's first one
+      release_chunk(released);
+      ++released;
+    }
     if (c < p.chunks) {
       mbar_wait(halo_full + 8 * hs, hph);
       if (sw_id == 0 && lane == 0) PW_TS(3);
@@ -345,8 +364,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
         const int upto = c < p.chunks ? c : p.chunks;
 #pragma unroll 1
         while (released < upto) {                        // chunks this warp is done reading
-          __syncwarp();
-          if (lane == 0) mbar_arrive(halo_empty + 8 * (released % p.nh));
+          release_chunk(released);
           ++released;
         }
         if (c < p.chunks) mbar_wait(halo_full + 8 * hs, hph);
@@ -361,8 +379,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     }
 #pragma unroll 1
     while (released < p.chunks) {                        // a set with no work in the last chunks
-      __syncwarp();
-      if (lane == 0) mbar_arrive(halo_empty + 8 * (released % p.nh));
+      release_chunk(released);
       ++released;
     }
 
@@ -628,6 +645,9 @@ HaloPlan make_plan_uncached(const pw_conv_desc& in) {
           int nb = min(T * chunks, min(4, (512 - acc_cols) / (mt * A_SLOT_COLS)));
           if (knobs().nb) nb = min(nb, max(1, knobs().nb));
           if (nb < 1 || (nb < 2 && T * chunks > 1)) continue;
+          // A set advances by SPLIT_SETS / mt ring entries per row; with a shallower
+          // ring its parity wait on ring_empty would alias a phase it never observed.
+          if (T * chunks > nb && nb < (SPLIT_SETS + mt - 1) / mt) continue;
           if (knobs().mt && knobs().mt != mt) continue;
           // halo ring
           int nh = min(chunks, 2);
@@ -635,7 +655,7 @@ HaloPlan make_plan_uncached(const pw_conv_desc& in) {
             return (long long)max(nh_ * halo_stride, 4 * SPLIT_SETS * STAGE_BYTES_PER_WARP) +
                    (long long)nb_ * b_stage + SMEM_SLACK;
           };
-          while (nb > 2 && smem_need(nh, nb) > SMEM_LIMIT) --nb;
+          while (nb > max(2, (SPLIT_SETS + mt - 1) / mt) && smem_need(nh, nb) > SMEM_LIMIT) --nb;
           // a multi-chunk conv needs two halo slots (load of chunk c+1 under the
           // taps of chunk c); if that does not fit, conv_umma.cu takes the layer
           if (smem_need(nh, nb) > SMEM_LIMIT) continue;
