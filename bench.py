@@ -321,7 +321,7 @@ def main():
         host = pin_samples[i % len(pin_samples)]
         with torch.no_grad():
             out = model(return_loss=False, img_inputs=[host], img_metas=[None])
-        return out['semantic_occ'][0]
+        return out['semantic_occ'][0], out['geo_occ'][0]
 
     # ---- device-resident timing -------------------------------------------
     for i in range(args.warmup):
@@ -363,7 +363,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e2e = t.item()
     h2d = sum(t.numel() * t.element_size() for t in pin_samples[0])
-    d2h = int(occ_np.nbytes)
+    d2h = int(sum(a.nbytes for a in occ_np))     # semantic_occ + geo_occ grids
 
     if rank != 0:
         if world > 1:
@@ -462,7 +462,7 @@ def main():
                 'ms_per_step': ms_e2e / args.steps,
                 'api': 'model(return_loss=False, img_inputs=[...]) with '
                        'pinned host tensors, model.enable_cuda_graph() '
-                       '(forward replayed as one CUDA graph)'},
+                       '(forward replayed as CUDA graphs; images uploaded frame by frame under the stem of the previous frame)'},
         'gpu_launches': int(launches),
         'clocks': clk, 'roofline': roof, 'cpu_baseline': cpu,
         'kernels': kernels,

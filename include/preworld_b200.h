@@ -265,6 +265,17 @@ int pw_copy_channels(const float* x, int x_ld, float* y, int y_ld,
  * (first maximum wins, as torch.argmax). */
 int pw_argmax_zyx_to_xyz(const float* logits, int ld, int ncls, unsigned char* occ,
                          int gx, int gy, int gz, void* stream);
+/* preworld.py:201-221 (nuScenes branch): the same argmax plus the geometry grid
+ * geo = (class != free_idx) ? 0 : geo_value, both in [X,Y,Z] order. */
+int pw_argmax_geo_zyx_to_xyz(const float* logits, int ld, int ncls, int free_idx,
+                             int geo_value, unsigned char* occ, unsigned char* geo,
+                             int gx, int gy, int gz, void* stream);
+/* Host plumbing of the public call (bevdet_occ.py:88-97 splits the loader's
+ * camera-major image batch into frames): `rows` rows of `row_bytes` from a
+ * pitched source into a pitched destination, asynchronously on `stream`
+ * (host->device when src is pinned host memory, device->device otherwise). */
+int pw_copy_rows(void* dst, long long dst_pitch, const void* src, long long src_pitch,
+                 long long row_bytes, long long rows, void* stream);
 /* preworld.py:173-194 density path: occ = density>thr ? argmax(semantic) : 17;
  * density [voxels] , semantic [voxels, ld]. */
 int pw_density_occ_zyx_to_xyz(const float* density, int density_ld,

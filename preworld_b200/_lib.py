@@ -94,6 +94,9 @@ SIGNATURES = {
                                c_int, c_int, c_p],
     'pw_copy_channels': [c_p, c_int, c_p, c_int, c_ll, c_int, c_p],
     'pw_argmax_zyx_to_xyz': [c_p, c_int, c_int, c_p, c_int, c_int, c_int, c_p],
+    'pw_argmax_geo_zyx_to_xyz': [c_p, c_int, c_int, c_int, c_int, c_p, c_p,
+                                 c_int, c_int, c_int, c_p],
+    'pw_copy_rows': [c_p, c_ll, c_p, c_ll, c_ll, c_ll, c_p],
     'pw_density_occ_zyx_to_xyz': [c_p, c_int, c_p, c_int, c_int, c_f, c_int,
                                   c_p, c_p, c_int, c_int, c_int, c_p],
     'pw_zyx_to_xyz': [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],

@@ -41,13 +41,16 @@ using namespace pwtc;
 
 constexpr int BLOCK_K = 32;                  // floats = one 128-byte swizzle row
 constexpr int ROW_BYTES = 128;
-// Split-warp sets (4 warps = 4 TMEM lane quadrants each).  3 sets were measured:
-// +3 % on the 3x3x3 volume layers, -2 % on the whole step (84.1 vs 85.9 frames/s);
-// the protocol is safe for 2..4 sets (tools/halo_protocol_sim.py), 2 is shipped.
-constexpr int SPLIT_SETS = 2;
+// Split-warp sets (4 warps = 4 TMEM lane quadrants each) per CTA.  Two variants
+// are compiled: 2 sets with one CTA per SM (352 threads, up to 512 TMEM columns,
+// 227 KB of shared memory) and 1 set with two co-resident CTAs per SM (224
+// threads, <= 256 columns and <= 113 KB each), where one CTA's prologue, halo
+// load and epilogue run under the other's main loop.  (3 sets x 1 CTA: +3 % on
+// the 3x3x3 volume layers, -2 % on the whole step.)  The barrier protocol is
+// checked for 1..4 sets by tools/halo_protocol_sim.py.
+constexpr int MAX_SPLIT_SETS = 2;
 constexpr int FIRST_SPLIT_WARP = 3;
-constexpr int NUM_WARPS = FIRST_SPLIT_WARP + 4 * SPLIT_SETS;
-constexpr int NUM_THREADS = NUM_WARPS * 32;  // 352
+constexpr int halo_threads(int sets) { return (FIRST_SPLIT_WARP + 4 * sets) * 32; }
 constexpr int A_SLOT_COLS = 2 * BLOCK_K;     // hi | lo
 constexpr int STAGE_BYTES_PER_WARP = 32 * ROW_BYTES;
 constexpr int MAX_RING = 8;
@@ -92,7 +95,8 @@ struct HaloParams {
 #endif
 #define PW_TS(k) do { if (PW_TSON) p.ts[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (k)] = clock64(); } while (0)
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int SPLIT_SETS, int MIN_CTAS>
+__global__ void __launch_bounds__(halo_threads(SPLIT_SETS), MIN_CTAS)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
                  const __grid_constant__ CUtensorMap map_bh,
                  const __grid_constant__ CUtensorMap map_bl, const HaloParams p) {
@@ -542,6 +546,7 @@ inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int SMEM_LIMIT_2CTA = (228 * 1024 - 2 * 1024) / 2;   // two CTAs + 1 KB reserved each
 constexpr int SMEM_SLACK = 1024 /*align*/ + (6 * MAX_RING + 1) * 8 + 16;   // barriers: 2nh + nb(2+mt) + 1
 
 struct HaloPlan {
@@ -550,16 +555,18 @@ struct HaloPlan {
   HaloParams p;
   size_t smem = 0;
   dim3 grid;
+  int sets = 2;                // kernel variant: split sets per CTA (2: 1 CTA/SM, 1: 2 CTAs/SM)
+  double cost = -1;            // cycle-model estimate of the whole launch
 };
 
 // Tuning knobs for experiments (tools/umma_probe.py), read once per process.
 struct HaloKnobs {
-  int nt = 0, nacc = 0, nb = 0, mt = 0, dbg = 0;
+  int nt = 0, nacc = 0, nb = 0, mt = 0, dbg = 0, sets = 0;
   bool ts = false;
   HaloKnobs() {
     auto geti = [](const char* k) { const char* e = getenv(k); return e ? atoi(e) : 0; };
     nt = geti("PW_HALO_NT"); nacc = geti("PW_HALO_NACC"); nb = geti("PW_HALO_NB");
-    mt = geti("PW_HALO_MT"); dbg = geti("PW_HALO_DBG");
+    mt = geti("PW_HALO_MT"); dbg = geti("PW_HALO_DBG"); sets = geti("PW_HALO_SETS");
     ts = getenv("PW_HALO_TS") != nullptr;
   }
 };
@@ -586,8 +593,23 @@ const HaloPlan& make_plan(const pw_conv_desc& in) {
   return it->second;
 }
 
+// Best plan for one kernel variant: `sets` split sets per CTA, the CTA limited to
+// `tmem_limit` TMEM columns and `smem_limit` bytes, `cps` CTAs resident per SM.
+HaloPlan search_plan(const pw_conv_desc& in, int sets, int tmem_limit, int smem_limit, int cps);
+
 HaloPlan make_plan_uncached(const pw_conv_desc& in) {
+  HaloPlan one_cta = search_plan(in, 2, 512, SMEM_LIMIT, 1);
+  if (knobs().sets == 2) return one_cta;
+  HaloPlan two_ctas = search_plan(in, 1, 256, SMEM_LIMIT_2CTA, 2);
+  if (!two_ctas.ok) return one_cta;
+  if (!one_cta.ok || knobs().sets == 1) return two_ctas;
+  return two_ctas.cost < one_cta.cost ? two_ctas : one_cta;
+}
+
+HaloPlan search_plan(const pw_conv_desc& in, const int SPLIT_SETS, const int tmem_limit,
+                     const int smem_limit, const int cps) {
   HaloPlan plan;
+  plan.sets = SPLIT_SETS;
   pw_conv_desc c = in;
   if (c.cin % BLOCK_K != 0 || c.in_ld % 4 != 0 || c.cout < 1) return plan;
   if (c.n < 1 || c.od < 1 || c.oh < 1 || c.ow < 1) return plan;
@@ -640,9 +662,9 @@ HaloPlan make_plan_uncached(const pw_conv_desc& in) {
           // TMEM: accumulators (mt * nacc * 2n) + A ring (nb * mt * 64 columns)
           int nacc = 1;
           if (knobs().nacc == 2) nacc = 2;
-          if (mt * nacc * 2 * n_tile + 2 * mt * A_SLOT_COLS > 512) nacc = 1;
+          if (mt * nacc * 2 * n_tile + 2 * mt * A_SLOT_COLS > tmem_limit) nacc = 1;
           const int acc_cols = mt * nacc * 2 * n_tile;
-          int nb = min(T * chunks, min(4, (512 - acc_cols) / (mt * A_SLOT_COLS)));
+          int nb = min(T * chunks, min(4, (tmem_limit - acc_cols) / (mt * A_SLOT_COLS)));
           if (knobs().nb) nb = min(nb, max(1, knobs().nb));
           if (nb < 1 || (nb < 2 && T * chunks > 1)) continue;
           // A set advances by SPLIT_SETS / mt ring entries per row; with a shallower
@@ -655,12 +677,12 @@ HaloPlan make_plan_uncached(const pw_conv_desc& in) {
             return (long long)max(nh_ * halo_stride, 4 * SPLIT_SETS * STAGE_BYTES_PER_WARP) +
                    (long long)nb_ * b_stage + SMEM_SLACK;
           };
-          while (nb > max(2, (SPLIT_SETS + mt - 1) / mt) && smem_need(nh, nb) > SMEM_LIMIT) --nb;
+          while (nb > max(2, (SPLIT_SETS + mt - 1) / mt) && smem_need(nh, nb) > smem_limit) --nb;
           // a multi-chunk conv needs two halo slots (load of chunk c+1 under the
           // taps of chunk c); if that does not fit, conv_umma.cu takes the layer
-          if (smem_need(nh, nb) > SMEM_LIMIT) continue;
+          if (smem_need(nh, nb) > smem_limit) continue;
           while (nh < min(chunks, MAX_RING) && nh * halo_stride < 64 * 1024 &&
-                 smem_need(nh + 1, nb) <= SMEM_LIMIT)
+                 smem_need(nh + 1, nb) <= smem_limit)
             ++nh;
           const long long tiles = (long long)pw_ceil_div(c.ow, cb[0]) * pw_ceil_div(c.oh, cb[1]) *
                                   pw_ceil_div(c.od, cb[2]) * c.n * slabs;
@@ -671,17 +693,18 @@ HaloPlan make_plan_uncached(const pw_conv_desc& in) {
           const double per_ct = 430.0 + mt * 4.0 * kstep;
           double cta = chunks * (T * per_ct + (nh > 1 ? 0.25 : 1.0) * hrows * 2.0) + 3000.0 +
                        mt * n_tile * 40.0;
-          // co-resident CTAs (TMEM columns and shared memory permitting) overlap one
-          // CTA's prologue / epilogue with the other's main loop
-          int cols_need = acc_cols + nb * mt * A_SLOT_COLS, tcols = 32;
-          while (tcols < cols_need) tcols <<= 1;
-          const long long smem_cta = smem_need(nh, nb);
-          int cps = min(512 / tcols, (int)((228 * 1024 - 1024) / (smem_cta + 1024)));
-          // measured: a register-capped two-CTA-per-SM variant spills in the split
-          // loop and loses more than the overlap gains -> one CTA per SM
-          cps = 1;
+          // Two co-resident CTAs overlap one CTA's prologue / halo load / epilogue
+          // with the other's main loop, but each has half the split warps: the main
+          // loop of a CTA runs at the split rate (measured ~1250 cycles per 128-row
+          // A tile per set) when that is slower than the MMA issue rate.
+          if (cps == 2) {
+            const double split_ct = mt * 1250.0;
+            const double main_ct = per_ct > split_ct ? per_ct : split_ct;
+            const double fixed = cta - chunks * T * per_ct;
+            cta = chunks * T * main_ct + 0.35 * fixed;
+          }
           const double waves = (double)((tiles + 148 * cps - 1) / (148 * cps));
-          const double cost = waves * cta * (cps == 2 ? 1.3 : 1.0);
+          const double cost = waves * cta;
           if (best < 0 || cost < best) {
             best = cost;
             HaloParams& p = plan.p;
@@ -705,6 +728,7 @@ HaloPlan make_plan_uncached(const pw_conv_desc& in) {
             plan.smem = (size_t)p.halo_region + (size_t)nb * b_stage + SMEM_SLACK;
             plan.grid = dim3((unsigned)(tiles / slabs), (unsigned)slabs);
             plan.ok = true;
+            plan.cost = cost;
           }
         }
       }
@@ -780,8 +804,11 @@ PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* 
 
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<2, 1>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(conv_halo_kernel<1, 2>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT_2CTA);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
@@ -791,7 +818,10 @@ PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* 
     cudaMalloc(&p.ts, n_cta * 16 * sizeof(long long));
     cudaMemset(p.ts, 0, n_cta * 16 * sizeof(long long));
   }
-  conv_halo_kernel<<<plan.grid, NUM_THREADS, plan.smem, st>>>(ma, mbh, mbl, p);
+  if (plan.sets == 1)
+    conv_halo_kernel<1, 2><<<plan.grid, halo_threads(1), plan.smem, st>>>(ma, mbh, mbl, p);
+  else
+    conv_halo_kernel<2, 1><<<plan.grid, halo_threads(2), plan.smem, st>>>(ma, mbh, mbl, p);
   PW_LAUNCH_CHECK();
   if (want_ts) {
     cudaStreamSynchronize(st);
@@ -800,9 +830,9 @@ PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* 
     double sum[16] = {0};
     for (size_t i = 0; i < n_cta; ++i)
       for (int k = 0; k < 16; ++k) sum[k] += (double)(h[i * 16 + k] - h[i * 16]);
-    fprintf(stderr, "[halo ts] grid %u x %u mt %d n_tile %d nh %d nb %d nacc %d box %dx%dx%d halo %dx%dx%d smem %zu tmem %d cps %d:",
+    fprintf(stderr, "[halo ts] grid %u x %u mt %d n_tile %d nh %d nb %d nacc %d box %dx%dx%d halo %dx%dx%d smem %zu tmem %d sets %d cps %d:",
             plan.grid.x, plan.grid.y, p.mt, p.n_tile, p.nh, p.nb, p.nacc, p.cbx, p.cby, p.cbz,
-            p.hx, p.hy, p.hz, plan.smem, p.tmem_cols, p.cps);
+            p.hx, p.hy, p.hz, plan.smem, p.tmem_cols, plan.sets, p.cps);
     for (int k = 0; k < 16; ++k) fprintf(stderr, " t%d=%.0f", k, sum[k] / n_cta);
     fprintf(stderr, "\n");
     free(h);

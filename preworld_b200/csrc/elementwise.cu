@@ -299,7 +299,9 @@ __global__ void copy_channels_kernel(const float* __restrict__ x, int x_ld, floa
 
 // ---- occupancy argmax, [Z,Y,X] voxel order -> [X,Y,Z] uint8 grid -----------
 __global__ void argmax_zyx_to_xyz_kernel(const float* __restrict__ logits, int ld, int ncls,
-                                         unsigned char* __restrict__ occ, int gx, int gy, int gz) {
+                                         unsigned char* __restrict__ occ,
+                                         unsigned char* __restrict__ geo, int free_idx,
+                                         int geo_value, int gx, int gy, int gz) {
   long long total = (long long)gx * gy * gz;
   // iterate in OUTPUT order (x,y,z with z fastest) so byte stores coalesce
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -316,6 +318,7 @@ __global__ void argmax_zyx_to_xyz_kernel(const float* __restrict__ logits, int l
       if (v > best) { best = v; arg = k; }
     }
     occ[i] = (unsigned char)arg;
+    if (geo) geo[i] = (unsigned char)(arg != free_idx ? 0 : geo_value);
   }
 }
 
@@ -486,10 +489,32 @@ PW_API int pw_copy_channels(const float* x, int x_ld, float* y, int y_ld, long l
 PW_API int pw_argmax_zyx_to_xyz(const float* logits, int ld, int ncls, unsigned char* occ, int gx,
                                 int gy, int gz, void* stream) {
   PW_REQUIRE(logits && occ && ncls > 0 && ld >= ncls);
-  argmax_zyx_to_xyz_kernel<<<grid_for((long long)gx * gy * gz), TPB, 0, ST>>>(logits, ld, ncls,
-                                                                               occ, gx, gy, gz);
+  argmax_zyx_to_xyz_kernel<<<grid_for((long long)gx * gy * gz), TPB, 0, ST>>>(
+      logits, ld, ncls, occ, nullptr, 0, 0, gx, gy, gz);
   PW_LAUNCH_CHECK(); pw_count_launch(1);
   return 0;
+}
+
+PW_API int pw_argmax_geo_zyx_to_xyz(const float* logits, int ld, int ncls, int free_idx,
+                                    int geo_value, unsigned char* occ, unsigned char* geo, int gx,
+                                    int gy, int gz, void* stream) {
+  PW_REQUIRE(logits && occ && geo && ncls > 0 && ld >= ncls);
+  argmax_zyx_to_xyz_kernel<<<grid_for((long long)gx * gy * gz), TPB, 0, ST>>>(
+      logits, ld, ncls, occ, geo, free_idx, geo_value, gx, gy, gz);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+// Strided rows -> contiguous rows on `stream` (cudaMemcpy2DAsync, direction from
+// the pointers): ONE call moves a frame's images out of the loader's camera-major
+// host batch.  Not counted as a kernel launch.
+PW_API int pw_copy_rows(void* dst, long long dst_pitch, const void* src, long long src_pitch,
+                        long long row_bytes, long long rows, void* stream) {
+  PW_REQUIRE(dst && src && row_bytes > 0 && rows > 0 && row_bytes <= dst_pitch &&
+             row_bytes <= src_pitch);
+  cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch,
+                                    (size_t)row_bytes, (size_t)rows, cudaMemcpyDefault, ST);
+  return e == cudaSuccess ? 0 : (int)e;
 }
 
 PW_API int pw_density_occ_zyx_to_xyz(const float* density, int density_ld, const float* semantic,

@@ -542,6 +542,36 @@ def argmax_zyx_to_xyz(logits_cl):
     return occ
 
 
+def argmax_geo_zyx_to_xyz(logits_cl, free_idx, geo_value):
+    """logits [1,Z,Y,X,ncls] -> uint8 [2,X,Y,Z]: [0] the argmax grid, [1] the
+    geometry grid (0 where class != free_idx else geo_value) -- one buffer, so
+    one device->host transfer brings both."""
+    _, gz, gy, gx, ncls = logits_cl.shape
+    both = torch.empty((2, gx, gy, gz), device=logits_cl.device, dtype=torch.uint8)
+    check(_lib.lib().pw_argmax_geo_zyx_to_xyz(
+        _ptr(logits_cl), cl_ld(logits_cl), ncls, int(free_idx), int(geo_value),
+        _ptr(both[0]), _ptr(both[1]), gx, gy, gz, _stream()),
+        'pw_argmax_geo_zyx_to_xyz')
+    return both
+
+
+def copy_rows_(dst, src, stream=None):
+    """dst [R, ...] (rows contiguous, device) <- src [R, ...] whose rows are
+    contiguous but strided (pinned host or device), as ONE asynchronous
+    cudaMemcpy2D on ``stream`` (default: the current stream)."""
+    assert dst.is_cuda and dst.shape == src.shape and dst.dtype == src.dtype
+    assert dst[0].is_contiguous() and src[0].is_contiguous()
+    rows = dst.shape[0]
+    row_bytes = dst[0].numel() * dst.element_size()
+    pitch = lambda t: (t.stride(0) if rows > 1 else t[0].numel()) * t.element_size()
+    st = stream.cuda_stream if stream is not None else \
+        torch.cuda.current_stream(dst.device).cuda_stream
+    check(_lib.lib().pw_copy_rows(_ptr(dst), pitch(dst), _ptr(src), pitch(src),
+                                  row_bytes, rows, ctypes.c_void_p(st)),
+          'pw_copy_rows')
+    return dst
+
+
 def density_occ_zyx_to_xyz(density_cl, semantic_cl, thr, empty_idx):
     """density [1,Z,Y,X,1+] (channel 0 used), semantic [1,Z,Y,X,ncls]."""
     _, gz, gy, gx, ncls = semantic_cl.shape

@@ -39,11 +39,11 @@ class _Bottleneck(nn.Module):
         return p
 
     @staticmethod
-    def run(p, x):
+    def run(p, x, out=None):
         identity = ops.conv(x, p[3]) if len(p) == 4 else x
         y = ops.conv(x, p[0], 'relu')
         y = ops.conv(y, p[1], 'relu')
-        return ops.conv(y, p[2], 'relu', residual=identity)
+        return ops.conv(y, p[2], 'relu', residual=identity, out=out)
 
 
 class _BasicBlock(nn.Module):
@@ -65,10 +65,10 @@ class _BasicBlock(nn.Module):
         return p
 
     @staticmethod
-    def run(p, x):
+    def run(p, x, out=None):
         identity = ops.conv(x, p[2]) if len(p) == 3 else x
         y = ops.conv(x, p[0], 'relu')
-        return ops.conv(y, p[1], 'relu', residual=identity)
+        return ops.conv(y, p[1], 'relu', residual=identity, out=out)
 
 
 @BACKBONES.register_module()
@@ -201,11 +201,14 @@ class ResNet(BaseModule):
                 outs.append(ops.to_logical(x))
         return tuple(outs)
 
-    def run_layer(self, i, x):
+    def run_layer(self, i, x, out=None):
+        """Residual stage i on a cl array; ``out`` receives the last block's
+        output (e.g. one frame's rows of a batch other frames are written to)."""
         p = self.packs()
         blk = type(getattr(self, self.res_layers[i])[0])
-        for bp in p['layers'][i]:
-            x = blk.run(bp, x)
+        bps = p['layers'][i]
+        for k, bp in enumerate(bps):
+            x = blk.run(bp, x, out=out if k == len(bps) - 1 else None)
         return x
 
     def forward(self, x):

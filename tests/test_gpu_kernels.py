@@ -167,6 +167,15 @@ def test_voxel_side_elementwise():
     want = logits[0].argmax(-1).permute(2, 1, 0)            # [X,Y,Z]
     assert occ.dtype == torch.uint8 and torch.equal(occ.long(), want)
     assert occ[0, 0, 0] == 3
+    # preworld.py:205-221: geo_occ = num_classes-1 where the class is 17 else 0
+    logits[0, 1, 2, 3, 17] = 50.0
+    both = ops.argmax_geo_zyx_to_xyz(logits.to(DEV), 17, 17).cpu()
+    want = logits[0].argmax(-1).permute(2, 1, 0)
+    want_geo = torch.ones_like(want) * 17
+    want_geo[want != 17] = 0
+    assert both.shape == (2, 9, 7, 5) and both.dtype == torch.uint8
+    assert torch.equal(both[0].long(), want) and torch.equal(both[1].long(), want_geo)
+    assert both[1, 3, 2, 1] == 17 and (both[1] == 17).sum() >= 1
     dens = torch.rand(1, 5, 7, 9, 2, generator=g) * 17
     occ, geo = ops.density_occ_zyx_to_xyz(dens.to(DEV)[..., 0:1],
                                           logits.to(DEV)[..., :17], 8.5, 17)
@@ -553,3 +562,25 @@ def test_device_temporal_miou_matches_oracle():
         assert np.array_equal(getattr(dev, f'occ_hist_{k}s'), ref.m[idx].occ_hist)
     assert dev.count_miou()[1] == ref.count_miou()
     assert dev.count_iou() == ref.count_iou()
+
+
+def test_copy_rows_splits_the_camera_major_batch():
+    """ops.copy_rows_: one pitched async copy takes frame f's images out of the
+    loader's camera-major [B, N*T, C, H, W] batch (bevdet_occ.py:88-97), from
+    pinned host memory and from device memory."""
+    g = torch.Generator().manual_seed(3)
+    bn, nf = 6, 3
+    raw = torch.randn(1, bn * nf, 3, 16, 44, generator=g)
+    for src_t in (raw.pin_memory(), raw.to(DEV)):
+        src = src_t.view(bn, nf, 3, 16, 44)
+        for f in range(nf):
+            dst = torch.zeros(bn, 3, 16, 44, device=DEV)
+            ops.copy_rows_(dst[2:6], src[2:6, f])
+            torch.cuda.synchronize()
+            want = raw.view(bn, nf, 3, 16, 44)[:, f]
+            assert torch.equal(dst[2:6].cpu(), want[2:6]) and (dst[:2] == 0).all()
+    side = torch.cuda.Stream()
+    dst = torch.zeros(bn, 3, 16, 44, device=DEV)
+    ops.copy_rows_(dst[:1], raw.pin_memory().view(bn, nf, 3, 16, 44)[:1, 1], stream=side)
+    side.synchronize()
+    assert torch.equal(dst[0].cpu(), raw.view(bn, nf, 3, 16, 44)[0, 1])

@@ -1,2 +1,6 @@
-timeout -s KILL 150 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-profile 2>&1 | tail -1 | cut -c1-330
-timeout -s KILL 200 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -q -x -p no:cacheprovider 2>&1 | tail -3
+export PW_HALO_SETS=1
+timeout -s KILL 120 python tools/umma_probe.py small 2>&1 | sed -e "s/'simt': '[^']*', //" -e "s/'umma': '[^']*', //" | cut -c1-150 | tail -14
+timeout -s KILL 200 python tools/umma_probe.py full 2>&1 | sed -e "s/'simt': '[^']*', //" -e "s/'umma': '[^']*', //"
+export PW_HALO_SETS=2
+echo SETS2
+timeout -s KILL 200 python tools/umma_probe.py full 2>&1 | sed -e "s/'simt': '[^']*', //" -e "s/'umma': '[^']*', //"
