@@ -121,7 +121,8 @@ class LaunchProfiler:
         for name in _lib.SIGNATURES:
             if name in ('pw_abi_version', 'pw_launch_count',
                         'pw_lift_workspace_bytes', 'pw_conv_umma_supported',
-                        'pw_conv_halo_supported'):
+                        'pw_conv_halo_supported', 'pw_conv_fold_supported',
+                        'pw_conv_fold_n'):
                 continue
             fn = getattr(self.L, name)
             self.orig[name] = fn
@@ -142,7 +143,8 @@ class LaunchProfiler:
 
     @staticmethod
     def _shape(name, a):
-        if name in ('pw_conv_fwd', 'pw_conv_umma_fwd', 'pw_conv_halo_fwd'):
+        if name in ('pw_conv_fwd', 'pw_conv_umma_fwd', 'pw_conv_halo_fwd',
+                    'pw_conv_fold_fwd'):
             d = a[0]._obj
             return (f'{d.n}x{d.d}x{d.h}x{d.w}x{d.cin}->{d.cout} '
                     f'k{d.kd}{d.kh}{d.kw} s{d.sw} d{d.dw}')
@@ -151,7 +153,8 @@ class LaunchProfiler:
     @staticmethod
     def _work(name, a):
         """(algorithmic flops, algorithmic bytes) of one call."""
-        if name in ('pw_conv_fwd', 'pw_conv_umma_fwd', 'pw_conv_halo_fwd'):
+        if name in ('pw_conv_fwd', 'pw_conv_umma_fwd', 'pw_conv_halo_fwd',
+                    'pw_conv_fold_fwd'):
             d = a[0]._obj
             m = d.n * d.od * d.oh * d.ow
             k = d.kd * d.kh * d.kw * d.cin
@@ -182,7 +185,9 @@ class LaunchProfiler:
         layers = {}
         for name, e0, e1, (fl, by), shape in self.records:
             ms = e0.elapsed_time(e1)
-            a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
+            # pw_conv_fold_fwd launches the same CUDA kernel (conv_halo_kernel)
+            fam = 'pw_conv_halo_fwd' if name == 'pw_conv_fold_fwd' else name
+            a = agg.setdefault(fam, [0, 0.0, 0.0, 0.0])
             a[0] += 1; a[1] += ms; a[2] += fl; a[3] += by
             if shape:
                 b = layers.setdefault(name[3:-4] + ' ' + shape, [0, 0.0, 0.0])
@@ -392,9 +397,10 @@ def main():
                      'implicit GEMM, 3xTF32 split, TMA)')
             # the roofline line is quoted on the kernel's heaviest LAYER SHAPE
             # (per-launch figures); the whole family is reported next to it
-            fam = top[3:-4] + ' '
+            fams = ('conv_halo ', 'conv_fold ') if top == 'pw_conv_halo_fwd' \
+                else (top[3:-4] + ' ',)
             lname, lay = max(((n, v) for n, v in prof.layers.items()
-                              if n.startswith(fam)),
+                              if n.startswith(fams)),
                              key=lambda kv: kv[1]['ms_per_step'])
             roof = {'kernel': kname, 'layer': lname,
                     'bound': 'tensor', 'achieved': lay['tflops'],

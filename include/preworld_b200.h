@@ -90,6 +90,23 @@ int pw_conv_halo_fwd(const pw_conv_desc* desc, const float* x,
                      const float* bias, const float* residual, float* y,
                      void* stream);
 
+/* The same kernel with the kw taps along x folded into the MMA's N dimension
+ * (stride 1 along x, kw in 2..4): the main loop runs kd*kh taps over N =
+ * kw*fold_n columns, P[row, kx, n] over INPUT columns, and the epilogue adds
+ * the shifted partial rows, out[x] = sum_kx P[x + kx*dw, kx, :] -- every input
+ * row is split and read from tensor memory once per (kz,ky) instead of once per
+ * tap.  Weights: wf_hi/wf_lo [slabs*kw*fold_n, kd*kh*cin] (K-major), row
+ * (slab*kw + kx)*fold_n + n = output channel slab*fold_n + n at x tap kx (zero
+ * rows beyond cout), column (kz*kh + ky)*cin + ci; fold_n = pw_conv_fold_n(cout),
+ * slabs = ceil(cout / fold_n).  Same results as pw_conv_halo_fwd up to the
+ * summation order of the taps. */
+int pw_conv_fold_n(int cout);
+int pw_conv_fold_supported(const pw_conv_desc* desc);
+int pw_conv_fold_fwd(const pw_conv_desc* desc, const float* x,
+                     const float* wf_hi, const float* wf_lo, const float* scale,
+                     const float* bias, const float* residual, float* y,
+                     void* stream);
+
 /* ------------------------------------------------------------------------
  * Image-side element-wise helpers (all channels-last).
  * ---------------------------------------------------------------------- */

@@ -49,6 +49,10 @@ SIGNATURES = {
     'pw_conv_halo_supported': [ctypes.POINTER(ConvDesc)],
     'pw_conv_halo_fwd': [ctypes.POINTER(ConvDesc), c_p, c_p, c_p, c_p, c_p,
                          c_p, c_p, c_p],
+    'pw_conv_fold_n': [c_int],
+    'pw_conv_fold_supported': [ctypes.POINTER(ConvDesc)],
+    'pw_conv_fold_fwd': [ctypes.POINTER(ConvDesc), c_p, c_p, c_p, c_p, c_p,
+                         c_p, c_p, c_p],
     'pw_nchw_to_nhwc_pad': [c_p, c_ll, c_p, c_int, c_int, c_int, c_int, c_int,
                             c_p],
     'pw_nchw_to_s2d_nhwc': [c_p, c_ll, c_p, c_int, c_int, c_int, c_int, c_int,

@@ -73,6 +73,13 @@ struct HaloParams {
   int nacc;                    // accumulator copies per M tile (k-step k -> copy k % nacc):
                                // independent MMA chains hide the accumulate latency at small N
   int tmem_cols;
+  // x-tap folding (fold > 0): the kw taps along x become N columns -- the MMA
+  // computes P[row, kx*fold_n + n] over INPUT columns and the epilogue adds the
+  // shifted partial rows, out[x] = sum_kx P[x + kx*fold_shift, kx, :].  The main
+  // loop then runs kh*kd taps with N = fold*fold_n and every A row is split once
+  // per (ky, kz) instead of once per tap.  n_tile == fold * fold_n.
+  int fold, fold_n, fold_shift;
+  int out_bx;                  // valid outputs per x row group (== bx unless folded)
   int cps;                     // CTAs per SM the plan counts on (1 or 2)
   int dbg;                     // PW_HALO_DBG knock-out bits (timing experiments only)
   long long* ts;               // PW_HALO_TS: per-CTA clock64 milestones (debug)
@@ -152,7 +159,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
   const int tz = tt % p.tiles_z;
   const int img = tt / p.tiles_z;
   const int x0 = tx * p.cbx, y0 = ty * p.cby, z0 = tz * p.cbz;
-  const int n0 = blockIdx.y * p.n_tile;
+  const int n0w = blockIdx.y * p.n_tile;                 // weight rows of this N slab
+  const int n_real = p.fold ? p.fold_n : p.n_tile;       // output channels of this N slab
+  const int n0 = blockIdx.y * n_real;
   const int T = p.n_taps;
   const int total_ct = p.chunks * T;            // (chunk, tap) pairs
 
@@ -190,8 +199,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
           mbar_expect_tx(b_full + 8 * s, (uint32_t)b_stage);
           const uint32_t dst = b_ring_u32 + (uint32_t)(s * b_stage);
           const int k0 = (t * p.chunks + c) * BLOCK_K;   // weights are tap-major in K
-          tma_load_2d(dst, &map_bh, b_full + 8 * s, k0, n0);
-          tma_load_2d(dst + p.n_tile * ROW_BYTES, &map_bl, b_full + 8 * s, k0, n0);
+          tma_load_2d(dst, &map_bh, b_full + 8 * s, k0, n0w);
+          tma_load_2d(dst + p.n_tile * ROW_BYTES, &map_bl, b_full + 8 * s, k0, n0w);
         }
         __syncwarp();
         if (++s == p.nb) { s = 0; ph ^= 1; }
@@ -396,7 +405,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       t[15] = t[0] + sp_wait; t[4] = t[0] + sp_busy;
     }
     const uint32_t stage = smem_base_u32 + (uint32_t)(sw_id * STAGE_BYTES_PER_WARP);
-    const int ncg = (p.n_tile + 31) >> 5;
+    const int ncg = (n_real + 31) >> 5;
     const int items = p.mt * ncg;
     const int act_end = p.act_channels > 0 ? p.act_channels : p.cout;
     const bool vec_ok = ((p.out_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
@@ -417,7 +426,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
         if (p.mt_axis == 0) ox += mm * p.bx;
         else if (p.mt_axis == 1) oy += mm * p.by;
         else oz += mm * p.bz;
-        const bool ok = mm < p.mt && ox < p.ow && oy < p.oh && oz < p.od;
+        const bool ok = mm < p.mt && (Rr & (p.bx - 1)) < p.out_bx && ox < p.ow && oy < p.oh &&
+                        oz < p.od;
         rowpix[mm][i] = ok ? ((img * p.od + oz) * p.oh + oy) * p.ow + ox : -1;
       }
     }
@@ -428,7 +438,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       const int m = item / ncg;
       const int cb = n0 + (item - m * ncg) * 32 + ch4 * 4;
       const bool on = p.res != nullptr && vec_ok && cb + 4 <= p.cout &&
-                      (item - m * ncg) * 32 + ch4 * 4 < p.n_tile;
+                      (item - m * ncg) * 32 + ch4 * 4 < n_real;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int pixi = m == 0 ? rowpix[0][i] : rowpix[1][i];
@@ -444,13 +454,31 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     for (int item = set; item < items; item += SPLIT_SETS) {
       const int m = item / ncg;
       const int col0 = (item - m * ncg) * 32;
-      const int ncol = min(32, p.n_tile - col0);         // 16 or 32 (warp-uniform)
+      const int ncol = min(32, n_real - col0);           // 16 or 32 (warp-uniform)
       if (item != set) prefetch_res(item);
       // phase 1: this thread's accumulator row (32 channels) -> its staging row
       for (int half = 0; half * 16 < ncol; ++half) {
         float acc[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        if (p.fold) {
+          // out[row] = sum_kx P_kx[row + kx * shift]: the partial rows of the other
+          // x taps sit `shift` lanes further down in this warp (bx <= 32)
+          for (int kx = 0; kx < p.fold; ++kx) {
+            uint32_t a[16], b[16];
+            const uint32_t taddr = tmem_base + lane_field +
+                                   (uint32_t)(m * tile_cols + kx * p.fold_n + half * 16);
+            tmem_ld16_nowait(taddr, a);
+            tmem_ld16_nowait(taddr + p.n_tile, b);
+            tmem_ld_wait();
+            const int sh = kx * p.fold_shift;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float v = __uint_as_float(a[j]) + __uint_as_float(b[j]);
+              acc[j] += __shfl_down_sync(0xffffffffu, v, sh);
+            }
+          }
+        } else
         for (int copy = 0; copy < p.nacc; ++copy) {
           uint32_t a[16], b[16];
           const uint32_t taddr = tmem_base + lane_field +
@@ -562,12 +590,14 @@ struct HaloPlan {
 // Tuning knobs for experiments (tools/umma_probe.py), read once per process.
 struct HaloKnobs {
   int nt = 0, nacc = 0, nb = 0, mt = 0, dbg = 0, sets = 0;
+  int fold = -1;               // PW_HALO_FOLD=0: pw_conv_fold_supported() always says no
   bool ts = false;
   HaloKnobs() {
     auto geti = [](const char* k) { const char* e = getenv(k); return e ? atoi(e) : 0; };
     nt = geti("PW_HALO_NT"); nacc = geti("PW_HALO_NACC"); nb = geti("PW_HALO_NB");
     mt = geti("PW_HALO_MT"); dbg = geti("PW_HALO_DBG"); sets = geti("PW_HALO_SETS");
     ts = getenv("PW_HALO_TS") != nullptr;
+    if (getenv("PW_HALO_FOLD")) fold = geti("PW_HALO_FOLD");
   }
 };
 const HaloKnobs& knobs() {
@@ -595,22 +625,44 @@ const HaloPlan& make_plan(const pw_conv_desc& in) {
 
 // Best plan for one kernel variant: `sets` split sets per CTA, the CTA limited to
 // `tmem_limit` TMEM columns and `smem_limit` bytes, `cps` CTAs resident per SM.
-HaloPlan search_plan(const pw_conv_desc& in, int sets, int tmem_limit, int smem_limit, int cps);
+HaloPlan search_plan(const pw_conv_desc& in, int sets, int tmem_limit, int smem_limit, int cps,
+                     int fold_n = 0);
+
+// Plan of the x-tap-folded variant (pw_conv_fold_fwd), cached like make_plan.
+const HaloPlan& make_fold_plan(const pw_conv_desc& in, int fold_n) {
+  static std::mutex mu;
+  static std::unordered_map<std::string, HaloPlan> cache;
+  pw_conv_desc key = in;
+  key.act = 0; key.act_channels = 0; key.out_ld = 0; key.res_ld = 0; key.w_ld = 0;
+  std::string k(reinterpret_cast<const char*>(&key), sizeof(key));
+  k.push_back((char)fold_n);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(k);
+  if (it == cache.end())
+    it = cache.emplace(k, search_plan(key, 2, 512, SMEM_LIMIT, 1, fold_n)).first;
+  return it->second;
+}
 
 HaloPlan make_plan_uncached(const pw_conv_desc& in) {
   HaloPlan one_cta = search_plan(in, 2, 512, SMEM_LIMIT, 1);
-  if (knobs().sets == 2) return one_cta;
+  // The 1-set / 2-CTAs-per-SM variant is opt-in (PW_HALO_SETS=1): measured on the
+  // path's layers it wins 7-9 % on two shapes (32->64 k333, 224->32 k111) and loses
+  // up to 75 % where the 256-column TMEM share forces one M tile per CTA.
+  if (knobs().sets != 1) return one_cta;
   HaloPlan two_ctas = search_plan(in, 1, 256, SMEM_LIMIT_2CTA, 2);
-  if (!two_ctas.ok) return one_cta;
-  if (!one_cta.ok || knobs().sets == 1) return two_ctas;
-  return two_ctas.cost < one_cta.cost ? two_ctas : one_cta;
+  return two_ctas.ok ? two_ctas : one_cta;
 }
 
 HaloPlan search_plan(const pw_conv_desc& in, const int SPLIT_SETS, const int tmem_limit,
-                     const int smem_limit, const int cps) {
+                     const int smem_limit, const int cps, const int fold_n) {
   HaloPlan plan;
   plan.sets = SPLIT_SETS;
   pw_conv_desc c = in;
+  // x-tap folding: stride 1 along x, 2..4 taps, N = kw * fold_n <= 128
+  const int fold = fold_n > 0 ? c.kw : 0;
+  if (fold_n > 0 && (c.sw != 1 || c.kw < 2 || c.kw > 4 || c.kw * fold_n > 128 ||
+                     (fold_n != 16 && fold_n != 32)))
+    return plan;
   if (c.cin % BLOCK_K != 0 || c.in_ld % 4 != 0 || c.cout < 1) return plan;
   if (c.n < 1 || c.od < 1 || c.oh < 1 || c.ow < 1) return plan;
   const bool pointwise = c.kd == 1 && c.kh == 1 && c.kw == 1 && c.sd == 1 && c.sh == 1 &&
@@ -623,27 +675,34 @@ HaloPlan search_plan(const pw_conv_desc& in, const int SPLIT_SETS, const int tme
     c.n = c.d = c.h = c.od = c.oh = 1;
   }
   const int chunks = c.cin / BLOCK_K;
-  const int T = c.kd * c.kh * c.kw;
+  const int T = c.kd * c.kh * (fold ? 1 : c.kw);         // taps the main loop iterates
   static const int boxes3[][3] = {{8, 4, 4}, {8, 8, 2}, {16, 4, 2}, {16, 8, 1}, {8, 16, 1},
                                   {32, 4, 1}, {16, 2, 4}, {32, 2, 2}, {8, 2, 8}};
   static const int boxes2[][3] = {{16, 8, 1}, {8, 16, 1}, {32, 4, 1}, {64, 2, 1}, {128, 1, 1}};
   static const int boxes1[][3] = {{128, 1, 1}};
   const int (*boxes)[3] = pointwise ? boxes1 : (c.od > 1 ? boxes3 : boxes2);
   const int nboxes = pointwise ? 1 : (c.od > 1 ? 9 : 5);
-  const int n_full = min(round_up(c.cout, 16), 128);
+  const int n_full = fold ? fold * fold_n : min(round_up(c.cout, 16), 128);
 
   double best = -1;
   for (int ntry = 0; ntry < 3; ++ntry) {
     const int n_tile = ntry == 0 ? n_full : (ntry == 1 ? 64 : 32);
-    if (ntry > 0 && n_tile >= n_full) continue;
+    if (ntry > 0 && (fold || n_tile >= n_full)) continue;
     if (knobs().nt && knobs().nt != n_tile && knobs().nt < n_full) continue;
-    const int slabs = pw_ceil_div(c.cout, n_tile);
+    const int slabs = fold ? pw_ceil_div(c.cout, fold_n) : pw_ceil_div(c.cout, n_tile);
     const int b_stage = 2 * n_tile * ROW_BYTES;
     for (int bi = 0; bi < nboxes; ++bi) {
       for (int mt = 1; mt <= 2; ++mt) {
         for (int axis = 0; axis < (mt == 1 ? 1 : 3); ++axis) {
           int b[3] = {boxes[bi][0], boxes[bi][1], boxes[bi][2]};
           int cb[3] = {b[0], b[1], b[2]};
+          if (fold) {
+            // an x row group (bx input columns) must sit inside one warp and keep
+            // at least half of its rows as outputs
+            if (mt != 1 || b[0] > 32) continue;
+            cb[0] = b[0] - (c.kw - 1) * c.dw;
+            if (cb[0] * 2 < b[0]) continue;
+          }
           if (mt == 2) cb[axis] *= 2;
           if (pointwise && axis != 0) continue;
           const int ext[3] = {c.ow, c.oh, c.od};
@@ -661,7 +720,7 @@ HaloPlan search_plan(const pw_conv_desc& in, const int SPLIT_SETS, const int tme
           const int halo_stride = round_up(hrows * ROW_BYTES, 1024);
           // TMEM: accumulators (mt * nacc * 2n) + A ring (nb * mt * 64 columns)
           int nacc = 1;
-          if (knobs().nacc == 2) nacc = 2;
+          if (knobs().nacc == 2 && !fold) nacc = 2;
           if (mt * nacc * 2 * n_tile + 2 * mt * A_SLOT_COLS > tmem_limit) nacc = 1;
           const int acc_cols = mt * nacc * 2 * n_tile;
           int nb = min(T * chunks, min(4, (tmem_limit - acc_cols) / (mt * A_SLOT_COLS)));
@@ -718,6 +777,8 @@ HaloPlan search_plan(const pw_conv_desc& in, const int SPLIT_SETS, const int tme
             p.mt_halo_off = mt == 2 ? b[axis] * st[axis] * hstr[axis] : 0;
             p.halo_stride = halo_stride;
             p.halo_region = max(nh * halo_stride, 4 * SPLIT_SETS * STAGE_BYTES_PER_WARP);
+            p.fold = fold; p.fold_n = fold_n; p.fold_shift = c.dw;
+            p.out_bx = fold ? cb[0] : b[0];
             p.tiles_x = pw_ceil_div(c.ow, cb[0]); p.tiles_y = pw_ceil_div(c.oh, cb[1]);
             p.tiles_z = pw_ceil_div(c.od, cb[2]);
             p.n_tile = n_tile; p.nh = nh; p.nb = nb; p.nacc = nacc;
@@ -737,7 +798,7 @@ HaloPlan search_plan(const pw_conv_desc& in, const int SPLIT_SETS, const int tme
   if (!plan.ok) return plan;
   HaloParams& p = plan.p;
   p.od = c.od; p.oh = c.oh; p.ow = c.ow; p.cout = c.cout;
-  p.kh = c.kh; p.kw = c.kw; p.n_taps = T; p.chunks = chunks;
+  p.kh = c.kh; p.kw = fold ? 1 : c.kw; p.n_taps = T; p.chunks = chunks;
   p.sd = c.sd; p.sh = c.sh; p.sw = c.sw; p.pd = c.pd; p.ph = c.ph; p.pw = c.pw;
   p.dd = c.dd; p.dh = c.dh; p.dw = c.dw;
   p.out_ld = c.out_ld; p.res_ld = c.res_ld; p.act = c.act; p.act_channels = c.act_channels;
@@ -754,20 +815,16 @@ PW_API int pw_conv_halo_supported(const pw_conv_desc* d) {
   return make_plan(*d).ok ? 1 : 0;
 }
 
-PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* wt_hi,
-                            const float* wt_lo, const float* scale, const float* bias,
-                            const float* residual, float* y, void* stream) {
-  PW_REQUIRE(d && x && wt_hi && wt_lo && y);
-  PW_REQUIRE(d->sd >= 1 && d->sh >= 1 && d->sw >= 1);
-  PW_REQUIRE(d->out_ld >= d->cout);
-  PW_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wt_hi & 15) == 0 &&
-             ((uintptr_t)wt_lo & 15) == 0);
-  PW_REQUIRE(residual == nullptr || d->res_ld >= d->cout);
-  PW_REQUIRE(d->act_channels >= 0 && (d->act_channels & 3) == 0);
+namespace {
+
+// Encodes the three tensor maps of a plan and launches its kernel variant.
+// `w_rows` = rows of the (pre-split) weight matrices [w_rows, n_taps * cin].
+int launch_halo(HaloPlan plan /* copy: per-launch fields are filled here */,
+                const pw_conv_desc* d, long long w_rows, const float* x, const float* wt_hi,
+                const float* wt_lo, const float* scale, const float* bias,
+                const float* residual, float* y, void* stream) {
   EncodeTiledFn enc = encode_tiled_fn();
   PW_REQUIRE(enc != nullptr);
-  HaloPlan plan = make_plan(*d);                 // copy: per-launch fields are filled below
-  PW_REQUIRE(plan.ok);
   const pw_conv_desc& c = plan.c;
   HaloParams& p = plan.p;
   p.out_ld = d->out_ld; p.res_ld = d->res_ld; p.act = d->act; p.act_channels = d->act_channels;
@@ -791,7 +848,7 @@ PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* 
   }
   const long long K = (long long)p.n_taps * c.cin;
   for (int i = 0; i < 2; ++i) {
-    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)c.cout};
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)w_rows};
     cuuint64_t gstr[1] = {(cuuint64_t)K * 4};
     cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)p.n_tile};
     cuuint32_t estr[2] = {1, 1};
@@ -830,9 +887,9 @@ PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* 
     double sum[16] = {0};
     for (size_t i = 0; i < n_cta; ++i)
       for (int k = 0; k < 16; ++k) sum[k] += (double)(h[i * 16 + k] - h[i * 16]);
-    fprintf(stderr, "[halo ts] grid %u x %u mt %d n_tile %d nh %d nb %d nacc %d box %dx%dx%d halo %dx%dx%d smem %zu tmem %d sets %d cps %d:",
+    fprintf(stderr, "[halo ts] grid %u x %u mt %d n_tile %d nh %d nb %d nacc %d box %dx%dx%d halo %dx%dx%d smem %zu tmem %d sets %d fold %d:",
             plan.grid.x, plan.grid.y, p.mt, p.n_tile, p.nh, p.nb, p.nacc, p.cbx, p.cby, p.cbz,
-            p.hx, p.hy, p.hz, plan.smem, p.tmem_cols, plan.sets, p.cps);
+            p.hx, p.hy, p.hz, plan.smem, p.tmem_cols, plan.sets, p.fold);
     for (int k = 0; k < 16; ++k) fprintf(stderr, " t%d=%.0f", k, sum[k] / n_cta);
     fprintf(stderr, "\n");
     free(h);
@@ -840,4 +897,56 @@ PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* 
   }
   pw_count_launch(1);
   return 0;
+}
+
+int check_halo_args(const pw_conv_desc* d, const float* x, const float* wt_hi,
+                    const float* wt_lo, const float* residual, const float* y) {
+  PW_REQUIRE(d && x && wt_hi && wt_lo && y);
+  PW_REQUIRE(d->sd >= 1 && d->sh >= 1 && d->sw >= 1);
+  PW_REQUIRE(d->out_ld >= d->cout);
+  PW_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wt_hi & 15) == 0 &&
+             ((uintptr_t)wt_lo & 15) == 0);
+  PW_REQUIRE(residual == nullptr || d->res_ld >= d->cout);
+  PW_REQUIRE(d->act_channels >= 0 && (d->act_channels & 3) == 0);
+  return 0;
+}
+
+}  // namespace
+
+PW_API int pw_conv_halo_fwd(const pw_conv_desc* d, const float* x, const float* wt_hi,
+                            const float* wt_lo, const float* scale, const float* bias,
+                            const float* residual, float* y, void* stream) {
+  if (int rc = check_halo_args(d, x, wt_hi, wt_lo, residual, y)) return rc;
+  const HaloPlan& plan = make_plan(*d);
+  PW_REQUIRE(plan.ok);
+  return launch_halo(plan, d, d->cout, x, wt_hi, wt_lo, scale, bias, residual, y, stream);
+}
+
+// ---- x-tap-folded variant --------------------------------------------------------
+PW_API int pw_conv_fold_n(int cout) { return cout <= 16 ? 16 : 32; }
+
+PW_API int pw_conv_fold_supported(const pw_conv_desc* d) {
+  if (!d || knobs().fold == 0) return 0;
+  if (d->sd < 1 || d->sh < 1 || d->sw != 1 || d->kw < 2) return 0;
+  if (encode_tiled_fn() == nullptr) return 0;
+  // Feasibility only; the caller decides (preworld_b200/ops.py: USE_FOLD, off by
+  // default).  Measured (tools/umma_probe.py and the full step): the main loop gets
+  // ~3x shorter, but a folded CTA covers one M tile of (bx - 2) outputs per row
+  // group, so the per-CTA prologue + halo latency + epilogue (not overlapped: one
+  // CTA per SM) is paid 2.3x as often -- inside the step 32->32 k333 runs 334 us
+  // folded vs 309 us unfolded, and every extra N slab re-splits the halo (32->64:
+  // +70 %).  It becomes the faster kernel once CTAs are persistent and prefetch
+  // the next tile's halo.
+  return make_fold_plan(*d, pw_conv_fold_n(d->cout)).ok ? 1 : 0;
+}
+
+PW_API int pw_conv_fold_fwd(const pw_conv_desc* d, const float* x, const float* wf_hi,
+                            const float* wf_lo, const float* scale, const float* bias,
+                            const float* residual, float* y, void* stream) {
+  if (int rc = check_halo_args(d, x, wf_hi, wf_lo, residual, y)) return rc;
+  const int fold_n = pw_conv_fold_n(d->cout);
+  const HaloPlan& plan = make_fold_plan(*d, fold_n);
+  PW_REQUIRE(plan.ok);
+  const long long w_rows = (long long)pw_ceil_div(d->cout, fold_n) * d->kw * fold_n;
+  return launch_halo(plan, d, w_rows, x, wf_hi, wf_lo, scale, bias, residual, y, stream);
 }

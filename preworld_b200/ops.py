@@ -12,6 +12,7 @@ other dims dense over a pixel pitch ``ld >= C``).  ``to_logical`` /
 ``[N,C,H,W]`` / ``[B,C,Z,Y,X]`` tensors with channels_last strides.
 """
 import ctypes
+import os
 
 import torch
 
@@ -75,7 +76,7 @@ class PackedConv:
     """Weights of one conv/linear in the kernel's layout: w [K, w_ld] with
     K = taps*cin_pad (tap-major), plus the folded per-channel affine."""
     __slots__ = ('w', 'scale', 'bias', 'cin', 'cout', 'k', 'stride', 'pad',
-                 'dil', 'w_ld', 'wt_hi', 'wt_lo')
+                 'dil', 'w_ld', 'wt_hi', 'wt_lo', 'wf_hi', 'wf_lo')
 
     def __init__(self, weight, bias=None, bn=None, stride=1, padding=0,
                  dilation=1, in_scale=None, in_shift=None, eps=None,
@@ -125,9 +126,11 @@ class PackedConv:
         wk = torch.zeros(*k, cin_pad, w_ld, device=w.device)
         wk[..., :cin, :cout] = w.permute(2, 3, 4, 1, 0)
         self.w = wk.reshape(-1, w_ld).contiguous()
-        self.wt_hi = self.wt_lo = None
+        self.wt_hi = self.wt_lo = self.wf_hi = self.wf_lo = None
         if cin % 32 == 0:
             self.set_umma_weights(w.permute(0, 2, 3, 4, 1).reshape(cout, -1))
+            if 2 <= k[2] <= 4 and cout <= FOLD_MAX_COUT:
+                self.set_fold_weights(w)
         if bn is not None:
             gamma, beta, mean, var, eps_ = bn
             s = gamma.detach().float() / torch.sqrt(var.detach().float() + eps_)
@@ -166,12 +169,34 @@ class PackedConv:
         self.wt_lo = (wt - hi).contiguous()
 
 
+    def set_fold_weights(self, w5):
+        """w5 [cout, cin, kd, kh, kw]: weights of the x-tap-folded kernel
+        (pw_conv_fold_fwd, layout in include/preworld_b200.h): rows
+        (slab, kx, n), columns (kz, ky, ci), pre-split hi/lo."""
+        cout, cin, kd, kh, kw = w5.shape
+        fold_n = 16 if cout <= 16 else 32            # == pw_conv_fold_n(cout)
+        slabs = -(-cout // fold_n)
+        wp = torch.zeros((slabs * fold_n, cin, kd, kh, kw), device=w5.device)
+        wp[:cout] = w5
+        wf = wp.view(slabs, fold_n, cin, kd, kh, kw).permute(0, 5, 1, 3, 4, 2) \
+            .reshape(slabs * kw * fold_n, kd * kh * cin).contiguous()
+        hi = (wf.view(torch.int32) & -8192).view(torch.float32)
+        self.wf_hi = hi.contiguous()
+        self.wf_lo = (wf - hi).contiguous()
+
+
 # The tensor-core path is used whenever the layer qualifies; set to False to
 # force the fp32 SIMT kernel (tests compare the two).
 USE_UMMA = True
 # ... and among the tensor-core kernels the halo-resident / TMEM-operand one
 # (conv_halo.cu) wherever its plan fits; False falls back to conv_umma.cu.
 USE_HALO = True
+# ... or its x-tap-folded variant (pw_conv_fold_fwd).  Off by default: with one
+# CTA per SM the folded kernel's smaller CTAs pay the prologue more often than
+# the shorter main loop saves (334 vs 309 us on the 32->32 volume layers inside
+# the step); PW_HALO_FOLD=1 or ops.USE_FOLD = True switches it on.
+USE_FOLD = os.environ.get('PW_HALO_FOLD') == '1'
+FOLD_MAX_COUT = 128          # fold weights are packed up to this width
 
 
 def conv(x, pc, act=None, residual=None, out=None, act_channels=0,
@@ -209,6 +234,13 @@ def conv(x, pc, act=None, residual=None, out=None, act_channels=0,
     if residual is not None:
         assert residual.shape == out.shape
     L = _lib.lib()
+    if USE_UMMA and USE_HALO and USE_FOLD and pc.wf_hi is not None and \
+            L.pw_conv_fold_supported(ctypes.byref(d)):
+        check(L.pw_conv_fold_fwd(ctypes.byref(d), _ptr(x), _ptr(pc.wf_hi),
+                                 _ptr(pc.wf_lo), _ptr(pc.scale), _ptr(pc.bias),
+                                 _ptr(residual), _ptr(out), _stream()),
+              'pw_conv_fold_fwd')
+        return out
     if USE_UMMA and USE_HALO and pc.wt_hi is not None and \
             L.pw_conv_halo_supported(ctypes.byref(d)):
         check(L.pw_conv_halo_fwd(ctypes.byref(d), _ptr(x), _ptr(pc.wt_hi),

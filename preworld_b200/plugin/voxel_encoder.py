@@ -55,6 +55,13 @@ class BasicBlock3D(nn.Module):
         if c1.wt_hi is not None and ds.wt_hi is not None:
             f.wt_hi = torch.cat([c1.wt_hi, ds.wt_hi], 0).contiguous()
             f.wt_lo = torch.cat([c1.wt_lo, ds.wt_lo], 0).contiguous()
+        # x-tap-folded layout: rows are (slab of 32 channels, kx, n) -- the two
+        # halves concatenate when each is a whole number of slabs
+        f.wf_hi = f.wf_lo = None
+        if c1.wf_hi is not None and ds.wf_hi is not None and \
+                c1.cout % 32 == 0 and ds.cout % 32 == 0:
+            f.wf_hi = torch.cat([c1.wf_hi, ds.wf_hi], 0).contiguous()
+            f.wf_lo = torch.cat([c1.wf_lo, ds.wf_lo], 0).contiguous()
         assert f.w_ld % 4 == 0 and c1.cout % 4 == 0
         return dict(c1=f, c2=c2, fused=True, split=c1.cout)
 

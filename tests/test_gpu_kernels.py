@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 from oracle import c_ref, torch_ref          # noqa: E402  (checker only)
 from oracle.cases import RENDER_CASE, render_inputs   # noqa: E402
-from preworld_b200 import ops                # noqa: E402
+from preworld_b200 import _lib, ops          # noqa: E402
 from preworld_b200 import synthetic as S     # noqa: E402
 
 DEV = 'cuda'
@@ -85,6 +85,62 @@ def test_conv_matches_torch_fp32(case, conv_path):
     assert got.shape == want.shape
     # fp32 FMA accumulation in a different order than the CPU reference
     assert _rel(got, want) < 2e-5, _rel(got, want)
+
+
+FOLD_CASES = [
+    # (dims, n, cin, cout, spatial, k, pad, dil): stride-1 3-tap convs with
+    # cout <= 32 -- the shapes pw_conv_fold_supported() takes by rule
+    (3, 1, 32, 32, (7, 13, 45), 3, 1, 1),      # ragged x: 45 = 3*14 + 3
+    (3, 2, 64, 32, (4, 9, 31), 3, 1, 1),       # two K chunks, batch 2
+    (3, 1, 32, 16, (5, 9, 37), 3, 1, 1),       # fold_n = 16
+    (2, 2, 64, 32, (19, 45), 3, 2, 2),         # dilated 2-D
+    (2, 1, 96, 24, (11, 29), 3, 1, 1),         # cout not a multiple of 16
+]
+
+
+@pytest.mark.parametrize('case', FOLD_CASES)
+def test_conv_fold_matches_torch_and_halo(case):
+    """The x-tap-folded launch (pw_conv_fold_fwd: kw taps in the MMA's N
+    dimension, shifted row sums in the epilogue) against torch fp32 and
+    against the unfolded tensor-core kernel, with affine + residual + ReLU."""
+    dims, n, cin, cout, sp, k, pad, dil = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(n, cin, *sp, generator=g)
+    w = torch.randn(cout, cin, *([k] * dims), generator=g) / (cin * k ** dims) ** .5
+    b = torch.randn(cout, generator=g)
+    r = torch.randn(n, cout, *sp, generator=g)
+    conv = F.conv2d if dims == 2 else F.conv3d
+    want = F.relu(conv(x, w, b, 1, pad, dil) + r)
+    pc = ops.PackedConv(w.to(DEV), b.to(DEV), None, stride=1, padding=pad,
+                        dilation=dil)
+    assert pc.wf_hi is not None
+    perm = (0, *range(2, 2 + dims), 1)
+    x_cl = x.permute(*perm).contiguous().to(DEV)
+    r_cl = r.permute(*perm).contiguous().to(DEV)
+    got = {}
+    for fold in (True, False):
+        old = ops.USE_FOLD
+        ops.USE_FOLD = fold
+        n0 = _lib.launch_count()
+        try:
+            got[fold] = ops.to_logical(ops.conv(x_cl, pc, 'relu', residual=r_cl)).cpu()
+        finally:
+            ops.USE_FOLD = old
+        assert _lib.launch_count() == n0 + 1
+    assert _rel(got[True], want) < 2e-5, _rel(got[True], want)
+    assert _rel(got[True], got[False]) < 2e-5
+    # the folded path really was the one taken
+    sp3 = (1,) * (3 - dims) + tuple(sp)
+    k3 = (1,) * (3 - dims) + (k,) * dims
+    p3 = (0,) * (3 - dims) + (pad,) * dims
+    d3 = (1,) * (3 - dims) + (dil,) * dims
+    d = ops.ConvDesc(n=n, d=sp3[0], h=sp3[1], w=sp3[2], cin=cin, in_ld=cin,
+                     od=sp3[0], oh=sp3[1], ow=sp3[2], cout=cout, out_ld=cout,
+                     res_ld=cout, w_ld=pc.w_ld, kd=k3[0], kh=k3[1], kw=k3[2],
+                     sd=1, sh=1, sw=1, pd=p3[0], ph=p3[1], pw=p3[2],
+                     dd=d3[0], dh=d3[1], dw=d3[2], act=0, act_channels=0)
+    import ctypes
+    assert _lib.lib().pw_conv_fold_supported(ctypes.byref(d)) == 1
 
 
 def test_conv_channel_slices_and_split_activation(conv_path):

@@ -7,6 +7,6 @@ timeout 1500 python -m pytest tests -m gpu -q --maxfail=40 -p no:cacheprovider -
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/smoke.log
-timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2>&1
+PW_BENCH_LAYERS=gpurun_out/layers.json timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1
 echo "bench exit $?" >> gpurun_out/bench.log
 tail -c 1500 gpurun_out/pytest_gpu.log; tail -c 600 gpurun_out/smoke.log; tail -c 3000 gpurun_out/bench.log

@@ -28,6 +28,9 @@ SMALL = [
     (3, 1, 224, 32, (4, 8, 8), 1, 1, 0, 1),
     (3, 1, 32, 16, (6, 10, 12), 3, 1, 1, 1),
     (3, 2, 128, 128, (4, 10, 10), 3, 1, 1, 1),
+    (2, 2, 64, 32, (19, 45), 3, 1, 2, 2),
+    (3, 1, 32, 16, (5, 9, 37), 3, 1, 1, 1),
+    (3, 1, 64, 80, (3, 11, 70), 3, 1, 1, 1),
 ]
 FULL = [
     (3, 1, 32, 32, (16, 200, 200), 3, 1, 1, 1),
@@ -49,7 +52,7 @@ FULL = [
 ]
 
 
-def run(case, check=True, reps=5):
+def run(case, check=True, reps=5, only=None):
     dims, n, cin, cout, sp, k, stride, pad, dil = case
     g = torch.Generator().manual_seed(1)
     x = torch.randn(n, cin, *sp, generator=g)
@@ -62,9 +65,13 @@ def run(case, check=True, reps=5):
     x_cl = x.permute(*perm).contiguous().cuda()
     flops = 2.0 * cin * k ** dims * cout
     res = {}
-    for name, umma, halo in (('simt', False, False), ('umma', True, False),
-                             ('halo', True, True)):
-        ops.USE_UMMA, ops.USE_HALO = umma, halo
+    for name, umma, halo, fold in (('simt', False, False, False),
+                                   ('umma', True, False, False),
+                                   ('halo', True, True, False),
+                                   ('fold', True, True, True)):
+        if only and name not in only:
+            continue
+        ops.USE_UMMA, ops.USE_HALO, ops.USE_FOLD = umma, halo, fold
         got = ops.conv(x_cl, pc)
         torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True)
@@ -89,14 +96,14 @@ def main():
     which = sys.argv[1] if len(sys.argv) > 1 else 'small'
     torch.manual_seed(0)
     if which == 'one':                       # ncu target: one FULL case
-        run(FULL[int(sys.argv[2])], check=False, reps=1)
+        run(FULL[int(sys.argv[2])], check=False, reps=1, only=('fold',))
         return
     if which in ('small', 'all'):
         for case in SMALL:
             run(case)
     if which in ('full', 'all'):
         for case in FULL:
-            run(case, check=len(sys.argv) > 2, reps=10)
+            run(case, check=len(sys.argv) > 2, reps=10, only=('halo', 'fold'))
 
 
 if __name__ == '__main__':
