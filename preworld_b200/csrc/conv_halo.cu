@@ -15,10 +15,20 @@
 //     Al*Bh a second one: 2 instructions per k-step instead of 3;
 //   * a CTA owns up to two 128-pixel M tiles that share every weight stage;
 //   * the epilogue transposes through (swizzled) smem so that global stores
-//     and residual loads are full 128-byte rows.
+//     and residual loads are full 128-byte rows;
+//   * CTAs are PERSISTENT (one per SM, tiles b, b + gridDim.x, ...): TMEM,
+//     barriers and tensor maps are set up once, every ring (halo slots, weight
+//     stages, A slots) runs on across tiles, so the next tile's halo and first
+//     weight stages load under the current tile's taps and epilogue; the MMA
+//     warp waits on acc_empty (all split warps done reading the accumulators)
+//     before it overwrites them.  -7..-22 % per launch against one tile per CTA;
+//   * optionally the kw taps along x are folded into the MMA's N dimension
+//     (HaloParams::fold, pw_conv_fold_fwd).
 //
 // Warp roles: 0 halo TMA, 1 weight TMA, 2 MMA issue + TMEM owner, 3..10 two
-// sets of four split/epilogue warps (warp%4 = TMEM lane quadrant).
+// sets of four split/epilogue warps (warp%4 = TMEM lane quadrant).  The
+// mbarrier protocol between them is model-checked on the CPU by
+// tools/halo_protocol_sim.py (tests/test_halo_protocol.py).
 //
 // Replaces the cuDNN convolutions of the reference path (mmdet ResNet,
 // necks/fpn.py, necks/view_transformer.py:473-638, backbones/resnet.py:88-184,
@@ -80,6 +90,14 @@ struct HaloParams {
   // per (ky, kz) instead of once per tap.  n_tile == fold * fold_n.
   int fold, fold_n, fold_shift;
   int out_bx;                  // valid outputs per x row group (== bx unless folded)
+  // Tile loop: CTA b runs tiles b, b + gridDim.x, ... (tile = spatial tile + sp_tiles *
+  // N slab).  One tile per CTA unless the plan is persistent: then TMEM, barriers and
+  // tensor maps are set up once, the rings run on across tiles (the halo and the first
+  // weight stages of the next tile load under the current tile's taps and epilogue),
+  // and the epilogue stages through its own shared-memory region (stage_off).
+  int total_tiles, sp_tiles, slabs;
+  int stage_off;               // byte offset of the epilogue staging (0: aliases the halo ring)
+  int stage_bytes;             // bytes reserved between the weight ring and the barriers
   int cps;                     // CTAs per SM the plan counts on (1 or 2)
   int dbg;                     // PW_HALO_DBG knock-out bits (timing experiments only)
   long long* ts;               // PW_HALO_TS: per-CTA clock64 milestones (debug)
@@ -112,8 +130,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int b_stage = 2 * p.n_tile * ROW_BYTES;
   uint8_t* b_ring = smem + p.halo_region;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.nb * b_stage);
-  // bars: halo_full[nh] halo_empty[nh] b_full[nb] empty[nb] a_full[nb*mt] accum
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.nb * b_stage + p.stage_bytes);
+  // bars: halo_full[nh] halo_empty[nh] b_full[nb] empty[nb] a_full[nb*mt] accum acc_empty
   // Ring entry r = (chunk,tap) % nb owns weight stage r and A slots r*mt + m; ONE
   // tcgen05.commit per entry frees both (a commit costs ~400 issue cycles).
   const uint32_t bar0 = smem_u32(bars);
@@ -121,7 +139,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
   const uint32_t b_full = halo_empty + 8 * p.nh, ring_empty = b_full + 8 * p.nb;
   const uint32_t a_full = ring_empty + 8 * p.nb;
   const uint32_t accum_bar = a_full + 8 * p.nb * p.mt;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * p.nh + p.nb * (2 + p.mt) + 1);
+  const uint32_t acc_empty = accum_bar + 8;      // epilogue done reading the accumulators
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * p.nh + p.nb * (2 + p.mt) + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -139,6 +158,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     }
     for (int s = 0; s < p.nb * p.mt; ++s) mbar_init(a_full + 8 * s, 4);   // four warps of a set
     mbar_init(accum_bar, 1);
+    mbar_init(acc_empty, 4 * SPLIT_SETS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_holder), (uint32_t)p.tmem_cols);
@@ -153,15 +173,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
   const uint32_t a_ring_col = (uint32_t)(p.mt * tile_cols);
 
   // ---- tile coordinates ------------------------------------------------------
-  int tt = blockIdx.x;
-  const int tx = tt % p.tiles_x; tt /= p.tiles_x;
-  const int ty = tt % p.tiles_y; tt /= p.tiles_y;
-  const int tz = tt % p.tiles_z;
-  const int img = tt / p.tiles_z;
-  const int x0 = tx * p.cbx, y0 = ty * p.cby, z0 = tz * p.cbz;
-  const int n0w = blockIdx.y * p.n_tile;                 // weight rows of this N slab
-  const int n_real = p.fold ? p.fold_n : p.n_tile;       // output channels of this N slab
-  const int n0 = blockIdx.y * n_real;
+  struct Tile { int x0, y0, z0, img, slab; };
+  auto decode = [&](int t) {
+    Tile tl;
+    tl.slab = t / p.sp_tiles;
+    int tt = t - tl.slab * p.sp_tiles;
+    const int tx = tt % p.tiles_x; tt /= p.tiles_x;
+    const int ty = tt % p.tiles_y; tt /= p.tiles_y;
+    const int tz = tt % p.tiles_z;
+    tl.img = tt / p.tiles_z;
+    tl.x0 = tx * p.cbx; tl.y0 = ty * p.cby; tl.z0 = tz * p.cbz;
+    return tl;
+  };
+  const int n_real = p.fold ? p.fold_n : p.n_tile;       // output channels of one N slab
   const int T = p.n_taps;
   const int total_ct = p.chunks * T;            // (chunk, tap) pairs
 
@@ -173,18 +197,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     // ===================== halo producer ======================================
     const bool leader = elect_one();
     const uint32_t bytes = (uint32_t)(p.hx * p.hy * p.hz) * ROW_BYTES;
-    const int cx = x0 * p.sw - p.pw, cy = y0 * p.sh - p.ph, cz = z0 * p.sd - p.pd;
     int s = 0;
     uint32_t ph = 1;
-    for (int c = 0; c < p.chunks; ++c) {
-      mbar_wait(halo_empty + 8 * s, ph);
-      if (leader) {
-        mbar_expect_tx(halo_full + 8 * s, bytes);
-        tma_load_5d(smem_u32(smem + (size_t)s * p.halo_stride), &map_a, halo_full + 8 * s,
-                    c * BLOCK_K, cx, cy, cz, img);
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const Tile tl = decode(t);
+      const int cx = tl.x0 * p.sw - p.pw, cy = tl.y0 * p.sh - p.ph, cz = tl.z0 * p.sd - p.pd;
+      for (int c = 0; c < p.chunks; ++c) {
+        mbar_wait(halo_empty + 8 * s, ph);
+        if (leader) {
+          mbar_expect_tx(halo_full + 8 * s, bytes);
+          tma_load_5d(smem_u32(smem + (size_t)s * p.halo_stride), &map_a, halo_full + 8 * s,
+                      c * BLOCK_K, cx, cy, cz, tl.img);
+        }
+        __syncwarp();
+        if (++s == p.nh) { s = 0; ph ^= 1; }
       }
-      __syncwarp();
-      if (++s == p.nh) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // ===================== weight producer ====================================
@@ -192,18 +219,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     const uint32_t b_ring_u32 = smem_u32(b_ring);
     int s = 0;
     uint32_t ph = 1;
-    for (int c = 0; c < p.chunks; ++c) {
-      for (int t = 0; t < T; ++t) {
-        mbar_wait(ring_empty + 8 * s, ph);
-        if (leader) {
-          mbar_expect_tx(b_full + 8 * s, (uint32_t)b_stage);
-          const uint32_t dst = b_ring_u32 + (uint32_t)(s * b_stage);
-          const int k0 = (t * p.chunks + c) * BLOCK_K;   // weights are tap-major in K
-          tma_load_2d(dst, &map_bh, b_full + 8 * s, k0, n0w);
-          tma_load_2d(dst + p.n_tile * ROW_BYTES, &map_bl, b_full + 8 * s, k0, n0w);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n0w = (tile / p.sp_tiles) * p.n_tile;    // weight rows of this N slab
+      for (int c = 0; c < p.chunks; ++c) {
+        for (int t = 0; t < T; ++t) {
+          mbar_wait(ring_empty + 8 * s, ph);
+          if (leader) {
+            mbar_expect_tx(b_full + 8 * s, (uint32_t)b_stage);
+            const uint32_t dst = b_ring_u32 + (uint32_t)(s * b_stage);
+            const int k0 = (t * p.chunks + c) * BLOCK_K; // weights are tap-major in K
+            tma_load_2d(dst, &map_bh, b_full + 8 * s, k0, n0w);
+            tma_load_2d(dst + p.n_tile * ROW_BYTES, &map_bl, b_full + 8 * s, k0, n0w);
+          }
+          __syncwarp();
+          if (++s == p.nb) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++s == p.nb) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 2) {
@@ -217,8 +247,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     const uint32_t acc_stride = (uint32_t)(2 * p.n_tile);
     int r = 0;
     uint32_t ph = 0;
-    uint32_t accumulate = 0;                                   // first k-steps overwrite
     long long cyc_b = 0, cyc_a = 0, cyc_i = 0, tq = 0;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+    if (iter > 0) {                                            // accumulators read out?
+      mbar_wait(acc_empty, (uint32_t)((iter - 1) & 1));
+      tc_fence_after();
+    }
+    uint32_t accumulate = 0;                                   // first k-steps overwrite
     for (int ct = 0; ct < total_ct; ++ct) {
       if (PW_TSON) tq = clock64();
       mbar_wait(b_full + 8 * r, ph);
@@ -253,6 +289,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     }
     if (leader) umma_commit(accum_bar);
     __syncwarp();
+    }
     if (PW_TSON && leader) {
       long long* t = p.ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
       t[6] = clock64(); t[12] = t[0] + cyc_b; t[13] = t[0] + cyc_a; t[14] = t[0] + cyc_i;
@@ -303,13 +340,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     // its load has been ISSUED -- i.e. after the previous occupant of the slot was
     // released by everybody -- or the arrival would land in the previous phase
     // and free the slot under a slower set: wait for its halo_full first.
+    int gc0 = 0;                                         // chunks of the tiles before this one
     auto release_chunk = [&](int ch) {
-      const int slot = ch % p.nh;
-      mbar_wait(halo_full + 8 * slot, (uint32_t)((ch / p.nh) & 1));
+      const int g = gc0 + ch;                            // the halo ring runs on across tiles
+      const int slot = g % p.nh;
+      mbar_wait(halo_full + 8 * slot, (uint32_t)((g / p.nh) & 1));
       __syncwarp();
       if (lane == 0) mbar_arrive(halo_empty + 8 * slot);
     };
     for (int q = 0; q < set / p.mt; ++q) step_tap();     // first tap of this set
+    // The (chunk, tap, M tile) sequence of a persistent CTA simply runs on across its
+    // tiles: a set whose stride overshoots a tile's end starts the next one mid-way.
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+    const Tile tl = decode(tile);
+    const int x0 = tl.x0, y0 = tl.y0, z0 = tl.z0, img = tl.img;
+    const int n0 = tl.slab * n_real;
     int released = 0;                                    // halo chunks this warp has released
     int pending = -1;                                    // A slot stored but not yet published
     long long sp_wait = 0, sp_busy = 0, sp_t0 = 0;       // PW_HALO_TS: cycles waiting / storing
@@ -404,8 +450,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       long long* t = p.ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
       t[15] = t[0] + sp_wait; t[4] = t[0] + sp_busy;
     }
-    const uint32_t stage = smem_base_u32 + (uint32_t)(sw_id * STAGE_BYTES_PER_WARP);
-    const int ncg = (n_real + 31) >> 5;
+    const uint32_t stage = smem_base_u32 + (uint32_t)(p.stage_off + sw_id * STAGE_BYTES_PER_WARP);
+    // an epilogue item = (M tile, group of cgw channels); the sets take items in turn.
+    // Folded launches use 16-channel groups so that both sets share the one M tile.
+    const int cgw = p.fold ? 16 : 32;
+    const int ncg = (n_real + cgw - 1) / cgw;
     const int items = p.mt * ncg;
     const int act_end = p.act_channels > 0 ? p.act_channels : p.cout;
     const bool vec_ok = ((p.out_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
@@ -436,9 +485,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     float4 rr[8];
     auto prefetch_res = [&](int item) {
       const int m = item / ncg;
-      const int cb = n0 + (item - m * ncg) * 32 + ch4 * 4;
-      const bool on = p.res != nullptr && vec_ok && cb + 4 <= p.cout &&
-                      (item - m * ncg) * 32 + ch4 * 4 < n_real;
+      const int cb = n0 + (item - m * ncg) * cgw + ch4 * 4;
+      const bool on = p.res != nullptr && vec_ok && cb + 4 <= p.cout && ch4 * 4 < cgw &&
+                      (item - m * ncg) * cgw + ch4 * 4 < n_real;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int pixi = m == 0 ? rowpix[0][i] : rowpix[1][i];
@@ -448,13 +497,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     };
     if (set < items) prefetch_res(set);
     if (sw_id == 0 && lane == 0) PW_TS(2);
-    mbar_wait(accum_bar, 0);
+    mbar_wait(accum_bar, (uint32_t)(iter & 1));
     tc_fence_after();
     if (sw_id == 0 && lane == 0) PW_TS(7);
     for (int item = set; item < items; item += SPLIT_SETS) {
       const int m = item / ncg;
-      const int col0 = (item - m * ncg) * 32;
-      const int ncol = min(32, n_real - col0);           // 16 or 32 (warp-uniform)
+      const int col0 = (item - m * ncg) * cgw;
+      const int ncol = min(cgw, n_real - col0);          // 16 or 32 (warp-uniform)
       if (item != set) prefetch_res(item);
       // phase 1: this thread's accumulator row (32 channels) -> its staging row
       for (int half = 0; half * 16 < ncol; ++half) {
@@ -467,7 +516,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
           for (int kx = 0; kx < p.fold; ++kx) {
             uint32_t a[16], b[16];
             const uint32_t taddr = tmem_base + lane_field +
-                                   (uint32_t)(m * tile_cols + kx * p.fold_n + half * 16);
+                                   (uint32_t)(m * tile_cols + kx * p.fold_n + col0 + half * 16);
             tmem_ld16_nowait(taddr, a);
             tmem_ld16_nowait(taddr + p.n_tile, b);
             tmem_ld_wait();
@@ -560,6 +609,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       }
       __syncwarp();
     }
+    // accumulators of this tile are read out: the MMA warp may start the next tile
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(acc_empty);
+    c -= p.chunks;                                       // position within the next tile
+    gc0 += p.chunks;
+    }
   }
 
   if (warp == FIRST_SPLIT_WARP && lane == 0) PW_TS(8);
@@ -591,6 +647,7 @@ struct HaloPlan {
 struct HaloKnobs {
   int nt = 0, nacc = 0, nb = 0, mt = 0, dbg = 0, sets = 0;
   int fold = -1;               // PW_HALO_FOLD=0: pw_conv_fold_supported() always says no
+  int persist = 1;             // PW_HALO_PERSIST=0: one tile per CTA (the pre-persistent launch)
   bool ts = false;
   HaloKnobs() {
     auto geti = [](const char* k) { const char* e = getenv(k); return e ? atoi(e) : 0; };
@@ -598,6 +655,7 @@ struct HaloKnobs {
     mt = geti("PW_HALO_MT"); dbg = geti("PW_HALO_DBG"); sets = geti("PW_HALO_SETS");
     ts = getenv("PW_HALO_TS") != nullptr;
     if (getenv("PW_HALO_FOLD")) fold = geti("PW_HALO_FOLD");
+    if (getenv("PW_HALO_PERSIST")) persist = geti("PW_HALO_PERSIST");
   }
 };
 const HaloKnobs& knobs() {
@@ -626,7 +684,22 @@ const HaloPlan& make_plan(const pw_conv_desc& in) {
 // Best plan for one kernel variant: `sets` split sets per CTA, the CTA limited to
 // `tmem_limit` TMEM columns and `smem_limit` bytes, `cps` CTAs resident per SM.
 HaloPlan search_plan(const pw_conv_desc& in, int sets, int tmem_limit, int smem_limit, int cps,
-                     int fold_n = 0);
+                     int fold_n, bool persist);
+
+// Persistent when that plan fits without giving up ring depth: the persistent CTA
+// needs a second halo slot even for a one-chunk conv plus its own 32 KB epilogue
+// staging; where that costs a weight stage or a halo slot (the stride-2 layers, whose
+// halo is 2x per axis) the one-tile-per-CTA plan stays the faster one (measured).
+HaloPlan pick_plan(const pw_conv_desc& in, int sets, int tmem_limit, int smem_limit, int cps,
+                   int fold_n) {
+  HaloPlan one_tile = search_plan(in, sets, tmem_limit, smem_limit, cps, fold_n, false);
+  if (knobs().persist != 1) return one_tile;
+  HaloPlan loop = search_plan(in, sets, tmem_limit, smem_limit, cps, fold_n, true);
+  if (!loop.ok) return one_tile;
+  if (!one_tile.ok) return loop;
+  if (loop.p.nb < one_tile.p.nb || loop.p.nh < one_tile.p.nh) return one_tile;
+  return loop;
+}
 
 // Plan of the x-tap-folded variant (pw_conv_fold_fwd), cached like make_plan.
 const HaloPlan& make_fold_plan(const pw_conv_desc& in, int fold_n) {
@@ -639,22 +712,33 @@ const HaloPlan& make_fold_plan(const pw_conv_desc& in, int fold_n) {
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(k);
   if (it == cache.end())
-    it = cache.emplace(k, search_plan(key, 2, 512, SMEM_LIMIT, 1, fold_n)).first;
+    it = cache.emplace(k, pick_plan(key, 2, 512, SMEM_LIMIT, 1, fold_n)).first;
   return it->second;
 }
 
 HaloPlan make_plan_uncached(const pw_conv_desc& in) {
-  HaloPlan one_cta = search_plan(in, 2, 512, SMEM_LIMIT, 1);
+  HaloPlan one_cta = pick_plan(in, 2, 512, SMEM_LIMIT, 1, 0);
   // The 1-set / 2-CTAs-per-SM variant is opt-in (PW_HALO_SETS=1): measured on the
   // path's layers it wins 7-9 % on two shapes (32->64 k333, 224->32 k111) and loses
   // up to 75 % where the 256-column TMEM share forces one M tile per CTA.
   if (knobs().sets != 1) return one_cta;
-  HaloPlan two_ctas = search_plan(in, 1, 256, SMEM_LIMIT_2CTA, 2);
+  HaloPlan two_ctas = pick_plan(in, 1, 256, SMEM_LIMIT_2CTA, 2, 0);
   return two_ctas.ok ? two_ctas : one_cta;
 }
 
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 HaloPlan search_plan(const pw_conv_desc& in, const int SPLIT_SETS, const int tmem_limit,
-                     const int smem_limit, const int cps, const int fold_n) {
+                     const int smem_limit, const int cps, const int fold_n, const bool persist) {
   HaloPlan plan;
   plan.sets = SPLIT_SETS;
   pw_conv_desc c = in;
@@ -730,11 +814,14 @@ HaloPlan search_plan(const pw_conv_desc& in, const int SPLIT_SETS, const int tme
           // ring its parity wait on ring_empty would alias a phase it never observed.
           if (T * chunks > nb && nb < (SPLIT_SETS + mt - 1) / mt) continue;
           if (knobs().mt && knobs().mt != mt) continue;
-          // halo ring
-          int nh = min(chunks, 2);
+          // halo ring; a persistent CTA keeps two slots even for a one-chunk conv (the
+          // next tile's halo loads under this tile) and stages its epilogue elsewhere
+          const int stage_bytes = 4 * SPLIT_SETS * STAGE_BYTES_PER_WARP;
+          int nh = persist ? 2 : min(chunks, 2);
           auto smem_need = [&](int nh_, int nb_) {
-            return (long long)max(nh_ * halo_stride, 4 * SPLIT_SETS * STAGE_BYTES_PER_WARP) +
-                   (long long)nb_ * b_stage + SMEM_SLACK;
+            const long long halo = persist ? (long long)nh_ * halo_stride + stage_bytes
+                                           : (long long)max(nh_ * halo_stride, stage_bytes);
+            return halo + (long long)nb_ * b_stage + SMEM_SLACK;
           };
           while (nb > max(2, (SPLIT_SETS + mt - 1) / mt) && smem_need(nh, nb) > smem_limit) --nb;
           // a multi-chunk conv needs two halo slots (load of chunk c+1 under the
@@ -776,7 +863,10 @@ HaloPlan search_plan(const pw_conv_desc& in, const int SPLIT_SETS, const int tme
             const int hstr[3] = {1, h[0], h[0] * h[1]};
             p.mt_halo_off = mt == 2 ? b[axis] * st[axis] * hstr[axis] : 0;
             p.halo_stride = halo_stride;
-            p.halo_region = max(nh * halo_stride, 4 * SPLIT_SETS * STAGE_BYTES_PER_WARP);
+            p.halo_region = persist ? nh * halo_stride : max(nh * halo_stride, stage_bytes);
+            p.stage_bytes = persist ? stage_bytes : 0;
+            p.stage_off = persist ? p.halo_region + nb * b_stage : 0;
+            p.total_tiles = (int)tiles; p.slabs = slabs; p.sp_tiles = (int)(tiles / slabs);
             p.fold = fold; p.fold_n = fold_n; p.fold_shift = c.dw;
             p.out_bx = fold ? cb[0] : b[0];
             p.tiles_x = pw_ceil_div(c.ow, cb[0]); p.tiles_y = pw_ceil_div(c.oh, cb[1]);
@@ -786,8 +876,8 @@ HaloPlan search_plan(const pw_conv_desc& in, const int SPLIT_SETS, const int tme
             while (pw2 < cols) pw2 <<= 1;
             p.tmem_cols = pw2;
             p.cps = cps;
-            plan.smem = (size_t)p.halo_region + (size_t)nb * b_stage + SMEM_SLACK;
-            plan.grid = dim3((unsigned)(tiles / slabs), (unsigned)slabs);
+            plan.smem = (size_t)p.halo_region + (size_t)nb * b_stage + p.stage_bytes + SMEM_SLACK;
+            plan.grid = dim3((unsigned)(persist ? min(tiles, (long long)sm_count() * cps) : tiles));
             plan.ok = true;
             plan.cost = cost;
           }

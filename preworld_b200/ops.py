@@ -191,11 +191,14 @@ USE_UMMA = True
 # ... and among the tensor-core kernels the halo-resident / TMEM-operand one
 # (conv_halo.cu) wherever its plan fits; False falls back to conv_umma.cu.
 USE_HALO = True
-# ... or its x-tap-folded variant (pw_conv_fold_fwd).  Off by default: with one
-# CTA per SM the folded kernel's smaller CTAs pay the prologue more often than
-# the shorter main loop saves (334 vs 309 us on the 32->32 volume layers inside
-# the step); PW_HALO_FOLD=1 or ops.USE_FOLD = True switches it on.
-USE_FOLD = os.environ.get('PW_HALO_FOLD') == '1'
+# ... or its x-tap-folded launch (pw_conv_fold_fwd) for stride-1 3-tap convs with
+# at most FOLD_AUTO_COUT output channels.  Measured inside the step (persistent
+# CTAs): 32->16 k333 (OccHead) 276 -> 207 us; 32->32 k333 with residual 289 -> 324 us
+# (its smaller CTAs pay the epilogue more often), wider layers re-split the halo
+# once per 32-channel slab and lose more -- hence 16.  PW_HALO_FOLD=0 switches it
+# off, PW_HALO_FOLD=1 folds every layer the library can (experiments).
+USE_FOLD = os.environ.get('PW_HALO_FOLD') != '0'
+FOLD_AUTO_COUT = 128 if os.environ.get('PW_HALO_FOLD') == '1' else 16
 FOLD_MAX_COUT = 128          # fold weights are packed up to this width
 
 
@@ -235,6 +238,7 @@ def conv(x, pc, act=None, residual=None, out=None, act_channels=0,
         assert residual.shape == out.shape
     L = _lib.lib()
     if USE_UMMA and USE_HALO and USE_FOLD and pc.wf_hi is not None and \
+            pc.cout <= FOLD_AUTO_COUT and \
             L.pw_conv_fold_supported(ctypes.byref(d)):
         check(L.pw_conv_fold_fwd(ctypes.byref(d), _ptr(x), _ptr(pc.wf_hi),
                                  _ptr(pc.wf_lo), _ptr(pc.scale), _ptr(pc.bias),

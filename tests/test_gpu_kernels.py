@@ -119,13 +119,13 @@ def test_conv_fold_matches_torch_and_halo(case):
     r_cl = r.permute(*perm).contiguous().to(DEV)
     got = {}
     for fold in (True, False):
-        old = ops.USE_FOLD
-        ops.USE_FOLD = fold
+        old = ops.USE_FOLD, ops.FOLD_AUTO_COUT
+        ops.USE_FOLD, ops.FOLD_AUTO_COUT = fold, 128     # (auto rule: cout <= 16)
         n0 = _lib.launch_count()
         try:
             got[fold] = ops.to_logical(ops.conv(x_cl, pc, 'relu', residual=r_cl)).cpu()
         finally:
-            ops.USE_FOLD = old
+            ops.USE_FOLD, ops.FOLD_AUTO_COUT = old
         assert _lib.launch_count() == n0 + 1
     assert _rel(got[True], want) < 2e-5, _rel(got[True], want)
     assert _rel(got[True], got[False]) < 2e-5

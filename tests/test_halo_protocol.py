@@ -25,6 +25,15 @@ def test_protocol_is_safe_for_every_planned_ring():
     assert not bad, bad
 
 
+def test_protocol_is_safe_for_persistent_ctas():
+    """Three tiles per CTA: rings run on across tiles, sets whose stride
+    overshoots a tile start the next one mid-way, the MMA warp waits for the
+    epilogue (acc_empty) before it overwrites the accumulators."""
+    cases, bad = sim.sweep(_shipped_sets(), n=2, seed=5, tiles=3)
+    assert cases > 500
+    assert not bad, bad
+
+
 def test_protocol_is_safe_with_more_split_sets():
     _, bad = sim.sweep((3, 4), n=2, seed=2)
     assert not bad, bad

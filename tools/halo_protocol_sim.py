@@ -11,7 +11,9 @@ counts, exactly in the order the kernel issues waits / arrives, and checks
     nothing is overwritten before its reader is done).
 
 It runs on the CPU in seconds and is how the "release a skipped chunk only after
-its load was issued" rule in the split warps was found and verified.
+its load was issued" rule in the split warps was found and verified, and how the
+persistent (several tiles per CTA) version of the protocol was checked before it
+first ran on a GPU.
 
     python tools/halo_protocol_sim.py [n_random_schedules]
 """
@@ -38,14 +40,19 @@ class Bar:
 
 
 class Sim:
-    def __init__(self, sets, mt, T, chunks, nh, nb, rng, fixed=True):
+    def __init__(self, sets, mt, T, chunks, nh, nb, rng, fixed=True, tiles=1):
         self.sets, self.mt, self.T, self.chunks, self.nh, self.nb = sets, mt, T, chunks, nh, nb
+        self.tiles = tiles                     # tiles one (persistent) CTA runs through
         self.rng, self.fixed = rng, fixed
         self.halo_full = [Bar(1, f'halo_full{i}') for i in range(nh)]
         self.halo_empty = [Bar(4 * sets, f'halo_empty{i}') for i in range(nh)]
         self.b_full = [Bar(1, f'b_full{i}') for i in range(nb)]
         self.ring_empty = [Bar(1, f'ring_empty{i}') for i in range(nb)]
         self.a_full = [Bar(4, f'a_full{i}') for i in range(nb * mt)]
+        self.accum = Bar(1, 'accum')
+        self.acc_empty = Bar(4 * sets, 'acc_empty')
+        self.acc_tile = None                   # tile whose sums sit in the accumulators
+        self.acc_readers = 0
         self.halo_slot = [None] * nh           # chunk resident in each halo slot
         self.halo_readers = [0] * nh
         self.b_slot = [None] * nb
@@ -56,7 +63,7 @@ class Sim:
     # every role is a generator yielding ('wait', bar, parity) or ('step',)
     def halo_producer(self):
         s, ph = 0, 1
-        for c in range(self.chunks):
+        for c in range(self.chunks * self.tiles):      # global chunk index
             yield ('wait', self.halo_empty[s], ph)
             def land(s=s, c=c):
                 assert self.halo_readers[s] == 0, f'halo slot {s} overwritten under a reader'
@@ -70,7 +77,7 @@ class Sim:
 
     def weight_producer(self):
         s, ph = 0, 1
-        for g in range(self.chunks * self.T):
+        for g in range(self.chunks * self.T * self.tiles):
             yield ('wait', self.ring_empty[s], ph)
             def land(s=s, g=g):
                 self.b_slot[s] = g
@@ -83,7 +90,14 @@ class Sim:
 
     def mma(self):
         r, ph = 0, 0
-        for g in range(self.chunks * self.T):
+        per_tile = self.chunks * self.T
+        for g in range(per_tile * self.tiles):
+            tile = g // per_tile
+            if g % per_tile == 0:
+                if tile > 0:
+                    yield ('wait', self.acc_empty, (tile - 1) & 1)
+                assert self.acc_readers == 0, 'accumulators overwritten under the epilogue'
+                self.acc_tile = ('partial', tile)
             yield ('wait', self.b_full[r], ph)
             assert self.b_slot[r] == g, f'weights of {g}: stage holds {self.b_slot[r]}'
             for m in range(self.mt):
@@ -93,6 +107,11 @@ class Sim:
             def retire(r=r):
                 self.ring_empty[r].arrive()
             self.commitq.append(retire)
+            if g % per_tile == per_tile - 1:
+                def done(tile=tile):
+                    self.acc_tile = tile
+                    self.accum.arrive()
+                self.commitq.append(done)
             yield ('step',)
             r += 1
             if r == self.nb:
@@ -102,6 +121,7 @@ class Sim:
     def split_warp(self, set_, quad):
         mt, T, nb, nh, chunks = self.mt, self.T, self.nb, self.nh, self.chunks
         st = dict(c=0, t=0, r=0, eph=1, hs=0, hph=0)
+        gc0 = 0                                # chunks of the tiles before this one
 
         def step_tap():
             st['r'] += 1
@@ -117,26 +137,18 @@ class Sim:
                 st['hs'], st['hph'] = 0, st['hph'] ^ 1
 
         def release(ch):
-            slot = ch % nh
+            g = gc0 + ch                       # the halo ring runs on across tiles
+            slot = g % nh
             if self.fixed:
-                yield ('wait', self.halo_full[slot], (ch // nh) & 1)
+                yield ('wait', self.halo_full[slot], (g // nh) & 1)
             self.halo_empty[slot].arrive()
 
-        m_cur = set_ % mt
-        for _ in range(set_ // mt):
-            step_tap()
-        released = 0
-        pending = None
-        if self.fixed:
-            while released < min(st['c'], chunks):
-                yield from release(released)
-                released += 1
         reading = None
 
         def begin_read():
             nonlocal reading
-            assert self.halo_slot[st['hs']] == st['c'], \
-                f"set {set_} reads chunk {st['c']}: slot holds {self.halo_slot[st['hs']]}"
+            assert self.halo_slot[st['hs']] == gc0 + st['c'], \
+                f"set {set_} reads chunk {gc0 + st['c']}: slot holds {self.halo_slot[st['hs']]}"
             reading = st['hs']
             self.halo_readers[reading] += 1
 
@@ -146,43 +158,66 @@ class Sim:
                 self.halo_readers[reading] -= 1
                 reading = None
 
-        if st['c'] < chunks:
-            yield ('wait', self.halo_full[st['hs']], st['hph'])
-            begin_read()
-            yield ('step',)
-            end_read()
-        while st['c'] < chunks:
-            g = st['c'] * T + st['t']
-            slot = st['r'] * mt + m_cur
-            ring_r, ring_ph = st['r'], st['eph']
-            yield ('step',)                       # hi/lo split
-            if pending is not None:
-                self.a_full[pending].arrive()
-            yield ('wait', self.ring_empty[ring_r], ring_ph)
-            self.a_slot[slot][quad] = (g, m_cur)
-            pending = slot
-            c_prev = st['c']
-            mm = m_cur + self.sets
-            taps = mm // mt
-            m_cur = mm - taps * mt
-            for _ in range(taps):
-                step_tap()
-            if st['c'] != c_prev:
-                upto = min(st['c'], chunks)
-                while released < upto:
+        m_cur = set_ % mt
+        for _ in range(set_ // mt):
+            step_tap()
+        items = mt                             # epilogue items of one tile (one column group)
+        for tile in range(self.tiles):
+            released = 0
+            pending = None
+            if self.fixed:
+                while released < min(st['c'], chunks):
                     yield from release(released)
                     released += 1
-                if st['c'] < chunks:
-                    yield ('wait', self.halo_full[st['hs']], st['hph'])
             if st['c'] < chunks:
+                yield ('wait', self.halo_full[st['hs']], st['hph'])
                 begin_read()
                 yield ('step',)
                 end_read()
-        if pending is not None:
-            self.a_full[pending].arrive()
-        while released < chunks:
-            yield from release(released)
-            released += 1
+            while st['c'] < chunks:
+                g = (gc0 + st['c']) * T + st['t']
+                slot = st['r'] * mt + m_cur
+                ring_r, ring_ph = st['r'], st['eph']
+                yield ('step',)                   # hi/lo split
+                if pending is not None:
+                    self.a_full[pending].arrive()
+                yield ('wait', self.ring_empty[ring_r], ring_ph)
+                self.a_slot[slot][quad] = (g, m_cur)
+                pending = slot
+                c_prev = st['c']
+                mm = m_cur + self.sets
+                taps = mm // mt
+                m_cur = mm - taps * mt
+                for _ in range(taps):
+                    step_tap()
+                if st['c'] != c_prev:
+                    upto = min(st['c'], chunks)
+                    while released < upto:
+                        yield from release(released)
+                        released += 1
+                    if st['c'] < chunks:
+                        yield ('wait', self.halo_full[st['hs']], st['hph'])
+                if st['c'] < chunks:
+                    begin_read()
+                    yield ('step',)
+                    end_read()
+            if pending is not None:
+                self.a_full[pending].arrive()
+            while released < chunks:
+                yield from release(released)
+                released += 1
+            # epilogue of this tile: EVERY split warp waits for the accumulators (a
+            # warp without an item must not run a tile ahead: its acc_empty arrival
+            # would land in the previous phase); sets with an item read them
+            yield ('wait', self.accum, tile & 1)
+            if set_ < items:
+                assert self.acc_tile == tile, f'epilogue of tile {tile} reads {self.acc_tile}'
+                self.acc_readers += 1
+                yield ('step',)
+                self.acc_readers -= 1
+            self.acc_empty.arrive()
+            st['c'] -= chunks
+            gc0 += chunks
 
     def run(self):
         roles = [self.halo_producer(), self.weight_producer(), self.mma()]
@@ -226,19 +261,19 @@ def planner_allows(sets, mt, T, chunks, nh, nb):
     return nh >= min(chunks, 2)
 
 
-def sweep(sets_list=(2, 3, 4), n=10, seed=0, fixed=True, only_allowed=True):
+def sweep(sets_list=(2, 3, 4), n=10, seed=0, fixed=True, only_allowed=True, tiles=1):
     """-> (schedules run, {config: first failure})."""
     rng = random.Random(seed)
     bad, cases = {}, 0
     for sets, mt, T, chunks, nb in itertools.product(sets_list, (1, 2), (1, 2, 9, 27),
                                                      (1, 2, 3, 5, 8), (2, 3, 4, 6)):
-        for nh in {min(chunks, 2), min(chunks, 3)}:
+        for nh in ({min(chunks, 2), min(chunks, 3)} if tiles == 1 else {2, 3}):
             if only_allowed and not planner_allows(sets, mt, T, chunks, nh, nb):
                 continue
             for _ in range(n):
                 cases += 1
                 try:
-                    Sim(sets, mt, T, chunks, nh, nb, rng, fixed=fixed).run()
+                    Sim(sets, mt, T, chunks, nh, nb, rng, fixed=fixed, tiles=tiles).run()
                 except AssertionError as e:
                     bad.setdefault((sets, mt, T, chunks, nh, nb), str(e)[:200])
     return cases, bad
