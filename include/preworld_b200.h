@@ -380,6 +380,31 @@ int pw_occ_confusion(const unsigned char* pred, const unsigned char* gt,
                      int free_idx, long long* hist, long long* occ_hist,
                      void* stream);
 
+/* ------------------------------------------------------------------------
+ * Voxel SSC training losses: CE_ssc_loss, sem_scal_loss,
+ * geo_scal_loss of mmdet3d/models/detectors/loss.py:20-113 as called from
+ * preworld.py:151-154 -- one pass over the logits instead of ~60.
+ * logits [n_vox, ld] channels-last (any voxel order, the same as target's),
+ * target / camera_mask uint8 [n_vox] (camera_mask may be NULL; it applies to
+ * the sem and geo terms only, as in the reference), class_weights [n_cls]
+ * (the reference appends a 0 for the empty class, preworld.py:150).
+ * pw_voxel_loss_stats fills stats[pw_voxel_loss_stats_size(n_cls)] (fp64 sums:
+ * CE numerator/denominator, mask count, per class sum p / sum p*hit / count,
+ * the five geo sums) and losses[3] = {ce, sem_scal, geo_scal} (unweighted).
+ * pw_voxel_loss_grad writes d(w_ce*ce + w_sem*sem + w_geo*geo)/dlogits from the
+ * same stats (closed form; the BCE clamp at log = -100 is not differentiated).
+ */
+int pw_voxel_loss_stats_size(int n_cls);
+int pw_voxel_loss_stats(const float* logits, int ld, const unsigned char* target,
+                        const unsigned char* camera_mask, long long n_vox, int n_cls,
+                        int ignore_index, int empty_idx, const float* class_weights,
+                        double* stats, float* losses, void* stream);
+int pw_voxel_loss_grad(const float* logits, int ld, const unsigned char* target,
+                       const unsigned char* camera_mask, long long n_vox, int n_cls,
+                       int ignore_index, int empty_idx, const float* class_weights,
+                       const double* stats, float w_ce, float w_sem, float w_geo,
+                       float* grad_logits, int grad_ld, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,102 @@
+"""TEST INFRASTRUCTURE -- CPU restatement of the reference's voxel SSC losses
+(mmdet3d/models/detectors/loss.py:20-113, called from preworld.py:133-155 and
+preworld_temporal_traj.py:176-203).  Only tests/ may import this module; the
+product path (preworld_b200/losses.py -> csrc/losses.cu) never does.
+
+Pinned: tests/test_oracle.py runs these functions against the reference's own
+loss.py (imported by path when /root/reference is present) and against the
+committed values in tests/golden/voxel_losses.json (oracle/make_loss_golden.py).
+
+The restatement is written from the sums the reference takes, not from its
+control flow: every term is a masked reduction over voxels, which is also how
+the CUDA kernel computes it (one pass over the logits instead of ~60)."""
+import torch
+import torch.nn.functional as F
+
+
+def _bce_to_one(x):
+    """F.binary_cross_entropy(x, ones) == -max(log x, -100)  (loss.py:61-76)."""
+    return -torch.clamp(torch.log(x), min=-100.0)
+
+
+def ce_ssc_loss(pred, target, class_weights, ignore_index=255):
+    """loss.py:20-30.  pred [B,C,H,W,D] logits, target [B,H,W,D] integer."""
+    logp = F.log_softmax(pred.float(), dim=1)
+    t = target.long()
+    valid = t != ignore_index
+    tt = torch.where(valid, t, torch.zeros_like(t))
+    w = class_weights.float()[tt] * valid
+    picked = logp.gather(1, tt.unsqueeze(1)).squeeze(1)
+    return -(w * picked).sum() / w.sum()
+
+
+def sem_scal_loss(pred, ssc_target, ignore_index=255, camera_mask=None):
+    """loss.py:33-80: per class present among the kept voxels, BCE-to-one of
+    precision, recall and specificity; mean over those classes."""
+    p = F.softmax(pred.float(), dim=1)
+    mask = ssc_target != ignore_index
+    if camera_mask is not None:
+        mask = torch.logical_and(mask, camera_mask.bool())
+    n_classes = p.shape[1]
+    t = ssc_target[mask]
+    loss, count = 0.0, 0.0
+    for i in range(n_classes):
+        pi = p[:, i][mask]
+        hit = (t == i).float()
+        cnt = hit.sum()
+        if cnt > 0:
+            count += 1.0
+            nom = (pi * hit).sum()
+            lc = 0.0
+            if pi.sum() > 0:
+                lc = lc + _bce_to_one(nom / pi.sum())
+            lc = lc + _bce_to_one(nom / cnt)
+            miss = 1.0 - hit
+            if miss.sum() > 0:
+                lc = lc + _bce_to_one(((1.0 - pi) * miss).sum() / miss.sum())
+            loss = loss + lc
+    return loss / count
+
+
+def geo_scal_loss(pred, ssc_target, ignore_index=255, non_empty_idx=0,
+                  camera_mask=None):
+    """loss.py:83-113.  NB: the "non-empty target" is target != non_empty_idx over
+    ALL voxels (ignore_index voxels count as non-empty), as in the reference."""
+    p = F.softmax(pred.float(), dim=1)
+    empty = p[:, non_empty_idx].reshape(-1)
+    nonempty = 1.0 - empty
+    mask = ssc_target != non_empty_idx
+    if camera_mask is not None:
+        mask = torch.logical_and(mask, camera_mask.bool())
+    tgt = mask.reshape(-1).float()
+    inter = (tgt * nonempty).sum()
+    precision = inter / nonempty.sum()
+    recall = inter / tgt.sum()
+    spec = ((1.0 - tgt) * empty).sum() / (1.0 - tgt).sum()
+    return _bce_to_one(precision) + _bce_to_one(recall) + _bce_to_one(spec)
+
+
+def loss_voxel(pred, target, class_weights, empty_idx, camera_mask=None,
+               w_ce=1.0, w_sem=1.0, w_geo=1.0):
+    """The three terms of preworld.py:151-154 (Lovasz, :155, is not restated)."""
+    cw = torch.cat([class_weights.float(), torch.zeros(1)])
+    return dict(
+        loss_voxel_ce=w_ce * ce_ssc_loss(pred, target, cw, 255),
+        loss_voxel_sem=w_sem * sem_scal_loss(pred, target, 255, camera_mask),
+        loss_voxel_geo=w_geo * geo_scal_loss(pred, target, 255, empty_idx, camera_mask))
+
+
+def seeded_case(seed=0, shape=(1, 18, 20, 20, 8), ignore_frac=0.1, empty_idx=17):
+    """Logits, a target that is mostly `empty_idx` with some 255s, a camera mask
+    and class weights -- the same tensors on every machine."""
+    g = torch.Generator().manual_seed(seed)
+    b, c, h, w, d = shape
+    pred = torch.randn(shape, generator=g) * 2.0
+    target = torch.randint(0, c, (b, h, w, d), generator=g)
+    target[torch.rand((b, h, w, d), generator=g) < 0.6] = empty_idx
+    target[torch.rand((b, h, w, d), generator=g) < ignore_frac] = 255
+    if seed % 2:                                   # a class that never occurs
+        target[target == 3] = 4
+    camera_mask = torch.rand((b, h, w, d), generator=g) < 0.7
+    class_weights = torch.rand(c - 1, generator=g) + 0.5
+    return pred, target, camera_mask, class_weights

@@ -1,0 +1,53 @@
+"""Generates tests/golden/voxel_losses.json by running the REFERENCE's own
+mmdet3d/models/detectors/loss.py (imported by path; it needs only torch) on the
+seeded cases of oracle/loss_ref.py.  Run in the build container:
+
+    python oracle/make_loss_golden.py [/root/reference]
+"""
+import importlib.util
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import loss_ref  # noqa: E402
+
+
+def load_reference(root):
+    path = os.path.join(root, 'mmdet3d', 'models', 'detectors', 'loss.py')
+    spec = importlib.util.spec_from_file_location('ref_loss', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def reference_values(ref, seed, use_mask):
+    pred, target, cam, cw = loss_ref.seeded_case(seed)
+    cwz = torch.cat([cw, torch.zeros(1)])
+    m = cam if use_mask else None
+    return dict(
+        ce=float(ref.CE_ssc_loss(pred, target, cwz, 255)),
+        sem=float(ref.sem_scal_loss(pred, target, 255, camera_mask=m)),
+        geo=float(ref.geo_scal_loss(pred, target, 255, non_empty_idx=17, camera_mask=m)))
+
+
+def main():
+    root = sys.argv[1] if len(sys.argv) > 1 else '/root/reference'
+    ref = load_reference(root)
+    out = {}
+    for seed in range(4):
+        for use_mask in (False, True):
+            out[f'seed{seed}_mask{int(use_mask)}'] = reference_values(ref, seed, use_mask)
+    path = os.path.join(ROOT, 'tests', 'golden', 'voxel_losses.json')
+    with open(path, 'w') as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print('wrote', path)
+    for k, v in out.items():
+        print(k, v)
+
+
+if __name__ == '__main__':
+    main()

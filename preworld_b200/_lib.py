@@ -104,6 +104,11 @@ SIGNATURES = {
     'pw_density_occ_zyx_to_xyz': [c_p, c_int, c_p, c_int, c_int, c_f, c_int,
                                   c_p, c_p, c_int, c_int, c_int, c_p],
     'pw_zyx_to_xyz': [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
+    'pw_voxel_loss_stats_size': [c_int],
+    'pw_voxel_loss_stats': [c_p, c_int, c_p, c_p, c_ll, c_int, c_int, c_int, c_p,
+                            c_p, c_p, c_p],
+    'pw_voxel_loss_grad': [c_p, c_int, c_p, c_p, c_ll, c_int, c_int, c_int, c_p,
+                           c_p, c_f, c_f, c_f, c_p, c_int, c_p],
     'pw_occ_confusion': [c_p, c_p, c_p, c_ll, c_int, c_int, c_p, c_p, c_p],
     'pw_raw2alpha': [c_p, c_f, c_f, c_ll, c_p, c_p, c_p],
     'pw_alpha2weight': [c_p, c_p, c_ll, c_int, c_p, c_p, c_p, c_p, c_p, c_p],

@@ -1,0 +1,111 @@
+"""Voxel SSC training losses on the device: the CE,
+semantic-scal and geometric-scal terms of the reference's ``loss_voxel``
+(mmdet3d/models/detectors/preworld.py:129-157, functions in
+mmdet3d/models/detectors/loss.py:20-113), computed by ONE pass of
+``csrc/losses.cu`` over the logits, with closed-form gradients from the same
+statistics (one more pass per term that is back-propagated).
+
+Same names, argument meaning and results as the reference functions; inputs are
+the reference's logical tensors (``pred`` [B,C,H,W,D] logits, ``target``
+[B,H,W,D] integer labels with 255 = ignore, ``camera_mask`` [B,H,W,D] bool).
+The Lovasz term (preworld.py:155) is not built yet.  CUDA only: there is no CPU
+fallback (the CPU restatement lives in ``oracle/loss_ref.py`` for the tests)."""
+import torch
+
+from . import ops
+
+_TERMS = ('ce', 'sem', 'geo')
+
+
+def _rows(pred):
+    """[B,C,*spatial] logits -> [V, C] rows (a view when pred is channels-last,
+    as the heads of this package produce it; one transposing copy otherwise)."""
+    d = pred.dim()
+    v = pred.permute(0, *range(2, d), 1)
+    if not v.is_contiguous():
+        v = v.contiguous()
+    return v.reshape(-1, pred.shape[1])
+
+
+def _labels(target):
+    t = target.reshape(-1)
+    return (t if t.dtype == torch.uint8 else t.to(torch.uint8)).contiguous()
+
+
+class _Term(torch.autograd.Function):
+    """One of the three losses as a differentiable scalar; the statistics were
+    computed once for all three."""
+
+    @staticmethod
+    def forward(ctx, rows, k, target, camera_mask, class_weights, empty_idx,
+                ignore_index, stats, losses):
+        ctx.k, ctx.empty_idx, ctx.ignore_index = k, empty_idx, ignore_index
+        ctx.save_for_backward(rows, target, class_weights, stats)
+        ctx.camera_mask = camera_mask
+        return losses[k].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        rows, target, class_weights, stats = ctx.saved_tensors
+        w = [0.0, 0.0, 0.0]
+        w[ctx.k] = 1.0
+        grad = ops.voxel_loss_grad(rows, target, ctx.camera_mask, class_weights,
+                                   ctx.empty_idx, stats, *w,
+                                   ignore_index=ctx.ignore_index)
+        return (grad * g,) + (None,) * 8
+
+
+def voxel_loss_terms(pred, target, class_weights, ignore_index=255,
+                     non_empty_idx=0, camera_mask=None):
+    """-> dict(ce=, sem=, geo=) of differentiable scalars: CE_ssc_loss(pred,
+    target, class_weights, ignore_index), sem_scal_loss(pred, target,
+    ignore_index, camera_mask) and geo_scal_loss(pred, target, ignore_index,
+    non_empty_idx, camera_mask) of loss.py:20-113 from one pass."""
+    if not pred.is_cuda:
+        raise RuntimeError('preworld_b200.losses needs CUDA tensors '
+                           '(there is no CPU fallback)')
+    rows = _rows(pred.float())
+    t = _labels(target)
+    cam = None if camera_mask is None else \
+        camera_mask.reshape(-1).to(torch.uint8).contiguous()
+    cw = class_weights.to(pred.device).float().contiguous()
+    stats, losses = ops.voxel_loss_stats(rows.detach(), t, cam, cw, non_empty_idx,
+                                         ignore_index)
+    return {name: _Term.apply(rows, k, t, cam, cw, non_empty_idx, ignore_index,
+                              stats, losses)
+            for k, name in enumerate(_TERMS)}
+
+
+def CE_ssc_loss(pred, target, class_weights, ignore_index):
+    """loss.py:20-30."""
+    return voxel_loss_terms(pred, target, class_weights, ignore_index)['ce']
+
+
+def sem_scal_loss(pred, ssc_target, ignore_index, camera_mask=None):
+    """loss.py:33-80."""
+    cw = torch.ones(pred.shape[1], device=pred.device)
+    return voxel_loss_terms(pred, ssc_target, cw, ignore_index,
+                            camera_mask=camera_mask)['sem']
+
+
+def geo_scal_loss(pred, ssc_target, ignore_index, non_empty_idx=0,
+                  camera_mask=None):
+    """loss.py:83-113."""
+    cw = torch.ones(pred.shape[1], device=pred.device)
+    return voxel_loss_terms(pred, ssc_target, cw, ignore_index, non_empty_idx,
+                            camera_mask)['geo']
+
+
+def loss_voxel(output_voxels, target_voxels, class_weights, empty_idx,
+               camera_mask=None, weight_voxel_ce=1.0, weight_voxel_sem_scal=1.0,
+               weight_voxel_geo_scal=1.0):
+    """PreWorld.loss_voxel (preworld.py:129-157) without its Lovasz term:
+    ``class_weights`` are the per-class weights WITHOUT the empty class (a zero
+    is appended, preworld.py:150)."""
+    cw = torch.cat([class_weights.to(output_voxels.device).float(),
+                    torch.zeros(1, device=output_voxels.device)])
+    t = voxel_loss_terms(output_voxels, target_voxels, cw, 255, empty_idx,
+                         camera_mask)
+    return dict(loss_voxel_ce=weight_voxel_ce * t['ce'],
+                loss_voxel_sem=weight_voxel_sem_scal * t['sem'],
+                loss_voxel_geo=weight_voxel_geo_scal * t['geo'])

@@ -720,3 +720,47 @@ def render_rays(desc, rays, t_vals, bda, density_cl, semantic_cl, color_cl):
         _ptr(o_s), _ptr(o_c), _ptr(o_l), _ptr(o_v), _stream()),
         'pw_render_rays')
     return o_d, o_s, o_c, o_l, o_v
+
+
+# ------------------------------------------------------------------ losses
+def voxel_loss_stats(rows, target, camera_mask, class_weights, empty_idx,
+                     ignore_index=255):
+    """rows [V, C] fp32 logits (row pitch = rows.stride(0)), target uint8 [V],
+    camera_mask uint8/bool [V] or None, class_weights fp32 [C].
+    -> (stats fp64 [8+3C], losses fp32 [3] = ce, sem_scal, geo_scal) -- one pass
+    over the logits (pw_voxel_loss_stats, csrc/losses.cu)."""
+    _require_cuda(rows, target, camera_mask, class_weights)
+    v, c = rows.shape
+    assert rows.dtype == torch.float32 and rows.stride(1) == 1
+    assert target.dtype == torch.uint8 and target.numel() == v and target.is_contiguous()
+    if camera_mask is not None:
+        camera_mask = camera_mask.reshape(-1).to(torch.uint8).contiguous()
+        assert camera_mask.numel() == v
+    cw = class_weights.float().contiguous()
+    assert cw.numel() == c
+    L = _lib.lib()
+    stats = torch.empty(L.pw_voxel_loss_stats_size(c), device=rows.device,
+                        dtype=torch.float64)
+    losses = torch.empty(3, device=rows.device, dtype=torch.float32)
+    check(L.pw_voxel_loss_stats(_ptr(rows), rows.stride(0), _ptr(target),
+                                _ptr(camera_mask), v, c, int(ignore_index),
+                                int(empty_idx), _ptr(cw), _ptr(stats),
+                                _ptr(losses), _stream()), 'pw_voxel_loss_stats')
+    return stats, losses
+
+
+def voxel_loss_grad(rows, target, camera_mask, class_weights, empty_idx, stats,
+                    w_ce, w_sem, w_geo, ignore_index=255):
+    """d(w_ce*ce + w_sem*sem + w_geo*geo)/d rows, fp32 [V, C] contiguous."""
+    _require_cuda(rows, target, camera_mask, class_weights, stats)
+    v, c = rows.shape
+    if camera_mask is not None:
+        camera_mask = camera_mask.reshape(-1).to(torch.uint8).contiguous()
+    cw = class_weights.float().contiguous()
+    grad = torch.empty((v, c), device=rows.device, dtype=torch.float32)
+    check(_lib.lib().pw_voxel_loss_grad(
+        _ptr(rows), rows.stride(0), _ptr(target), _ptr(camera_mask), v, c,
+        int(ignore_index), int(empty_idx), _ptr(cw), _ptr(stats), float(w_ce),
+        float(w_sem), float(w_geo), _ptr(grad), c, _stream()),
+        'pw_voxel_loss_grad')
+    return grad

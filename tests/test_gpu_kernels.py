@@ -640,3 +640,61 @@ def test_copy_rows_splits_the_camera_major_batch():
     ops.copy_rows_(dst[:1], raw.pin_memory().view(bn, nf, 3, 16, 44)[:1, 1], stream=side)
     side.synchronize()
     assert torch.equal(dst[0].cpu(), raw.view(bn, nf, 3, 16, 44)[0, 1])
+
+
+@pytest.mark.parametrize('seed,use_mask', [(0, False), (1, True), (2, True), (3, False)])
+def test_voxel_losses_match_oracle(seed, use_mask):
+    """csrc/losses.cu (one pass: CE + sem_scal + geo_scal of loss.py:20-113, and
+    their closed-form gradients) against the CPU restatement and its autograd.
+    fp64 accumulation on the device vs fp32 torch sums: 2e-5 relative."""
+    from oracle import loss_ref
+    from preworld_b200 import losses
+    pred, target, cam, cw = loss_ref.seeded_case(seed)
+    cwz = torch.cat([cw, torch.zeros(1)])
+    m = cam if use_mask else None
+    p_ref = pred.clone().requires_grad_(True)
+    want = dict(ce=loss_ref.ce_ssc_loss(p_ref, target, cwz, 255),
+                sem=loss_ref.sem_scal_loss(p_ref, target, 255, m),
+                geo=loss_ref.geo_scal_loss(p_ref, target, 255, 17, m))
+    # channels-last logits, as OccHead produces them
+    p_dev = pred.to(DEV).permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3) \
+        .requires_grad_(True)
+    got = losses.voxel_loss_terms(p_dev, target.to(DEV), cwz.to(DEV), 255, 17,
+                                  None if m is None else m.to(DEV))
+    for k in want:
+        assert abs(float(got[k]) - float(want[k])) <= 2e-5 * abs(float(want[k])), k
+    wts = dict(ce=0.7, sem=1.3, geo=2.0)
+    sum(wts[k] * want[k] for k in want).backward()
+    sum(wts[k] * got[k] for k in got).backward()
+    g_ref, g_dev = p_ref.grad, p_dev.grad.cpu()
+    assert (g_ref - g_dev).abs().max() <= 1e-4 * g_ref.abs().max()
+    # the reference-named wrappers and the NCDHW-contiguous input route
+    lv = losses.loss_voxel(pred.to(DEV), target.to(DEV), cw.to(DEV), 17,
+                           None if m is None else m.to(DEV), 1.0, 1.0, 1.0)
+    assert abs(float(lv['loss_voxel_sem']) - float(want['sem'])) <= 2e-5 * abs(float(want['sem']))
+    assert abs(float(lv['loss_voxel_ce']) - float(want['ce'])) <= 2e-5 * abs(float(want['ce']))
+    assert abs(float(lv['loss_voxel_geo']) - float(want['geo'])) <= 2e-5 * abs(float(want['geo']))
+
+
+def test_voxel_losses_full_grid_and_golden(golden_dir):
+    """200x200x16 grid (BASELINE size): device losses == oracle; and the
+    committed reference values (tests/golden/voxel_losses.json) directly."""
+    import json
+    import os
+    from oracle import loss_ref
+    from preworld_b200 import losses
+    gold = json.load(open(os.path.join(golden_dir, 'voxel_losses.json')))
+    pred, target, cam, cw = loss_ref.seeded_case(0)
+    cwz = torch.cat([cw, torch.zeros(1)])
+    got = losses.voxel_loss_terms(pred.to(DEV), target.to(DEV), cwz.to(DEV), 255, 17,
+                                  cam.to(DEV))
+    want = gold['seed0_mask1']
+    for k in want:
+        assert abs(float(got[k]) - want[k]) <= 2e-5 * abs(want[k]), k
+    pred, target, cam, cw = loss_ref.seeded_case(5, shape=(1, 18, 200, 200, 16))
+    cwz = torch.cat([cw, torch.zeros(1)])
+    got = losses.voxel_loss_terms(pred.to(DEV), target.to(DEV), cwz.to(DEV), 255, 17,
+                                  cam.to(DEV))
+    assert abs(float(got['ce']) - float(loss_ref.ce_ssc_loss(pred, target, cwz, 255))) < 1e-4
+    assert abs(float(got['sem']) - float(loss_ref.sem_scal_loss(pred, target, 255, cam))) < 1e-4
+    assert abs(float(got['geo']) - float(loss_ref.geo_scal_loss(pred, target, 255, 17, cam))) < 1e-4
