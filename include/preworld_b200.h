@@ -405,6 +405,24 @@ int pw_voxel_loss_grad(const float* logits, int ld, const unsigned char* target,
                        const double* stats, float w_ce, float w_sem, float w_geo,
                        float* grad_logits, int grad_ld, void* stream);
 
+/* LSSViewTransformerBEVDepth.get_depth_loss + get_downsampled_gt_depth
+ * (view_transformer.py:736-789, sid=False) fused: gt_depth [bn, H, W] lidar depth
+ * maps (0 = no return); depth_pred = the D depth probabilities per feature cell,
+ * addressed by element strides (image, bin, y, x) so any layout of [bn,D,h,w]
+ * works; labels int32 [bn*h*w] receives the bin label of each cell (-1 =
+ * background), sums[2] = {sum of BCE over foreground cells, foreground count},
+ * loss[0] = weight * sums[0] / max(1, sums[1]).  pw_depth_loss_grad writes
+ * d loss / d depth_pred as [bn*h*w, D] (torch's BCE backward formula). */
+int pw_depth_loss(const float* gt_depth, int bn, int H, int W, int downsample,
+                  const float* depth_pred, long long stride_img, long long stride_d,
+                  long long stride_y, long long stride_x, int D, float depth_min,
+                  float depth_step, float weight, int* labels, double* sums, float* loss,
+                  void* stream);
+int pw_depth_loss_grad(const int* labels, int bn, int h, int w, const float* depth_pred,
+                       long long stride_img, long long stride_d, long long stride_y,
+                       long long stride_x, int D, const double* sums, float weight,
+                       float* grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,3 +100,41 @@ def seeded_case(seed=0, shape=(1, 18, 20, 20, 8), ignore_frac=0.1, empty_idx=17)
     camera_mask = torch.rand((b, h, w, d), generator=g) < 0.7
     class_weights = torch.rand(c - 1, generator=g) + 0.5
     return pred, target, camera_mask, class_weights
+
+
+# ---- depth loss (view_transformer.py:736-789, sid=False) ----------------------
+def downsampled_gt_depth(gt_depths, downsample, depth_cfg, D):
+    """get_downsampled_gt_depth: [B,N,H,W] lidar depths (0 = none) -> one-hot
+    [B*N*h*w, D] float (all-zero rows = background)."""
+    B, N, H, W = gt_depths.shape
+    h, w = H // downsample, W // downsample
+    g = gt_depths.view(B * N, h, downsample, w, downsample).permute(0, 1, 3, 2, 4)
+    g = g.reshape(-1, downsample * downsample)
+    g = torch.where(g == 0.0, torch.full_like(g, 1e5), g).min(dim=-1).values
+    g = (g - (depth_cfg[0] - depth_cfg[2])) / depth_cfg[2]
+    g = torch.where((g < D + 1) & (g >= 0.0), g, torch.zeros_like(g))
+    return F.one_hot(g.long(), num_classes=D + 1)[:, 1:].float()
+
+
+def depth_loss(depth_labels, depth_preds, downsample, depth_cfg, D, weight):
+    """get_depth_loss: BCE of the D depth probabilities [B*N,D,h,w] against the
+    one-hot labels, over foreground cells, / max(1, #foreground)."""
+    labels = downsampled_gt_depth(depth_labels, downsample, depth_cfg, D)
+    preds = depth_preds.permute(0, 2, 3, 1).reshape(-1, D)
+    fg = labels.max(dim=1).values > 0.0
+    loss = F.binary_cross_entropy(preds[fg], labels[fg], reduction='none')
+    return weight * loss.sum() / max(1.0, float(fg.sum()))
+
+
+def seeded_depth_case(seed=0, bn=(1, 6), H=64, W=176, downsample=16, D=88):
+    """A sparse lidar depth map (most pixels 0, some cells entirely empty, some
+    depths beyond the last bin) and softmax depth predictions."""
+    g = torch.Generator().manual_seed(seed)
+    B, N = bn
+    gt = torch.rand((B, N, H, W), generator=g) * 60.0
+    gt[torch.rand((B, N, H, W), generator=g) < 0.97] = 0.0
+    gt[:, :, :downsample, :downsample * 2] = 0.0          # empty cells
+    gt[:, 0, -1, -1] = 0.3                                 # below the first bin
+    h, w = H // downsample, W // downsample
+    preds = torch.softmax(torch.randn((B * N, D, h, w), generator=g) * 2.0, dim=1)
+    return gt, preds

@@ -34,6 +34,26 @@ def reference_values(ref, seed, use_mask):
         geo=float(ref.geo_scal_loss(pred, target, 255, non_empty_idx=17, camera_mask=m)))
 
 
+DEPTH_CFG = [1.0, 45.0, 0.5]                 # bevstereo-occ.py grid_config['depth']
+
+
+def reference_depth_loss(seed):
+    """LSSViewTransformerBEVDepth.get_depth_loss of the reference file (loaded
+    under oracle/ref_shim.py) on oracle.loss_ref.seeded_depth_case(seed)."""
+    import types
+    from oracle import ref_shim
+    ref_shim.install()
+    cls = ref_shim.load('mmdet3d.models.necks.view_transformer').LSSViewTransformerBEVDepth
+    gt, preds = loss_ref.seeded_depth_case(seed)
+    me = types.SimpleNamespace(downsample=16, sid=False, D=88, loss_depth_weight=3.0,
+                               grid_config={'depth': DEPTH_CFG})
+    me.get_downsampled_gt_depth = lambda g: cls.get_downsampled_gt_depth(me, g)
+    labels = cls.get_downsampled_gt_depth(me, gt)
+    return dict(loss=float(cls.get_depth_loss(me, gt, preds)),
+                n_fg=int((labels.sum(1) > 0).sum()),
+                label_checksum=int((labels.argmax(1) * (labels.sum(1) > 0)).sum()))
+
+
 def main():
     root = sys.argv[1] if len(sys.argv) > 1 else '/root/reference'
     ref = load_reference(root)
@@ -41,6 +61,8 @@ def main():
     for seed in range(4):
         for use_mask in (False, True):
             out[f'seed{seed}_mask{int(use_mask)}'] = reference_values(ref, seed, use_mask)
+    for seed in range(3):
+        out[f'depth_seed{seed}'] = reference_depth_loss(seed)
     path = os.path.join(ROOT, 'tests', 'golden', 'voxel_losses.json')
     with open(path, 'w') as f:
         json.dump(out, f, indent=1, sort_keys=True)

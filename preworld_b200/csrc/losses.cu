@@ -321,3 +321,130 @@ PW_API int pw_voxel_loss_grad(const float* logits, int ld, const unsigned char* 
   PW_LAUNCH_CHECK(); pw_count_launch(1);
   return 0;
 }
+
+// ---- depth loss (view_transformer.py:736-789) -----------------------------------
+// get_downsampled_gt_depth + get_depth_loss fused: one warp per feature-map cell takes
+// the minimum non-zero lidar depth of its downsample x downsample patch, turns it into
+// a bin label, and (foreground cells only) sums the binary cross entropy of the D
+// depth probabilities against the one-hot label.
+namespace {
+
+__device__ __forceinline__ float bce_term(float p, bool one) {   // torch: log clamped at -100
+  const float l = one ? logf(p) : log1pf(-p);
+  return -fmaxf(l, -100.f);
+}
+
+__global__ void __launch_bounds__(256)
+depth_loss_kernel(const float* __restrict__ gt, int bn, int H, int W, int ds,
+                  const float* __restrict__ pred, long long s_img, long long s_d, long long s_y,
+                  long long s_x, int D, float c0, float c2, int* __restrict__ labels,
+                  double* __restrict__ sums) {
+  const int h = H / ds, w = W / ds;
+  const long long cells = (long long)bn * h * w;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+  double loss = 0.0, nfg = 0.0;
+  for (long long cell = warp0; cell < cells; cell += nwarp) {
+    const int x = (int)(cell % w);
+    const int y = (int)((cell / w) % h);
+    const long long img = cell / ((long long)w * h);
+    // minimum over the patch, zeros (no lidar return) count as 1e5
+    float mn = 1e5f;
+    const float* g0 = gt + (img * H + (long long)y * ds) * W + (long long)x * ds;
+    for (int i = lane; i < ds * ds; i += 32) {
+      const float v = __ldg(g0 + (long long)(i / ds) * W + (i % ds));
+      mn = fminf(mn, v == 0.f ? 1e5f : v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    const float bin = (mn - c0) / c2;                       // (d - (d0 - dstep)) / dstep
+    const float kept = (bin < (float)(D + 1) && bin >= 0.f) ? bin : 0.f;
+    const int label = (int)kept - 1;                        // .long(), one-hot class 0 dropped
+    if (lane == 0) labels[cell] = label;
+    if (label < 0) continue;                                // background cell
+    const float* p0 = pred + img * s_img + y * s_y + x * s_x;
+    float acc = 0.f;
+    for (int d = lane; d < D; d += 32) acc += bce_term(__ldg(p0 + d * s_d), d == label);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    loss += (double)acc;
+    nfg += 1.0;
+  }
+  if (lane == 0 && nfg > 0.0) {
+    atomicAdd(sums, loss);
+    atomicAdd(sums + 1, nfg);
+  }
+}
+
+__global__ void depth_loss_finalize_kernel(const double* __restrict__ sums, float weight,
+                                           float* __restrict__ loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    loss[0] = (float)(weight * sums[0] / (sums[1] > 1.0 ? sums[1] : 1.0));
+}
+
+// d loss / d pred = weight / max(1, n_fg) * (p - y) / max((1 - p) p, 1e-12)   (torch's BCE
+// backward), zero on background cells; grad is [cells, D] contiguous
+__global__ void __launch_bounds__(256)
+depth_loss_grad_kernel(const int* __restrict__ labels, long long cells, int h, int w,
+                       const float* __restrict__ pred, long long s_img, long long s_d,
+                       long long s_y, long long s_x, int D, const double* __restrict__ sums,
+                       float weight, float* __restrict__ grad) {
+  const float scale = (float)(weight / (sums[1] > 1.0 ? sums[1] : 1.0));
+  const long long total = cells * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long cell = i / D;
+    const int d = (int)(i - cell * D);
+    const int label = labels[cell];
+    float g = 0.f;
+    if (label >= 0) {
+      const int x = (int)(cell % w);
+      const int y = (int)((cell / w) % h);
+      const long long img = cell / ((long long)w * h);
+      const float p = __ldg(pred + img * s_img + y * s_y + x * s_x + d * s_d);
+      g = scale * (p - (d == label ? 1.f : 0.f)) / fmaxf((1.f - p) * p, 1e-12f);
+    }
+    grad[i] = g;
+  }
+}
+
+}  // namespace
+
+PW_API int pw_depth_loss(const float* gt_depth, int bn, int H, int W, int downsample,
+                         const float* depth_pred, long long stride_img, long long stride_d,
+                         long long stride_y, long long stride_x, int D, float depth_min,
+                         float depth_step, float weight, int* labels, double* sums, float* loss,
+                         void* stream) {
+  PW_REQUIRE(gt_depth && depth_pred && labels && sums && loss);
+  PW_REQUIRE(bn > 0 && downsample > 0 && H % downsample == 0 && W % downsample == 0 && D > 0);
+  PW_REQUIRE(depth_step > 0.f);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(sums, 0, 2 * sizeof(double), st);
+  if (e != cudaSuccess) return (int)e;
+  const long long cells = (long long)bn * (H / downsample) * (W / downsample);
+  const int blocks = (int)min((long long)148 * 4, (cells + 7) / 8);
+  // the reference subtracts the python double (d0 - dstep) from an fp32 tensor
+  const float c0 = (float)((double)depth_min - (double)depth_step);
+  depth_loss_kernel<<<blocks, 256, 0, st>>>(gt_depth, bn, H, W, downsample, depth_pred, stride_img,
+                                            stride_d, stride_y, stride_x, D, c0, depth_step,
+                                            labels, sums);
+  PW_LAUNCH_CHECK();
+  depth_loss_finalize_kernel<<<1, 32, 0, st>>>(sums, weight, loss);
+  PW_LAUNCH_CHECK(); pw_count_launch(2);
+  return 0;
+}
+
+PW_API int pw_depth_loss_grad(const int* labels, int bn, int h, int w, const float* depth_pred,
+                              long long stride_img, long long stride_d, long long stride_y,
+                              long long stride_x, int D, const double* sums, float weight,
+                              float* grad, void* stream) {
+  PW_REQUIRE(labels && depth_pred && sums && grad && bn > 0 && h > 0 && w > 0 && D > 0);
+  const long long cells = (long long)bn * h * w;
+  const int blocks = (int)min((long long)148 * 8, (cells * D + 255) / 256);
+  depth_loss_grad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      labels, cells, h, w, depth_pred, stride_img, stride_d, stride_y, stride_x, D, sums, weight,
+      grad);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}

@@ -109,3 +109,32 @@ def loss_voxel(output_voxels, target_voxels, class_weights, empty_idx,
     return dict(loss_voxel_ce=weight_voxel_ce * t['ce'],
                 loss_voxel_sem=weight_voxel_sem_scal * t['sem'],
                 loss_voxel_geo=weight_voxel_geo_scal * t['geo'])
+
+
+class _DepthLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth_preds, gt_depth, downsample, depth_min, depth_step, weight):
+        loss, labels, sums = ops.depth_loss(gt_depth, depth_preds, downsample,
+                                            depth_min, depth_step, weight)
+        ctx.save_for_backward(depth_preds, labels, sums)
+        ctx.weight = weight
+        return loss[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        depth_preds, labels, sums = ctx.saved_tensors
+        return (ops.depth_loss_grad(labels, depth_preds, sums, ctx.weight) * g,
+                None, None, None, None, None)
+
+
+def get_depth_loss(depth_labels, depth_preds, downsample, depth_cfg, loss_depth_weight):
+    """LSSViewTransformerBEVDepth.get_depth_loss (view_transformer.py:736-789,
+    sid=False): depth_labels [B,N,H,W] lidar depth maps, depth_preds [B*N,D,h,w]
+    depth probabilities, depth_cfg = grid_config['depth'] = (min, max, step)."""
+    if not depth_preds.is_cuda:
+        raise RuntimeError('preworld_b200.losses needs CUDA tensors '
+                           '(there is no CPU fallback)')
+    B, N, H, W = depth_labels.shape
+    return _DepthLoss.apply(depth_preds.float(), depth_labels.reshape(B * N, H, W),
+                            int(downsample), float(depth_cfg[0]), float(depth_cfg[2]),
+                            float(loss_depth_weight))

@@ -764,3 +764,41 @@ def voxel_loss_grad(rows, target, camera_mask, class_weights, empty_idx, stats,
         float(w_sem), float(w_geo), _ptr(grad), c, _stream()),
         'pw_voxel_loss_grad')
     return grad
+
+
+def _depth_strides(depth_preds):
+    """element strides (image, bin, y, x) of a logical [BN, D, h, w] tensor"""
+    assert depth_preds.dim() == 4 and depth_preds.dtype == torch.float32
+    return tuple(int(v) for v in depth_preds.stride())
+
+
+def depth_loss(gt_depth, depth_preds, downsample, depth_min, depth_step, weight):
+    """gt_depth [BN,H,W] fp32, depth_preds logical [BN,D,h,w] (any strides).
+    -> (loss fp32 [1], labels int32 [BN*h*w], sums fp64 [2])  (pw_depth_loss)."""
+    _require_cuda(gt_depth, depth_preds)
+    bn, H, W = gt_depth.shape
+    gt_depth = gt_depth.float().contiguous()
+    D = depth_preds.shape[1]
+    assert depth_preds.shape == (bn, D, H // downsample, W // downsample)
+    si, sd, sy, sx = _depth_strides(depth_preds)
+    cells = bn * (H // downsample) * (W // downsample)
+    labels = torch.empty(cells, device=gt_depth.device, dtype=torch.int32)
+    sums = torch.empty(2, device=gt_depth.device, dtype=torch.float64)
+    loss = torch.empty(1, device=gt_depth.device, dtype=torch.float32)
+    check(_lib.lib().pw_depth_loss(_ptr(gt_depth), bn, H, W, int(downsample),
+                                   _ptr(depth_preds), si, sd, sy, sx, D,
+                                   float(depth_min), float(depth_step), float(weight),
+                                   _ptr(labels), _ptr(sums), _ptr(loss), _stream()),
+          'pw_depth_loss')
+    return loss, labels, sums
+
+
+def depth_loss_grad(labels, depth_preds, sums, weight):
+    """-> d loss / d depth_preds as a logical [BN, D, h, w] tensor."""
+    bn, D, h, w = depth_preds.shape
+    si, sd, sy, sx = _depth_strides(depth_preds)
+    grad = torch.empty((bn * h * w, D), device=depth_preds.device, dtype=torch.float32)
+    check(_lib.lib().pw_depth_loss_grad(_ptr(labels), bn, h, w, _ptr(depth_preds),
+                                        si, sd, sy, sx, D, _ptr(sums), float(weight),
+                                        _ptr(grad), _stream()), 'pw_depth_loss_grad')
+    return grad.view(bn, h, w, D).permute(0, 3, 1, 2)

@@ -220,6 +220,31 @@ class LSSViewTransformerBEVStereo(BaseModule):
             .view(1, H_feat, 1).expand(self.D, H_feat, W_feat)
         return torch.stack((x, y, d), -1)
 
+    # -- training side ---------------------------------------
+    def get_depth_loss(self, depth_labels, depth_preds):
+        """view_transformer.py:774-789 (+ get_downsampled_gt_depth, :736-771):
+        one fused kernel (csrc/losses.cu) instead of ~20 tensor ops;
+        differentiable w.r.t. ``depth_preds``."""
+        from .. import losses
+        return losses.get_depth_loss(depth_labels, depth_preds, self.downsample,
+                                     self.grid_config['depth'],
+                                     self.loss_depth_weight)
+
+    def get_downsampled_gt_depth(self, gt_depths):
+        """view_transformer.py:736-771: [B,N,H,W] -> one-hot [B*N*h*w, D] float
+        (all-zero rows = background), from the bin labels the kernel computes."""
+        B, N, H, W = gt_depths.shape
+        dummy = torch.full((B * N, self.D, H // self.downsample,
+                            W // self.downsample), 0.5, device=gt_depths.device)
+        _, labels, _ = ops.depth_loss(gt_depths.reshape(B * N, H, W), dummy,
+                                      self.downsample, self.grid_config['depth'][0],
+                                      self.grid_config['depth'][2], 1.0)
+        lab = labels.long()
+        onehot = torch.zeros((lab.numel(), self.D), device=lab.device)
+        fg = lab >= 0
+        onehot[fg, lab[fg]] = 1.0
+        return onehot
+
     def get_mlp_input(self, sensor2ego, ego2global, intrin, post_rot,
                       post_tran, bda):
         """view_transformer.py:713-734 (pure indexing: 27 floats/camera)."""
