@@ -506,6 +506,34 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       const int ncol = min(cgw, n_real - col0);          // 16 or 32 (warp-uniform)
       if (item != set) prefetch_res(item);
       // phase 1: this thread's accumulator row (32 channels) -> its staging row
+      if (!p.fold && p.nacc == 1 && ncol == 32) {
+        // common case: all four TMEM loads of the item (main | corr, two halves) in
+        // flight under ONE wait -- a tcgen05.ld round trip is ~600 cycles here and the
+        // epilogue is half of a pointwise layer's tile time.  (Issuing the NEXT item's
+        // loads before this item's store phase was tried: the 64 loop-carried
+        // registers spill into the split loop, 2x slower.)
+        uint32_t a0[16], b0[16], a1[16], b1[16];
+        const uint32_t taddr = tmem_base + lane_field + (uint32_t)(m * tile_cols + col0);
+        tmem_ld16_nowait(taddr, a0);
+        tmem_ld16_nowait(taddr + p.n_tile, b0);
+        tmem_ld16_nowait(taddr + 16, a1);
+        tmem_ld16_nowait(taddr + 16 + p.n_tile, b1);
+        tmem_ld_wait();
+        if (item == set && sw_id == 0 && lane == 0) PW_TS(5);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          sts128(stage + (uint32_t)((lane * 8 + (j4 ^ (lane & 7))) << 4),
+                 make_float4(__uint_as_float(a0[j4 * 4]) + __uint_as_float(b0[j4 * 4]),
+                             __uint_as_float(a0[j4 * 4 + 1]) + __uint_as_float(b0[j4 * 4 + 1]),
+                             __uint_as_float(a0[j4 * 4 + 2]) + __uint_as_float(b0[j4 * 4 + 2]),
+                             __uint_as_float(a0[j4 * 4 + 3]) + __uint_as_float(b0[j4 * 4 + 3])));
+          sts128(stage + (uint32_t)((lane * 8 + ((4 + j4) ^ (lane & 7))) << 4),
+                 make_float4(__uint_as_float(a1[j4 * 4]) + __uint_as_float(b1[j4 * 4]),
+                             __uint_as_float(a1[j4 * 4 + 1]) + __uint_as_float(b1[j4 * 4 + 1]),
+                             __uint_as_float(a1[j4 * 4 + 2]) + __uint_as_float(b1[j4 * 4 + 2]),
+                             __uint_as_float(a1[j4 * 4 + 3]) + __uint_as_float(b1[j4 * 4 + 3])));
+        }
+      } else
       for (int half = 0; half * 16 < ncol; ++half) {
         float acc[16];
 #pragma unroll
