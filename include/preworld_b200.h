@@ -423,6 +423,25 @@ int pw_depth_loss_grad(const int* labels, int bn, int h, int w, const float* dep
                        long long stride_x, int D, const double* sums, float weight,
                        float* grad, void* stream);
 
+/* lovasz_softmax (mmdet3d/models/detectors/lovasz_softmax.py:157-239 with
+ * classes='present', per_image=False; preworld.py:155 passes ignore = the
+ * empty class and the camera mask).  x [n_vox, ld]: class probabilities
+ * (is_logits = 0, as the reference function takes them) or logits (is_logits =
+ * 1: softmax fused into the first pass).  Kept voxels: target != ignore_label
+ * [and camera_mask != 0].  Per class the errors |[t==c] - p_c| are sorted
+ * (cub::DeviceSegmentedRadixSort in the caller's workspace,
+ * pw_lovasz_workspace_bytes) and one CTA per present class forms lovasz_grad and
+ * the dot product in fp32.  loss[0] = mean over present classes; grad_probas
+ * (NULL or [n_vox, n_cls], every element written) = d loss / d probabilities.
+ * pw_softmax_backward turns that into d loss / d logits. */
+long long pw_lovasz_workspace_bytes(long long n_vox, int n_cls);
+int pw_lovasz_softmax(const float* x, int ld, int is_logits, const unsigned char* target,
+                      const unsigned char* camera_mask, long long n_vox, int n_cls,
+                      int ignore_label, void* workspace, long long workspace_bytes,
+                      float* loss, float* grad_probas, void* stream);
+int pw_softmax_backward(const float* logits, int ld, const float* grad_probas,
+                        long long n_vox, int n_cls, float* grad_logits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

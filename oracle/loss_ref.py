@@ -78,7 +78,7 @@ def geo_scal_loss(pred, ssc_target, ignore_index=255, non_empty_idx=0,
 
 def loss_voxel(pred, target, class_weights, empty_idx, camera_mask=None,
                w_ce=1.0, w_sem=1.0, w_geo=1.0):
-    """The three terms of preworld.py:151-154 (Lovasz, :155, is not restated)."""
+    """The first three terms of preworld.py:151-154 (Lovasz, :155: lovasz_softmax below)."""
     cw = torch.cat([class_weights.float(), torch.zeros(1)])
     return dict(
         loss_voxel_ce=w_ce * ce_ssc_loss(pred, target, cw, 255),
@@ -138,3 +138,37 @@ def seeded_depth_case(seed=0, bn=(1, 6), H=64, W=176, downsample=16, D=88):
     h, w = H // downsample, W // downsample
     preds = torch.softmax(torch.randn((B * N, D, h, w), generator=g) * 2.0, dim=1)
     return gt, preds
+
+
+# ---- Lovasz-Softmax (lovasz_softmax.py:20-33,157-239) ---------------------------
+def lovasz_grad(gt_sorted):
+    """lovasz_softmax.py:20-33: first difference of the Jaccard index along the
+    sorted order."""
+    gts = gt_sorted.sum()
+    inter = gts - gt_sorted.float().cumsum(0)
+    union = gts + (1 - gt_sorted).float().cumsum(0)
+    jac = 1.0 - inter / union
+    if len(gt_sorted) > 1:
+        jac = torch.cat([jac[:1], jac[1:] - jac[:-1]])
+    return jac
+
+
+def lovasz_softmax(probas, labels, ignore=None, camera_mask=None):
+    """lovasz_softmax(..., classes='present', per_image=False): probas
+    [B,C,H,W,D], labels [B,H,W,D]."""
+    C = probas.shape[1]
+    p = probas.permute(0, 2, 3, 4, 1).reshape(-1, C)
+    t = labels.reshape(-1)
+    valid = torch.ones_like(t, dtype=torch.bool) if ignore is None else t != ignore
+    if camera_mask is not None:
+        valid = valid & camera_mask.reshape(-1).bool()
+    p, t = p[valid], t[valid]
+    losses = []
+    for c in range(C):
+        fg = (t == c).float()
+        if fg.sum() == 0:
+            continue
+        errors = (fg - p[:, c]).abs()
+        errors_sorted, perm = torch.sort(errors, 0, descending=True)
+        losses.append(torch.dot(errors_sorted, lovasz_grad(fg[perm]).detach()))
+    return sum(losses) / len(losses)

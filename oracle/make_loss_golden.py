@@ -16,12 +16,16 @@ sys.path.insert(0, ROOT)
 from oracle import loss_ref  # noqa: E402
 
 
-def load_reference(root):
-    path = os.path.join(root, 'mmdet3d', 'models', 'detectors', 'loss.py')
-    spec = importlib.util.spec_from_file_location('ref_loss', path)
+def load_reference_file(root, name):
+    path = os.path.join(root, 'mmdet3d', 'models', 'detectors', name)
+    spec = importlib.util.spec_from_file_location('ref_' + name[:-3], path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_reference(root):
+    return load_reference_file(root, 'loss.py')
 
 
 def reference_values(ref, seed, use_mask):
@@ -63,6 +67,13 @@ def main():
             out[f'seed{seed}_mask{int(use_mask)}'] = reference_values(ref, seed, use_mask)
     for seed in range(3):
         out[f'depth_seed{seed}'] = reference_depth_loss(seed)
+    lov = load_reference_file(root, 'lovasz_softmax.py')
+    for seed in range(4):
+        for use_mask in (False, True):
+            pred, target, cam, _ = loss_ref.seeded_case(seed)
+            out[f'lovasz_seed{seed}_mask{int(use_mask)}'] = float(lov.lovasz_softmax(
+                torch.softmax(pred, dim=1), target, ignore=17,
+                camera_mask=cam if use_mask else None))
     path = os.path.join(ROOT, 'tests', 'golden', 'voxel_losses.json')
     with open(path, 'w') as f:
         json.dump(out, f, indent=1, sort_keys=True)

@@ -113,6 +113,10 @@ SIGNATURES = {
                       c_int, c_f, c_f, c_f, c_p, c_p, c_p, c_p],
     'pw_depth_loss_grad': [c_p, c_int, c_int, c_int, c_p, c_ll, c_ll, c_ll, c_ll,
                            c_int, c_p, c_f, c_p, c_p],
+    'pw_lovasz_workspace_bytes': [c_ll, c_int],
+    'pw_lovasz_softmax': [c_p, c_int, c_int, c_p, c_p, c_ll, c_int, c_int, c_p, c_ll,
+                          c_p, c_p, c_p],
+    'pw_softmax_backward': [c_p, c_int, c_p, c_ll, c_int, c_p, c_p],
     'pw_occ_confusion': [c_p, c_p, c_p, c_ll, c_int, c_int, c_p, c_p, c_p],
     'pw_raw2alpha': [c_p, c_f, c_f, c_ll, c_p, c_p, c_p],
     'pw_alpha2weight': [c_p, c_p, c_ll, c_int, c_p, c_p, c_p, c_p, c_p, c_p],
@@ -121,7 +125,8 @@ SIGNATURES = {
                        c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_p, c_p, c_p,
                        c_p, c_p],
 }
-_LONGLONG_RET = {'pw_launch_count', 'pw_lift_workspace_bytes'}
+_LONGLONG_RET = {'pw_launch_count', 'pw_lift_workspace_bytes',
+                 'pw_lovasz_workspace_bytes'}
 
 _lib = None
 

@@ -8,7 +8,7 @@ statistics (one more pass per term that is back-propagated).
 Same names, argument meaning and results as the reference functions; inputs are
 the reference's logical tensors (``pred`` [B,C,H,W,D] logits, ``target``
 [B,H,W,D] integer labels with 255 = ignore, ``camera_mask`` [B,H,W,D] bool).
-The Lovasz term (preworld.py:155) is not built yet.  CUDA only: there is no CPU
+The Lovasz term (preworld.py:155) is ``lovasz_softmax`` below.  CUDA only: there is no CPU
 fallback (the CPU restatement lives in ``oracle/loss_ref.py`` for the tests)."""
 import torch
 
@@ -98,17 +98,24 @@ def geo_scal_loss(pred, ssc_target, ignore_index, non_empty_idx=0,
 
 def loss_voxel(output_voxels, target_voxels, class_weights, empty_idx,
                camera_mask=None, weight_voxel_ce=1.0, weight_voxel_sem_scal=1.0,
-               weight_voxel_geo_scal=1.0):
-    """PreWorld.loss_voxel (preworld.py:129-157) without its Lovasz term:
+               weight_voxel_geo_scal=1.0, weight_voxel_lovasz=1.0):
+    """PreWorld.loss_voxel (preworld.py:129-157), all four terms
+    (``weight_voxel_lovasz=None`` leaves the Lovasz term out):
     ``class_weights`` are the per-class weights WITHOUT the empty class (a zero
     is appended, preworld.py:150)."""
     cw = torch.cat([class_weights.to(output_voxels.device).float(),
                     torch.zeros(1, device=output_voxels.device)])
     t = voxel_loss_terms(output_voxels, target_voxels, cw, 255, empty_idx,
                          camera_mask)
-    return dict(loss_voxel_ce=weight_voxel_ce * t['ce'],
-                loss_voxel_sem=weight_voxel_sem_scal * t['sem'],
-                loss_voxel_geo=weight_voxel_geo_scal * t['geo'])
+    out = dict(loss_voxel_ce=weight_voxel_ce * t['ce'],
+               loss_voxel_sem=weight_voxel_sem_scal * t['sem'],
+               loss_voxel_geo=weight_voxel_geo_scal * t['geo'])
+    if weight_voxel_lovasz is not None:
+        # preworld.py:155: lovasz_softmax(softmax(out), target, ignore=empty_idx, mask)
+        out['loss_voxel_lovasz'] = weight_voxel_lovasz * lovasz_softmax(
+            output_voxels, target_voxels, ignore=empty_idx, camera_mask=camera_mask,
+            from_logits=True)
+    return out
 
 
 class _DepthLoss(torch.autograd.Function):
@@ -138,3 +145,40 @@ def get_depth_loss(depth_labels, depth_preds, downsample, depth_cfg, loss_depth_
     return _DepthLoss.apply(depth_preds.float(), depth_labels.reshape(B * N, H, W),
                             int(downsample), float(depth_cfg[0]), float(depth_cfg[2]),
                             float(loss_depth_weight))
+
+
+class _Lovasz(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rows, is_logits, target, camera_mask, ignore_label):
+        loss, gp = ops.lovasz_softmax_rows(rows, is_logits, target, camera_mask,
+                                           ignore_label, want_grad=True)
+        ctx.is_logits = is_logits
+        ctx.save_for_backward(rows, gp)
+        return loss[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        rows, gp = ctx.saved_tensors
+        grad = ops.softmax_backward(rows, gp) if ctx.is_logits else gp
+        return grad * g, None, None, None, None
+
+
+def lovasz_softmax(probas, labels, classes='present', per_image=False,
+                   ignore=None, camera_mask=None, from_logits=False):
+    """lovasz_softmax.py:157-175 for the configuration the path uses
+    (classes='present', per_image=False): ``probas`` [B,C,H,W,D] class
+    probabilities, ``labels`` [B,H,W,D]; voxels with label == ``ignore`` (and
+    outside ``camera_mask``) are dropped.  ``from_logits=True`` takes logits and
+    fuses the softmax (what ``loss_voxel`` uses)."""
+    if classes != 'present' or per_image:
+        raise NotImplementedError('lovasz_softmax: only classes="present", '
+                                  'per_image=False (preworld.py:155)')
+    if not probas.is_cuda:
+        raise RuntimeError('preworld_b200.losses needs CUDA tensors '
+                           '(there is no CPU fallback)')
+    rows = _rows(probas.float())
+    t = _labels(labels)
+    cam = None if camera_mask is None else \
+        camera_mask.reshape(-1).to(torch.uint8).contiguous()
+    ign = -1 if ignore is None else int(ignore)
+    return _Lovasz.apply(rows, bool(from_logits), t, cam, ign)

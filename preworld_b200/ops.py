@@ -802,3 +802,37 @@ def depth_loss_grad(labels, depth_preds, sums, weight):
                                         si, sd, sy, sx, D, _ptr(sums), float(weight),
                                         _ptr(grad), _stream()), 'pw_depth_loss_grad')
     return grad.view(bn, h, w, D).permute(0, 3, 1, 2)
+
+
+def lovasz_softmax_rows(rows, is_logits, target, camera_mask, ignore_label,
+                        want_grad=True):
+    """rows [V, C] fp32 probabilities (or logits), target uint8 [V], camera_mask
+    uint8 [V] or None.  -> (loss fp32 [1], d loss / d probabilities [V, C] or
+    None)  (pw_lovasz_softmax: keys, segmented sort, per-class scan)."""
+    _require_cuda(rows, target, camera_mask)
+    v, c = rows.shape
+    assert rows.dtype == torch.float32 and rows.stride(1) == 1
+    assert target.dtype == torch.uint8 and target.numel() == v
+    L = _lib.lib()
+    nbytes = L.pw_lovasz_workspace_bytes(v, c)
+    if nbytes < 0:
+        raise ValueError(f'lovasz_softmax: unsupported size {v} x {c}')
+    ws = torch.empty(nbytes, device=rows.device, dtype=torch.uint8)
+    loss = torch.empty(1, device=rows.device, dtype=torch.float32)
+    gp = torch.empty((v, c), device=rows.device, dtype=torch.float32) \
+        if want_grad else None
+    check(L.pw_lovasz_softmax(_ptr(rows), rows.stride(0), int(bool(is_logits)),
+                              _ptr(target), _ptr(camera_mask), v, c,
+                              int(ignore_label), _ptr(ws), nbytes, _ptr(loss),
+                              _ptr(gp), _stream()), 'pw_lovasz_softmax')
+    return loss, gp
+
+
+def softmax_backward(rows_logits, grad_probas):
+    """d L / d logits [V, C] from d L / d softmax(logits)."""
+    v, c = rows_logits.shape
+    gl = torch.empty((v, c), device=rows_logits.device, dtype=torch.float32)
+    check(_lib.lib().pw_softmax_backward(_ptr(rows_logits), rows_logits.stride(0),
+                                         _ptr(grad_probas), v, c, _ptr(gl),
+                                         _stream()), 'pw_softmax_backward')
+    return gl

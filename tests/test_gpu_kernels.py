@@ -732,3 +732,50 @@ def test_depth_loss_matches_oracle(seed, golden_dir):
     lab_ref = torch.where(want_lab.sum(1) > 0, want_lab.argmax(1), torch.full((1,), -1))
     assert torch.equal(labels.cpu().long(), lab_ref)
     assert int(sums[1].item()) == gold['n_fg']
+
+
+@pytest.mark.parametrize('seed,use_mask', [(0, True), (1, False), (2, True)])
+def test_lovasz_softmax_matches_oracle(seed, use_mask, golden_dir):
+    """pw_lovasz_softmax (keys -> segmented sort -> per-class Jaccard scan) against
+    the CPU restatement of lovasz_softmax.py:157-239 and the reference's own
+    values; gradient w.r.t. the logits against autograd (random data: no ties)."""
+    import json
+    import os
+    from oracle import loss_ref
+    from preworld_b200 import losses
+    gold = json.load(open(os.path.join(golden_dir, 'voxel_losses.json')))
+    pred, target, cam, cw = loss_ref.seeded_case(seed)
+    m = cam if use_mask else None
+    p_ref = pred.clone().requires_grad_(True)
+    want = loss_ref.lovasz_softmax(torch.softmax(p_ref, 1), target, 17, m)
+    want.backward()
+    md = None if m is None else m.to(DEV)
+    # (a) logits in, fused softmax
+    p_dev = pred.to(DEV).requires_grad_(True)
+    got = losses.lovasz_softmax(p_dev, target.to(DEV), ignore=17, camera_mask=md,
+                                from_logits=True)
+    assert abs(float(got) - float(want)) <= 1e-5 * float(want)
+    assert abs(float(got) - gold[f'lovasz_seed{seed}_mask{int(use_mask)}']) <= 1e-5 * float(want)
+    got.backward()
+    assert (p_dev.grad.cpu() - p_ref.grad).abs().max() <= 1e-4 * p_ref.grad.abs().max()
+    # (b) probabilities in, as the reference function is called (preworld.py:155)
+    p2 = pred.to(DEV).requires_grad_(True)
+    got2 = losses.lovasz_softmax(torch.softmax(p2, 1), target.to(DEV), ignore=17,
+                                 camera_mask=md)
+    assert abs(float(got2) - float(want)) <= 1e-5 * float(want)
+    got2.backward()
+    assert (p2.grad.cpu() - p_ref.grad).abs().max() <= 1e-4 * p_ref.grad.abs().max()
+    # all four terms through loss_voxel
+    lv = losses.loss_voxel(pred.to(DEV), target.to(DEV), cw.to(DEV), 17, md)
+    assert abs(float(lv['loss_voxel_lovasz']) - float(want)) <= 1e-5 * float(want)
+
+
+def test_lovasz_softmax_full_grid():
+    """200x200x16x18 (BASELINE grid): same value as the CPU restatement."""
+    from oracle import loss_ref
+    from preworld_b200 import losses
+    pred, target, cam, _ = loss_ref.seeded_case(5, shape=(1, 18, 200, 200, 16))
+    want = loss_ref.lovasz_softmax(torch.softmax(pred, 1), target, 17, cam)
+    got = losses.lovasz_softmax(pred.to(DEV), target.to(DEV), ignore=17,
+                                camera_mask=cam.to(DEV), from_logits=True)
+    assert abs(float(got) - float(want)) <= 2e-5 * float(want)

@@ -40,7 +40,11 @@ def main():
     by_g = v * (18 * 8 + 2)
     print(f'stats {us_s:.1f} us  {by_s / us_s / 1e3:.0f} GB/s   grad {us_g:.1f} us  '
           f'{by_g / us_g / 1e3:.0f} GB/s')
+    us_l = timed(lambda: ops.lovasz_softmax_rows(rows, True, t, c, 17), reps=10)
+    print(f'lovasz (keys + segmented sort + scan, with gradient) {us_l:.0f} us')
     pd, td, cd = pred.cuda(), target.cuda(), cam.cuda()
+    us_lt = timed(lambda: loss_ref.lovasz_softmax(torch.softmax(pd, 1), td, 17, cd), reps=3)
+    print(f'lovasz, reference formulation in torch on the same GPU (forward only): {us_lt:.0f} us')
     us_t = timed(lambda: (loss_ref.ce_ssc_loss(pd, td, cwz, 255),
                           loss_ref.sem_scal_loss(pd, td, 255, cd),
                           loss_ref.geo_scal_loss(pd, td, 255, 17, cd)), reps=3)
