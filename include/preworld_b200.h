@@ -429,7 +429,7 @@ int pw_depth_loss_grad(const int* labels, int bn, int h, int w, const float* dep
  * (is_logits = 0, as the reference function takes them) or logits (is_logits =
  * 1: softmax fused into the first pass).  Kept voxels: target != ignore_label
  * [and camera_mask != 0].  Per class the errors |[t==c] - p_c| are sorted
- * (cub::DeviceSegmentedRadixSort in the caller's workspace,
+ * (one cub::DeviceRadixSort of (class, error) keys in the caller's workspace,
  * pw_lovasz_workspace_bytes) and one CTA per present class forms lovasz_grad and
  * the dot product in fp32.  loss[0] = mean over present classes; grad_probas
  * (NULL or [n_vox, n_cls], every element written) = d loss / d probabilities.

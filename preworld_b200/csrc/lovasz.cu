@@ -8,8 +8,9 @@
 //      key, (voxel index | fg bit) its value; voxels that flatten_probas drops
 //      (label == ignore, camera mask off) get key -1 and sort behind every kept voxel.
 //      Counts: kept voxels P, foreground G_c per class.
-//   2. cub::DeviceSegmentedRadixSort (library sort, like the reference's torch.sort):
-//      C segments, descending.
+//   2. cub::DeviceRadixSort (library sort, like the reference's torch.sort): ONE sort of
+//      64-bit keys (class << 32 | ~error bits), 37 significant bits -- the segmented
+//      variant runs one CTA per segment and took 5 ms for 18 x 640 k.
 //   3. lovasz_scan_kernel: one CTA per present class walks its sorted segment with a
 //      running foreground count -- Jaccard index, its first difference (lovasz_grad) and
 //      the dot product with the sorted errors, all in fp32 like the reference; writes
@@ -30,11 +31,13 @@ struct LvLayout {          // carve-up of the caller's workspace
   size_t keys_in, keys_out, vals_in, vals_out, offsets, counts, cub_temp, cub_bytes, total;
 };
 
+constexpr int KEY_BITS = 32 + 5;       // error bits + class id (n_cls <= 32)
+
 size_t cub_temp_bytes(long long n_vox, int n_cls) {
   size_t bytes = 0;
-  cub::DeviceSegmentedRadixSort::SortPairsDescending(
-      nullptr, bytes, (const float*)nullptr, (float*)nullptr, (const unsigned*)nullptr,
-      (unsigned*)nullptr, (int)(n_vox * n_cls), n_cls, (const int*)nullptr, (const int*)nullptr);
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr,
+                                  (unsigned long long*)nullptr, (const unsigned*)nullptr,
+                                  (unsigned*)nullptr, (int)(n_vox * n_cls), 0, KEY_BITS);
   return bytes;
 }
 
@@ -43,8 +46,8 @@ LvLayout lv_layout(long long n_vox, int n_cls) {
   LvLayout L;
   const size_t kv = up((size_t)n_vox * n_cls * 4);
   size_t o = 0;
-  L.keys_in = o; o += kv;
-  L.keys_out = o; o += kv;
+  L.keys_in = o; o += 2 * kv;          // 64-bit keys
+  L.keys_out = o; o += 2 * kv;
   L.vals_in = o; o += kv;
   L.vals_out = o; o += kv;
   L.offsets = o; o += up((size_t)(n_cls + 1) * 4);
@@ -60,7 +63,7 @@ template <int C_MAX>
 __global__ void __launch_bounds__(LV_TPB)
 lovasz_keys_kernel(const float* __restrict__ x, int ld, int is_logits,
                    const unsigned char* __restrict__ target, const unsigned char* __restrict__ cam,
-                   long long n, int C, int ignore_label, float* __restrict__ keys,
+                   long long n, int C, int ignore_label, unsigned long long* __restrict__ keys,
                    unsigned* __restrict__ vals, unsigned long long* __restrict__ counts) {
   __shared__ unsigned s_cnt[C_MAX + 1];
   for (int i = threadIdx.x; i <= C; i += blockDim.x) s_cnt[i] = 0;
@@ -92,7 +95,10 @@ lovasz_keys_kernel(const float* __restrict__ x, int ld, int is_logits,
     for (int c = 0; c < C_MAX; ++c)
       if (c < C) {
         const bool fg = t == c;
-        keys[(long long)c * n + v] = kept ? fabsf((fg ? 1.f : 0.f) - p[c]) : -1.f;
+        // ascending key order == class by class, errors descending, dropped voxels last
+        // (errors are >= 0, so their bit patterns are monotone)
+        const unsigned eb = kept ? ~__float_as_uint(fabsf((fg ? 1.f : 0.f) - p[c])) : 0xFFFFFFFFu;
+        keys[(long long)c * n + v] = ((unsigned long long)c << 32) | eb;
         vals[(long long)c * n + v] = (unsigned)v | ((kept && fg) ? FG_BIT : 0u);
       }
   }
@@ -107,7 +113,7 @@ __global__ void lovasz_offsets_kernel(int* __restrict__ offsets, long long n, in
 
 // One CTA per class.  out[0] += loss_c / #present; grad_p (optional) [n, C].
 __global__ void __launch_bounds__(1024)
-lovasz_scan_kernel(const float* __restrict__ keys, const unsigned* __restrict__ vals, long long n,
+lovasz_scan_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ vals, long long n,
                    int C, const unsigned long long* __restrict__ counts,
                    const float* __restrict__ x_unused, double* __restrict__ loss_acc,
                    float* __restrict__ grad_p) {
@@ -118,7 +124,7 @@ lovasz_scan_kernel(const float* __restrict__ keys, const unsigned* __restrict__ 
   for (int k = 0; k < C; ++k) present += counts[1 + k] > 0 ? 1 : 0;
   const bool active = counts[1 + c] > 0 && present > 0;
   const float inv_present = present > 0 ? 1.f / (float)present : 0.f;
-  const float* kc = keys + (long long)c * n;
+  const unsigned long long* kc = keys + (long long)c * n;
   const unsigned* vc = vals + (long long)c * n;
   __shared__ float s_warp[32];
   __shared__ float s_carry;       // foreground count before this chunk (exact in fp32: < 2^24)
@@ -131,7 +137,7 @@ lovasz_scan_kernel(const float* __restrict__ keys, const unsigned* __restrict__ 
     const long long i = base + threadIdx.x;
     const bool in = i < n;
     const unsigned val = in ? vc[i] : 0u;
-    const float err = in ? kc[i] : -1.f;
+    const float err = in ? __uint_as_float(~(unsigned)kc[i]) : 0.f;   // (dropped: beyond P)
     const float fg = (val & FG_BIT) ? 1.f : 0.f;
     // inclusive scan of fg over the chunk
     float sc = fg;
@@ -235,8 +241,8 @@ PW_API int pw_lovasz_softmax(const float* x, int ld, int is_logits, const unsign
   const LvLayout L = lv_layout(n_vox, n_cls);
   PW_REQUIRE(workspace_bytes >= (long long)L.total);
   char* ws = (char*)workspace;
-  float* keys_in = (float*)(ws + L.keys_in);
-  float* keys_out = (float*)(ws + L.keys_out);
+  unsigned long long* keys_in = (unsigned long long*)(ws + L.keys_in);
+  unsigned long long* keys_out = (unsigned long long*)(ws + L.keys_out);
   unsigned* vals_in = (unsigned*)(ws + L.vals_in);
   unsigned* vals_out = (unsigned*)(ws + L.vals_out);
   int* offsets = (int*)(ws + L.offsets);
@@ -253,18 +259,16 @@ PW_API int pw_lovasz_softmax(const float* x, int ld, int is_logits, const unsign
     lovasz_keys_kernel<LV_MAX_CL><<<blocks, LV_TPB, 0, st>>>(
         x, ld, is_logits, target, camera_mask, n_vox, n_cls, ignore_label, keys_in, vals_in, counts);
   PW_LAUNCH_CHECK();
-  lovasz_offsets_kernel<<<1, 64, 0, st>>>(offsets, n_vox, n_cls);
-  PW_LAUNCH_CHECK();
+  (void)offsets;
   size_t cub_bytes = L.cub_bytes;
-  e = cub::DeviceSegmentedRadixSort::SortPairsDescending(
-      ws + L.cub_temp, cub_bytes, keys_in, keys_out, vals_in, vals_out, (int)(n_vox * n_cls), n_cls,
-      offsets, offsets + 1, 0, 32, st);
+  e = cub::DeviceRadixSort::SortPairs(ws + L.cub_temp, cub_bytes, keys_in, keys_out, vals_in,
+                                      vals_out, (int)(n_vox * n_cls), 0, KEY_BITS, st);
   if (e != cudaSuccess) return (int)e;
   lovasz_scan_kernel<<<n_cls, 1024, 0, st>>>(keys_out, vals_out, n_vox, n_cls, counts, nullptr,
                                              loss_acc, grad_probas);
   PW_LAUNCH_CHECK();
   lovasz_finalize_kernel<<<1, 32, 0, st>>>(loss_acc, loss);
-  PW_LAUNCH_CHECK(); pw_count_launch(4);
+  PW_LAUNCH_CHECK(); pw_count_launch(3);
   return 0;
 }
 

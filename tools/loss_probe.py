@@ -41,7 +41,7 @@ def main():
     print(f'stats {us_s:.1f} us  {by_s / us_s / 1e3:.0f} GB/s   grad {us_g:.1f} us  '
           f'{by_g / us_g / 1e3:.0f} GB/s')
     us_l = timed(lambda: ops.lovasz_softmax_rows(rows, True, t, c, 17), reps=10)
-    print(f'lovasz (keys + segmented sort + scan, with gradient) {us_l:.0f} us')
+    print(f'lovasz (keys + radix sort + per-class scan, with gradient) {us_l:.0f} us')
     pd, td, cd = pred.cuda(), target.cuda(), cam.cuda()
     us_lt = timed(lambda: loss_ref.lovasz_softmax(torch.softmax(pd, 1), td, 17, cd), reps=3)
     print(f'lovasz, reference formulation in torch on the same GPU (forward only): {us_lt:.0f} us')
