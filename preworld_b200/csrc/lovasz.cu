@@ -107,10 +107,6 @@ lovasz_keys_kernel(const float* __restrict__ x, int ld, int is_logits,
     if (s_cnt[i]) atomicAdd(counts + i, (unsigned long long)s_cnt[i]);
 }
 
-__global__ void lovasz_offsets_kernel(int* __restrict__ offsets, long long n, int C) {
-  for (int i = threadIdx.x; i <= C; i += blockDim.x) offsets[i] = (int)(i * n);
-}
-
 // One CTA per class.  out[0] += loss_c / #present; grad_p (optional) [n, C].
 __global__ void __launch_bounds__(1024)
 lovasz_scan_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ vals, long long n,
@@ -245,7 +241,6 @@ PW_API int pw_lovasz_softmax(const float* x, int ld, int is_logits, const unsign
   unsigned long long* keys_out = (unsigned long long*)(ws + L.keys_out);
   unsigned* vals_in = (unsigned*)(ws + L.vals_in);
   unsigned* vals_out = (unsigned*)(ws + L.vals_out);
-  int* offsets = (int*)(ws + L.offsets);
   unsigned long long* counts = (unsigned long long*)(ws + L.counts);
   double* loss_acc = (double*)(counts + LV_MAX_CL + 2);
   cudaStream_t st = (cudaStream_t)stream;
@@ -259,7 +254,6 @@ PW_API int pw_lovasz_softmax(const float* x, int ld, int is_logits, const unsign
     lovasz_keys_kernel<LV_MAX_CL><<<blocks, LV_TPB, 0, st>>>(
         x, ld, is_logits, target, camera_mask, n_vox, n_cls, ignore_label, keys_in, vals_in, counts);
   PW_LAUNCH_CHECK();
-  (void)offsets;
   size_t cub_bytes = L.cub_bytes;
   e = cub::DeviceRadixSort::SortPairs(ws + L.cub_temp, cub_bytes, keys_in, keys_out, vals_in,
                                       vals_out, (int)(n_vox * n_cls), 0, KEY_BITS, st);
