@@ -32,10 +32,10 @@ UNIT = 'frames/s'
 WORKLOAD = ('preworld-7frame-finetune, derived ResNet-50 @ 6x3x256x704 -> '
             '200x200x16, bs=1/GPU, forward-only')
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full
-# (profiles/r01m_hot_kernels.md), for the layer shapes that can lead the step
+# (profiles/r01n_hot_kernels.md), for the layer shapes that can lead the step
 NCU_TRAFFIC = {
-    'conv_halo 1x16x200x200x32->32 k333 s1 d1': 241.4e6,
-    'conv_halo 1x16x200x200x32->64 k333 s1 d1': 197.0e6,
+    'conv_halo 1x16x200x200x32->32 k333 s1 d1': 243.0e6,
+    'conv_halo 1x16x200x200x32->64 k333 s1 d1': 198.2e6,
 }
 FALLBACK_PEAKS = dict(hbm_gbs=6650.0, bf16_tflops=1590.0,
                       bf16_tflops_sustained=1400.0)
@@ -419,7 +419,7 @@ def main():
                             'peak is half the bf16 peak), so the executed-tensor-'
                             'work fraction is 6x this; traffic = ncu dram bytes '
                             'read+write of one launch of this layer shape '
-                            '(profiles/r01m_hot_kernels.md)'}
+                            '(profiles/r01n_hot_kernels.md)'}
         elif top == 'pw_conv_fwd':
             roof = {'kernel': 'conv_igemm_kernel (pw_conv_fwd, fp32 SIMT '
                               'implicit GEMM; all conv/linear layers)',
