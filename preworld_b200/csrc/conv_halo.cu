@@ -659,7 +659,7 @@ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int SMEM_LIMIT_2CTA = (228 * 1024 - 2 * 1024) / 2;   // two CTAs + 1 KB reserved each
-constexpr int SMEM_SLACK = 1024 /*align*/ + (6 * MAX_RING + 1) * 8 + 16;   // barriers: 2nh + nb(2+mt) + 1
+constexpr int SMEM_SLACK = 1024 /*align*/ + (6 * MAX_RING + 1) * 8 + 16;   // barriers: 2nh + nb(2+mt) + 2
 
 struct HaloPlan {
   bool ok = false;

@@ -170,6 +170,40 @@ def test_weight_packing():
     assert torch.allclose(got, want, atol=1e-5)
 
 
+def test_fold_weight_layout_reproduces_the_conv():
+    """PackedConv.set_fold_weights (the layout include/preworld_b200.h documents
+    for pw_conv_fold_fwd): evaluate the folded formulation in plain torch --
+    P[row, (slab,kx,n)] = sum over (kz,ky,ci) of x * Wf over INPUT columns, then
+    out[x] = sum_kx P[x + kx*dw] -- and compare with conv3d.  Pure host logic:
+    what the kernel's main loop and shifted-row epilogue compute."""
+    g = torch.Generator().manual_seed(4)
+    for cout, dil in ((32, 1), (16, 1), (40, 2)):
+        cin, kd, kh, kw = 32, 3, 3, 3
+        w = torch.randn(cout, cin, kd, kh, kw, generator=g)
+        pc = ops.PackedConv(w, padding=dil, dilation=dil)
+        fold_n = 16 if cout <= 16 else 32
+        slabs = -(-cout // fold_n)
+        wf = pc.wf_hi + pc.wf_lo
+        assert wf.shape == (slabs * kw * fold_n, kd * kh * cin)
+        assert (pc.wf_hi.view(torch.int32) & 0x1FFF == 0).all()
+        x = torch.randn(1, cin, 4, 5, 9, generator=g)
+        want = torch.nn.functional.conv3d(x, w, None, 1, dil, dil)
+        xp = torch.nn.functional.pad(x, (dil,) * 6)[0]            # [ci, Z+2d, Y+2d, X+2d]
+        Z, Y, X = x.shape[2:]
+        # K index = (kz*kh + ky)*cin + ci over the (kz,ky)-shifted input columns
+        cols = torch.stack([xp[:, kz * dil:kz * dil + Z, ky * dil:ky * dil + Y, :]
+                            for kz in range(kd) for ky in range(kh)], 0)   # [T',ci,Z,Y,Xin]
+        A = cols.permute(2, 3, 4, 0, 1).reshape(Z, Y, X + 2 * dil, kd * kh * cin)
+        P = (A.double() @ wf.double().t()).view(Z, Y, X + 2 * dil, slabs, kw, fold_n)
+        out = sum(P[:, :, kx * dil:kx * dil + X, :, kx] for kx in range(kw))  # [Z,Y,X,slab,n]
+        got = out.reshape(Z, Y, X, slabs * fold_n)[..., :cout].permute(3, 0, 1, 2)
+        assert torch.allclose(got.float(), want[0], atol=2e-4), (cout, dil)
+        # rows beyond cout are zero
+        if slabs * fold_n > cout:
+            pad_rows = wf.view(slabs, kw, fold_n, -1)[-1, :, cout - (slabs - 1) * fold_n:]
+            assert (pad_rows == 0).all()
+
+
 def test_cl_layout_helpers():
     x = torch.zeros(2, 5, 7, 16)
     assert ops.cl_ld(x) == 16 and ops.cl_ld(x[..., 4:12]) == 16
