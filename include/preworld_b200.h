@@ -442,6 +442,27 @@ int pw_lovasz_softmax(const float* x, int ld, int is_logits, const unsigned char
 int pw_softmax_backward(const float* logits, int ld, const float* grad_probas,
                         long long n_vox, int n_cls, float* grad_logits, void* stream);
 
+/* CustomFocalLoss.forward (mmdet3d/models/loss_utils/focal_loss.py:162-273), the
+ * voxel CE term PreWorld uses by default (use_focal_loss=True, preworld.py:43,
+ * 146-148): sigmoid focal loss per (voxel, class) -- mmcv-full 1.6.0's
+ * sigmoid_focal_loss op restated (third-party, absent from the reference tree;
+ * the file's own py_sigmoid_focal_loss is the same function) -- times
+ * class_weights[c] * radial[(v / depth) % hw] (the [H,W] centre-distance map of
+ * focal_loss.py:197-203; NULL = 1), summed over classes, mean over kept voxels
+ * (target != ignore_index [and camera_mask]), times loss_weight.
+ * sums[2] = {sum, kept count}; pw_focal_loss_grad writes d loss / d logits
+ * [n_vox, n_cls] (zero rows for dropped voxels). */
+int pw_focal_loss(const float* logits, int ld, const unsigned char* target,
+                  const unsigned char* camera_mask, long long n_vox, int n_cls,
+                  int ignore_index, const float* class_weights, const float* radial, int hw,
+                  int depth, float gamma, float alpha, float loss_weight, double* sums,
+                  float* loss, void* stream);
+int pw_focal_loss_grad(const float* logits, int ld, const unsigned char* target,
+                       const unsigned char* camera_mask, long long n_vox, int n_cls,
+                       int ignore_index, const float* class_weights, const float* radial,
+                       int hw, int depth, float gamma, float alpha, float loss_weight,
+                       const double* sums, float* grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

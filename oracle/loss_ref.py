@@ -172,3 +172,32 @@ def lovasz_softmax(probas, labels, ignore=None, camera_mask=None):
         errors_sorted, perm = torch.sort(errors, 0, descending=True)
         losses.append(torch.dot(errors_sorted, lovasz_grad(fg[perm]).detach()))
     return sum(losses) / len(losses)
+
+
+# ---- CustomFocalLoss (loss_utils/focal_loss.py:11-58,162-273) --------------------
+def radial_weight(H, W):
+    """focal_loss.py:197-203: 1 + distance from the grid centre / its maximum."""
+    xy, yx = torch.meshgrid([torch.arange(H) - H / 2, torch.arange(W) - W / 2], indexing='ij')
+    c = torch.norm(torch.stack([xy, yx], 2), 2, -1)
+    return c / c.max() + 1
+
+
+def custom_focal_loss(pred, target, class_weights, ignore_index=255, camera_mask=None,
+                      gamma=2.0, alpha=0.25, loss_weight=100.0):
+    """CustomFocalLoss.forward with py_sigmoid_focal_loss (the file's own torch
+    version of mmcv's CUDA op): pred [B,C,H,W,D] logits, target [B,H,W,D]."""
+    B, H, W, D = target.shape
+    C = pred.shape[1]
+    c = radial_weight(H, W)[None, :, :, None].repeat(B, 1, 1, D).reshape(-1)
+    valid = target != ignore_index
+    if camera_mask is not None:
+        valid = valid & camera_mask.bool()
+    vis = valid.reshape(-1).nonzero().squeeze(-1)
+    wm = class_weights.float()[None, :] * c[vis, None]
+    x = pred.permute(0, 2, 3, 4, 1).reshape(-1, C)[vis].float()
+    t = F.one_hot(target.reshape(-1)[vis].long(), num_classes=C + 1)[:, :C].float()
+    p = x.sigmoid()
+    pt = (1 - p) * t + p * (1 - t)
+    fw = (alpha * t + (1 - alpha) * (1 - t)) * pt.pow(gamma)
+    loss = F.binary_cross_entropy_with_logits(x, t, reduction='none') * fw * wm
+    return loss_weight * loss.sum(-1).mean()

@@ -58,6 +58,35 @@ def reference_depth_loss(seed):
                 label_checksum=int((labels.argmax(1) * (labels.sum(1) > 0)).sum()))
 
 
+def reference_focal_loss(root, seed, use_mask):
+    """CustomFocalLoss.forward of the reference (loss_utils/focal_loss.py:221-270) with
+    its CPU branch py_sigmoid_focal_loss; the module is imported by path with mmcv.ops /
+    mmdet.models.losses.utils stubbed (neither is called on this branch).  `self.c` is
+    rebuilt exactly as in __init__ (:197-203, minus the .cuda())."""
+    import types
+    from oracle import ref_shim
+    ref_shim.install()
+    ref_shim._install('mmcv.ops', sigmoid_focal_loss=None)
+    ref_shim._install('mmdet.models.losses')
+    ref_shim._install('mmdet.models.losses.utils', weight_reduce_loss=None)
+    import sys as _sys
+    if not hasattr(_sys.modules['mmdet.models.builder'], 'LOSSES'):
+        _sys.modules['mmdet.models.builder'].LOSSES = _sys.modules['mmdet.models.builder'].HEADS
+    path = os.path.join(root, 'mmdet3d', 'models', 'loss_utils', 'focal_loss.py')
+    spec = importlib.util.spec_from_file_location('ref_focal', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    pred, target, cam, cw = loss_ref.seeded_case(seed)
+    cwz = torch.cat([cw, torch.zeros(1)])
+    B, H, W, D = target.shape
+    xy, yx = torch.meshgrid([torch.arange(H) - H / 2, torch.arange(W) - W / 2])
+    c = torch.norm(torch.stack([xy, yx], 2), 2, -1)
+    me = types.SimpleNamespace(c=c / c.max() + 1, use_sigmoid=True, activated=False, gamma=2.0,
+                               alpha=0.25, reduction='mean', loss_weight=100.0)
+    return float(mod.CustomFocalLoss.forward(me, pred, target, cwz, None, 255, None,
+                                             cam if use_mask else None))
+
+
 def main():
     root = sys.argv[1] if len(sys.argv) > 1 else '/root/reference'
     ref = load_reference(root)
@@ -74,6 +103,9 @@ def main():
             out[f'lovasz_seed{seed}_mask{int(use_mask)}'] = float(lov.lovasz_softmax(
                 torch.softmax(pred, dim=1), target, ignore=17,
                 camera_mask=cam if use_mask else None))
+    for seed in range(3):
+        for use_mask in (False, True):
+            out[f'focal_seed{seed}_mask{int(use_mask)}'] = reference_focal_loss(root, seed, use_mask)
     path = os.path.join(ROOT, 'tests', 'golden', 'voxel_losses.json')
     with open(path, 'w') as f:
         json.dump(out, f, indent=1, sort_keys=True)

@@ -117,6 +117,10 @@ SIGNATURES = {
     'pw_lovasz_softmax': [c_p, c_int, c_int, c_p, c_p, c_ll, c_int, c_int, c_p, c_ll,
                           c_p, c_p, c_p],
     'pw_softmax_backward': [c_p, c_int, c_p, c_ll, c_int, c_p, c_p],
+    'pw_focal_loss': [c_p, c_int, c_p, c_p, c_ll, c_int, c_int, c_p, c_p, c_int, c_int,
+                      c_f, c_f, c_f, c_p, c_p, c_p],
+    'pw_focal_loss_grad': [c_p, c_int, c_p, c_p, c_ll, c_int, c_int, c_p, c_p, c_int,
+                           c_int, c_f, c_f, c_f, c_p, c_p, c_p],
     'pw_occ_confusion': [c_p, c_p, c_p, c_ll, c_int, c_int, c_p, c_p, c_p],
     'pw_raw2alpha': [c_p, c_f, c_f, c_ll, c_p, c_p, c_p],
     'pw_alpha2weight': [c_p, c_p, c_ll, c_int, c_p, c_p, c_p, c_p, c_p, c_p],

@@ -448,3 +448,104 @@ PW_API int pw_depth_loss_grad(const int* labels, int bn, int h, int w, const flo
   PW_LAUNCH_CHECK(); pw_count_launch(1);
   return 0;
 }
+
+// ---- CustomFocalLoss (loss_utils/focal_loss.py:162-273; PreWorld's default voxel CE
+// term, preworld.py:43,116-117,146-148) -------------------------------------------------
+// Sigmoid focal loss per (voxel, class) in the form of mmcv 1.6.0's CUDA op
+// (sigmoid_focal_loss_cuda_kernel.cuh; the file's own py_sigmoid_focal_loss is the same
+// function up to rounding), times class_weight[c] * radial[h,w], summed over classes,
+// mean over the kept voxels (target != ignore [& camera mask]), times loss_weight.
+namespace {
+
+__device__ __forceinline__ float focal_term(float x, bool hit, float gamma, float alpha) {
+  const float p = 1.f / (1.f + expf(-x));
+  if (hit) return -alpha * powf(1.f - p, gamma) * logf(fmaxf(p, 1.17549435e-38f));
+  return -(1.f - alpha) * powf(p, gamma) * logf(fmaxf(1.f - p, 1.17549435e-38f));
+}
+__device__ __forceinline__ float focal_term_grad(float x, bool hit, float gamma, float alpha) {
+  const float p = 1.f / (1.f + expf(-x));
+  if (hit)
+    return -alpha * powf(1.f - p, gamma) *
+           (1.f - p - gamma * p * logf(fmaxf(p, 1.17549435e-38f)));
+  return -(1.f - alpha) * powf(p, gamma) *
+         (gamma * (1.f - p) * logf(fmaxf(1.f - p, 1.17549435e-38f)) - p);
+}
+
+// grad == nullptr: sums[0] += sum of weighted losses, sums[1] += kept voxels.
+// grad != nullptr: grad[v, c] = loss_weight / sums[1] * w_c * radial * d term / d x.
+__global__ void __launch_bounds__(TPB_L)
+focal_loss_kernel(const float* __restrict__ logits, int ld, const unsigned char* __restrict__ target,
+                  const unsigned char* __restrict__ cam, long long n, int C, int ignore_index,
+                  const float* __restrict__ class_w, const float* __restrict__ radial, int hw,
+                  int depth, float gamma, float alpha, float loss_weight,
+                  double* __restrict__ sums, float* __restrict__ grad) {
+  const float scale = grad ? (float)(loss_weight / (sums[1] > 0.0 ? sums[1] : 1.0)) : 0.f;
+  double acc = 0.0, cnt = 0.0;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int t = target[v];
+    const bool kept = t != ignore_index && (cam == nullptr || cam[v] != 0);
+    if (!kept) {
+      if (grad)
+        for (int c = 0; c < C; ++c) grad[v * C + c] = 0.f;
+      continue;
+    }
+    const float rw = radial ? __ldg(radial + (v / depth) % hw) : 1.f;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float x = __ldg(logits + v * ld + c);
+      const float wm = __ldg(class_w + c) * rw;                 // weight_mask[v, c]
+      if (grad) grad[v * C + c] = scale * wm * focal_term_grad(x, t == c, gamma, alpha);
+      else s += focal_term(x, t == c, gamma, alpha) * wm;
+    }
+    acc += (double)s;
+    cnt += 1.0;
+  }
+  if (grad) return;
+  acc = warp_sum(acc);
+  cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0 && cnt > 0.0) {
+    atomicAdd(sums, acc);
+    atomicAdd(sums + 1, cnt);
+  }
+}
+
+__global__ void focal_finalize_kernel(const double* __restrict__ sums, float loss_weight,
+                                      float* __restrict__ loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) loss[0] = (float)(loss_weight * sums[0] / sums[1]);
+}
+
+}  // namespace
+
+PW_API int pw_focal_loss(const float* logits, int ld, const unsigned char* target,
+                         const unsigned char* camera_mask, long long n_vox, int n_cls,
+                         int ignore_index, const float* class_weights, const float* radial, int hw,
+                         int depth, float gamma, float alpha, float loss_weight, double* sums,
+                         float* loss, void* stream) {
+  PW_REQUIRE(logits && target && class_weights && sums && loss);
+  PW_REQUIRE(n_vox > 0 && n_cls > 0 && ld >= n_cls && (radial == nullptr || (hw > 0 && depth > 0)));
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(sums, 0, 2 * sizeof(double), st);
+  if (e != cudaSuccess) return (int)e;
+  focal_loss_kernel<<<grad_blocks(n_vox), TPB_L, 0, st>>>(
+      logits, ld, target, camera_mask, n_vox, n_cls, ignore_index, class_weights, radial, hw, depth,
+      gamma, alpha, loss_weight, sums, nullptr);
+  PW_LAUNCH_CHECK();
+  focal_finalize_kernel<<<1, 32, 0, st>>>(sums, loss_weight, loss);
+  PW_LAUNCH_CHECK(); pw_count_launch(2);
+  return 0;
+}
+
+PW_API int pw_focal_loss_grad(const float* logits, int ld, const unsigned char* target,
+                              const unsigned char* camera_mask, long long n_vox, int n_cls,
+                              int ignore_index, const float* class_weights, const float* radial,
+                              int hw, int depth, float gamma, float alpha, float loss_weight,
+                              const double* sums, float* grad, void* stream) {
+  PW_REQUIRE(logits && target && class_weights && sums && grad);
+  PW_REQUIRE(n_vox > 0 && n_cls > 0 && ld >= n_cls && (radial == nullptr || (hw > 0 && depth > 0)));
+  focal_loss_kernel<<<grad_blocks(n_vox), TPB_L, 0, (cudaStream_t)stream>>>(
+      logits, ld, target, camera_mask, n_vox, n_cls, ignore_index, class_weights, radial, hw, depth,
+      gamma, alpha, loss_weight, const_cast<double*>(sums), grad);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}

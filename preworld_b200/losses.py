@@ -98,16 +98,22 @@ def geo_scal_loss(pred, ssc_target, ignore_index, non_empty_idx=0,
 
 def loss_voxel(output_voxels, target_voxels, class_weights, empty_idx,
                camera_mask=None, weight_voxel_ce=1.0, weight_voxel_sem_scal=1.0,
-               weight_voxel_geo_scal=1.0, weight_voxel_lovasz=1.0):
+               weight_voxel_geo_scal=1.0, weight_voxel_lovasz=1.0,
+               use_focal_loss=True, focal_loss=None):
     """PreWorld.loss_voxel (preworld.py:129-157), all four terms
-    (``weight_voxel_lovasz=None`` leaves the Lovasz term out):
+    (``weight_voxel_lovasz=None`` leaves the Lovasz term out; the CE term is the
+    focal loss unless ``use_focal_loss=False``, as in the reference):
     ``class_weights`` are the per-class weights WITHOUT the empty class (a zero
     is appended, preworld.py:150)."""
     cw = torch.cat([class_weights.to(output_voxels.device).float(),
                     torch.zeros(1, device=output_voxels.device)])
     t = voxel_loss_terms(output_voxels, target_voxels, cw, 255, empty_idx,
                          camera_mask)
-    out = dict(loss_voxel_ce=weight_voxel_ce * t['ce'],
+    ce = t['ce']
+    if use_focal_loss:                                  # preworld.py:146-148 (the default)
+        focal_loss = focal_loss or CustomFocalLoss()
+        ce = focal_loss(output_voxels, target_voxels, cw, 255, camera_mask=camera_mask)
+    out = dict(loss_voxel_ce=weight_voxel_ce * ce,
                loss_voxel_sem=weight_voxel_sem_scal * t['sem'],
                loss_voxel_geo=weight_voxel_geo_scal * t['geo'])
     if weight_voxel_lovasz is not None:
@@ -182,3 +188,64 @@ def lovasz_softmax(probas, labels, classes='present', per_image=False,
         camera_mask.reshape(-1).to(torch.uint8).contiguous()
     ign = -1 if ignore is None else int(ignore)
     return _Lovasz.apply(rows, bool(from_logits), t, cam, ign)
+
+
+class _Focal(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rows, target, camera_mask, class_weights, radial, depth,
+                gamma, alpha, loss_weight, ignore_index):
+        loss, sums = ops.focal_loss(rows, target, camera_mask, class_weights, radial,
+                                    depth, gamma, alpha, loss_weight, ignore_index)
+        ctx.args = (camera_mask, radial, depth, gamma, alpha, loss_weight, ignore_index)
+        ctx.save_for_backward(rows, target, class_weights, sums)
+        return loss[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        rows, target, class_weights, sums = ctx.saved_tensors
+        camera_mask, radial, depth, gamma, alpha, loss_weight, ignore_index = ctx.args
+        grad = ops.focal_loss_grad(rows, target, camera_mask, class_weights, radial,
+                                   depth, gamma, alpha, loss_weight, sums, ignore_index)
+        return (grad * g,) + (None,) * 9
+
+
+class CustomFocalLoss(torch.nn.Module):
+    """mmdet3d/models/loss_utils/focal_loss.py:162-273 (registered as
+    ``CustomFocalLoss``; ``PreWorld`` builds it when ``use_focal_loss=True``, the
+    default, preworld.py:43,116-117): sigmoid focal loss weighted per class and by
+    the distance of the voxel column from the grid centre.  The centre-distance
+    map follows the input's H x W (the reference hard-codes 200 x 200)."""
+
+    def __init__(self, use_sigmoid=True, gamma=2.0, alpha=0.25, reduction='mean',
+                 loss_weight=100.0, activated=False):
+        super().__init__()
+        if not use_sigmoid or activated:
+            raise NotImplementedError('CustomFocalLoss: only sigmoid logits '
+                                      '(the configuration preworld.py:117 builds)')
+        self.gamma, self.alpha = gamma, alpha
+        self.reduction, self.loss_weight = reduction, loss_weight
+        self._radial = {}
+
+    def radial(self, H, W, device):
+        key = (H, W, str(device))
+        if key not in self._radial:
+            xy, yx = torch.meshgrid([torch.arange(H) - H / 2, torch.arange(W) - W / 2],
+                                    indexing='ij')
+            c = torch.norm(torch.stack([xy, yx], 2), 2, -1)
+            self._radial[key] = (c / c.max() + 1).reshape(-1).to(device).contiguous()
+        return self._radial[key]
+
+    def forward(self, pred, target, weight=None, avg_factor=None, ignore_index=255,
+                reduction_override=None, camera_mask=None):
+        if not pred.is_cuda:
+            raise RuntimeError('preworld_b200.losses needs CUDA tensors '
+                               '(there is no CPU fallback)')
+        B, H, W, D = target.shape
+        rows = _rows(pred.float())
+        cam = None if camera_mask is None else \
+            camera_mask.reshape(-1).to(torch.uint8).contiguous()
+        cw = (weight if weight is not None else torch.ones(pred.shape[1])) \
+            .to(pred.device).float().contiguous()
+        return _Focal.apply(rows, _labels(target), cam, cw, self.radial(H, W, pred.device),
+                            D, float(self.gamma), float(self.alpha),
+                            float(self.loss_weight), int(ignore_index))

@@ -836,3 +836,39 @@ def softmax_backward(rows_logits, grad_probas):
                                          _ptr(grad_probas), v, c, _ptr(gl),
                                          _stream()), 'pw_softmax_backward')
     return gl
+
+
+def focal_loss(rows, target, camera_mask, class_weights, radial, depth,
+               gamma, alpha, loss_weight, ignore_index=255):
+    """CustomFocalLoss on rows [V, C] logits (voxel order ..., H, W, D with
+    ``depth`` = D and ``radial`` the fp32 [H*W] centre-distance map or None).
+    -> (loss fp32 [1], sums fp64 [2] = weighted sum, kept count)."""
+    _require_cuda(rows, target, camera_mask, class_weights, radial)
+    v, c = rows.shape
+    assert rows.dtype == torch.float32 and rows.stride(1) == 1
+    cw = class_weights.float().contiguous()
+    assert cw.numel() == c and target.dtype == torch.uint8 and target.numel() == v
+    sums = torch.empty(2, device=rows.device, dtype=torch.float64)
+    loss = torch.empty(1, device=rows.device, dtype=torch.float32)
+    hw = radial.numel() if radial is not None else 0
+    check(_lib.lib().pw_focal_loss(_ptr(rows), rows.stride(0), _ptr(target),
+                                   _ptr(camera_mask), v, c, int(ignore_index), _ptr(cw),
+                                   _ptr(radial), hw, int(depth), float(gamma),
+                                   float(alpha), float(loss_weight), _ptr(sums),
+                                   _ptr(loss), _stream()), 'pw_focal_loss')
+    return loss, sums
+
+
+def focal_loss_grad(rows, target, camera_mask, class_weights, radial, depth,
+                    gamma, alpha, loss_weight, sums, ignore_index=255):
+    v, c = rows.shape
+    cw = class_weights.float().contiguous()
+    grad = torch.empty((v, c), device=rows.device, dtype=torch.float32)
+    hw = radial.numel() if radial is not None else 0
+    check(_lib.lib().pw_focal_loss_grad(_ptr(rows), rows.stride(0), _ptr(target),
+                                        _ptr(camera_mask), v, c, int(ignore_index),
+                                        _ptr(cw), _ptr(radial), hw, int(depth),
+                                        float(gamma), float(alpha), float(loss_weight),
+                                        _ptr(sums), _ptr(grad), _stream()),
+          'pw_focal_loss_grad')
+    return grad

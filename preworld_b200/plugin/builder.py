@@ -84,10 +84,9 @@ def build_model(cfg, train_cfg=None, test_cfg=None):
 
 
 class _TrainingOnlyLoss(nn.Module):
-    """Placeholder for the training losses the configs name
-    (bevstereo-occ.py:109-112 ``loss_occ``; preworld.py:118
-    ``CustomFocalLoss``).  Training losses are outside the forward-only scope
-    (SURVEY.md §2 row 14); calling one raises."""
+    """Placeholder for the training loss ``loss_occ`` the base config names
+    (bevstereo-occ.py:109-112, unused by PreWorld's own heads); calling it
+    raises.  ``CustomFocalLoss`` (preworld.py:117) is the real thing below."""
 
     def __init__(self, **kwargs):
         super().__init__()
@@ -98,5 +97,9 @@ class _TrainingOnlyLoss(nn.Module):
             'training losses are out of scope of the forward-only path')
 
 
-for _n in ('CrossEntropyLoss', 'CustomFocalLoss'):
+for _n in ('CrossEntropyLoss',):
     LOSSES.register_module(name=_n, module=type(_n, (_TrainingOnlyLoss,), {}))
+
+# preworld.py:117 builds this one; it is implemented
+from ..losses import CustomFocalLoss as _CustomFocalLoss  # noqa: E402
+LOSSES.register_module(name='CustomFocalLoss', module=_CustomFocalLoss)

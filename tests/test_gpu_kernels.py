@@ -670,7 +670,8 @@ def test_voxel_losses_match_oracle(seed, use_mask):
     assert (g_ref - g_dev).abs().max() <= 1e-4 * g_ref.abs().max()
     # the reference-named wrappers and the NCDHW-contiguous input route
     lv = losses.loss_voxel(pred.to(DEV), target.to(DEV), cw.to(DEV), 17,
-                           None if m is None else m.to(DEV), 1.0, 1.0, 1.0)
+                           None if m is None else m.to(DEV), 1.0, 1.0, 1.0,
+                           use_focal_loss=False)
     assert abs(float(lv['loss_voxel_sem']) - float(want['sem'])) <= 2e-5 * abs(float(want['sem']))
     assert abs(float(lv['loss_voxel_ce']) - float(want['ce'])) <= 2e-5 * abs(float(want['ce']))
     assert abs(float(lv['loss_voxel_geo']) - float(want['geo'])) <= 2e-5 * abs(float(want['geo']))
@@ -779,3 +780,35 @@ def test_lovasz_softmax_full_grid():
     got = losses.lovasz_softmax(pred.to(DEV), target.to(DEV), ignore=17,
                                 camera_mask=cam.to(DEV), from_logits=True)
     assert abs(float(got) - float(want)) <= 2e-5 * float(want)
+
+
+@pytest.mark.parametrize('seed,use_mask', [(0, True), (1, False), (2, True)])
+def test_custom_focal_loss_matches_oracle(seed, use_mask, golden_dir):
+    """pw_focal_loss / pw_focal_loss_grad (CustomFocalLoss, PreWorld's default CE
+    term) against the CPU restatement, its autograd and the reference's value;
+    built through the LOSSES registry as preworld.py:117 does."""
+    import json
+    import os
+    from oracle import loss_ref
+    from preworld_b200 import losses
+    from preworld_b200.plugin import builder
+    gold = json.load(open(os.path.join(golden_dir, 'voxel_losses.json')))
+    pred, target, cam, cw = loss_ref.seeded_case(seed)
+    cwz = torch.cat([cw, torch.zeros(1)])
+    m = cam if use_mask else None
+    p_ref = pred.clone().requires_grad_(True)
+    want = loss_ref.custom_focal_loss(p_ref, target, cwz, 255, m)
+    want.backward()
+    fl = builder.build_loss(dict(type='CustomFocalLoss'))
+    assert isinstance(fl, losses.CustomFocalLoss)
+    p_dev = pred.to(DEV).requires_grad_(True)
+    got = fl(p_dev, target.to(DEV), cwz.to(DEV), 255,
+             camera_mask=None if m is None else m.to(DEV))
+    assert abs(float(got) - float(want)) <= 2e-5 * float(want)
+    assert abs(float(got) - gold[f'focal_seed{seed}_mask{int(use_mask)}']) <= 2e-5 * float(want)
+    got.backward()
+    assert (p_dev.grad.cpu() - p_ref.grad).abs().max() <= 1e-4 * p_ref.grad.abs().max()
+    # loss_voxel takes the focal term by default (use_focal_loss=True, preworld.py:43)
+    lv = losses.loss_voxel(pred.to(DEV), target.to(DEV), cw.to(DEV), 17,
+                           None if m is None else m.to(DEV))
+    assert abs(float(lv['loss_voxel_ce']) - float(want)) <= 2e-5 * float(want)
