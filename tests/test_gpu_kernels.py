@@ -812,3 +812,44 @@ def test_custom_focal_loss_matches_oracle(seed, use_mask, golden_dir):
     lv = losses.loss_voxel(pred.to(DEV), target.to(DEV), cw.to(DEV), 17,
                            None if m is None else m.to(DEV))
     assert abs(float(lv['loss_voxel_ce']) - float(want)) <= 2e-5 * float(want)
+
+
+def test_loss_edge_cases():
+    """Degenerate inputs of the training losses, as the reference treats them:
+    no lidar return at all -> depth loss exactly 0 with zero gradient
+    (view_transformer.py:788: sum / max(1, #fg)); every voxel dropped -> Lovasz 0
+    with zero gradient (lovasz_softmax.py:182-184); a target with one single class
+    -> the per-class terms of sem_scal reduce to that class (loss.py:56-79); an
+    all-ignored target -> focal loss over zero voxels is NaN like a mean of nothing."""
+    from oracle import loss_ref
+    from preworld_b200 import losses
+    g = torch.Generator().manual_seed(11)
+    # depth loss, empty ground truth
+    gt = torch.zeros(1, 2, 32, 48)
+    preds = torch.softmax(torch.randn(2, 88, 2, 3, generator=g), 1).to(DEV).requires_grad_(True)
+    loss = losses.get_depth_loss(gt.to(DEV), preds, 16, [1.0, 45.0, 0.5], 3.0)
+    assert float(loss) == 0.0
+    loss.backward()
+    assert (preds.grad == 0).all()
+    # Lovasz, nothing kept (every label is the ignored empty class)
+    pred = torch.randn(1, 18, 4, 5, 3, generator=g)
+    target = torch.full((1, 4, 5, 3), 17)
+    p = pred.to(DEV).requires_grad_(True)
+    lv = losses.lovasz_softmax(p, target.to(DEV), ignore=17, from_logits=True)
+    assert float(lv) == 0.0
+    lv.backward()
+    assert (p.grad == 0).all()
+    # one class only (+ some ignored voxels): device == oracle
+    target = torch.full((1, 4, 5, 3), 6)
+    target[0, 0, :2] = 255
+    cw = torch.ones(18)
+    got = losses.voxel_loss_terms(pred.to(DEV), target.to(DEV), cw.to(DEV), 255, 17)
+    assert abs(float(got['sem']) - float(loss_ref.sem_scal_loss(pred, target, 255))) < 2e-5
+    assert abs(float(got['ce']) - float(loss_ref.ce_ssc_loss(pred, target, cw, 255))) < 2e-5
+    want_l = loss_ref.lovasz_softmax(torch.softmax(pred, 1), target, 17)
+    got_l = losses.lovasz_softmax(pred.to(DEV), target.to(DEV), ignore=17, from_logits=True)
+    assert abs(float(got_l) - float(want_l)) <= 1e-5 * float(want_l)
+    # focal loss over zero kept voxels
+    fl = losses.CustomFocalLoss()
+    nan = fl(pred.to(DEV), torch.full((1, 4, 5, 3), 255).to(DEV), cw.to(DEV), 255)
+    assert torch.isnan(nan)
