@@ -463,6 +463,15 @@ int pw_focal_loss_grad(const float* logits, int ld, const unsigned char* target,
                        int hw, int depth, float gamma, float alpha, float loss_weight,
                        const double* sums, float* grad, void* stream);
 
+/* pts2ray / get_rays (mmdet3d/datasets/ray.py:34-56): n labelled pixels of ONE
+ * camera -> rays [n, 16] = [x, y, depth, semantic, origin(3), direction(3), unit
+ * view direction(3), rgb(3)], the record NerfHead consumes.  coor [n,2] pixel
+ * xy, label_depth / label_seg [n], label_img [n,3], c2w [4,4] row-major
+ * (camera -> key ego), cam_intrinsic [3,3] row-major; all fp32 device arrays. */
+int pw_pts2ray(const float* coor, const float* label_depth, const float* label_seg,
+               const float* label_img, const float* c2w, const float* cam_intrinsic,
+               long long n, float* rays, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -121,6 +121,7 @@ SIGNATURES = {
                       c_f, c_f, c_f, c_p, c_p, c_p],
     'pw_focal_loss_grad': [c_p, c_int, c_p, c_p, c_ll, c_int, c_int, c_p, c_p, c_int,
                            c_int, c_f, c_f, c_f, c_p, c_p, c_p],
+    'pw_pts2ray': [c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_p],
     'pw_occ_confusion': [c_p, c_p, c_p, c_ll, c_int, c_int, c_p, c_p, c_p],
     'pw_raw2alpha': [c_p, c_f, c_f, c_ll, c_p, c_p, c_p],
     'pw_alpha2weight': [c_p, c_p, c_ll, c_int, c_p, c_p, c_p, c_p, c_p, c_p],

@@ -2,6 +2,8 @@
 reference of the same op, on seeded inputs small enough for the oracle to
 finish in seconds.  Integer / index results must be bit-exact; float results
 within the tolerance written at each assert."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -853,3 +855,34 @@ def test_loss_edge_cases():
     fl = losses.CustomFocalLoss()
     nan = fl(pred.to(DEV), torch.full((1, 4, 5, 3), 255).to(DEV), cw.to(DEV), 255)
     assert torch.isnan(nan)
+
+
+def test_pts2ray_matches_reference_fixture(golden_dir):
+    """pw_pts2ray / rays.generate_rays (datasets/ray.py:34-119) against the
+    reference's own output (tests/golden/rays.npz): pixel, label, origin and
+    direction columns bit-exact (the kernel rounds like the torch expression: no
+    FMA), unit view directions to 1 ulp-level tolerance; sampling weights equal to
+    the oracle's; weighted sampling draws the requested number of distinct rays."""
+    from oracle import ray_ref
+    from preworld_b200 import rays as R
+    coors, depths, segs, imgs, c2ws, Ks, time_ids, dyn = ray_ref.seeded_case(0)
+    dev = lambda ts: [t.to(DEV) for t in ts]
+    got = R.generate_rays(dev(coors), dev(depths), dev(segs), dev(imgs), dev(c2ws), dev(Ks),
+                          max_ray_nums=0, time_ids=time_ids, dynamic_class=dyn, use_wrs=False)
+    gold = torch.from_numpy(np.load(os.path.join(golden_dir, 'rays.npz'))['rays'])
+    assert got.shape == gold.shape
+    g = got.cpu()
+    assert torch.equal(g[:, :10], gold[:, :10]) and torch.equal(g[:, 13:], gold[:, 13:])
+    assert (g[:, 10:13] - gold[:, 10:13]).abs().max() <= 2e-7
+    per_cam = [R.pts2ray(*[t.to(DEV) for t in (coors[i], depths[i], segs[i], imgs[i], c2ws[i], Ks[i])])
+               for t_ in time_ids for i in time_ids[t_]]
+    ids = [t_ for t_ in time_ids for _ in time_ids[t_]]
+    w_dev, _ = R.ray_weights(per_cam, ids, dyn)
+    w_ref = ray_ref.ray_weights([r.cpu() for r in per_cam], ids, dyn)
+    assert (torch.cat(w_dev).cpu() - torch.cat(w_ref)).abs().max() <= 1e-6
+    pick = R.generate_rays(dev(coors), dev(depths), dev(segs), dev(imgs), dev(c2ws), dev(Ks),
+                           max_ray_nums=1000, time_ids=time_ids, dynamic_class=dyn)
+    assert pick.shape == (1000, 16)
+    assert len({tuple(r) for r in pick[:, [0, 1, 4, 5, 7]].cpu().tolist()}) > 990
+    assert R.pts2ray(*[t.to(DEV) for t in (coors[0][:0], depths[0][:0], segs[0][:0],
+                                           imgs[0][:0], c2ws[0], Ks[0])]).shape == (0, 16)
