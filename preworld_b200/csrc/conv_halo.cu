@@ -102,6 +102,7 @@ struct HaloParams {
   int dbg;                     // PW_HALO_DBG knock-out bits (timing experiments only)
   long long* ts;               // PW_HALO_TS: per-CTA clock64 milestones (debug)
   int out_ld, res_ld, act, act_channels;
+  float gain;                  // umma_chain_gain(): undoes the accumulator's truncation bias
   const float* scale;
   const float* bias;
   const float* res;
@@ -379,16 +380,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 v = raw[j];
-        const float f[4] = {v.x, v.y, v.z, v.w};
-        float lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) hl[j * 4 + e] = __float_as_uint(f[e]) & 0xFFFFE000u;
-        // lo = x - hi, two elements per FADD2 (exact either way: no rounding occurs)
-        sub2(f[0], f[1], __uint_as_float(hl[j * 4]), __uint_as_float(hl[j * 4 + 1]), lo[0], lo[1]);
-        sub2(f[2], f[3], __uint_as_float(hl[j * 4 + 2]), __uint_as_float(hl[j * 4 + 3]), lo[2],
-             lo[3]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) hl[BLOCK_K + j * 4 + e] = __float_as_uint(lo[e]);
+        float h0, h1, h2, h3, l0, l1, l2, l3;
+        // round-to-nearest split, two elements per packed instruction (tc_ptx.cuh)
+        split2_rn(v.x, v.y, h0, h1, l0, l1);
+        split2_rn(v.z, v.w, h2, h3, l2, l3);
+        hl[j * 4] = __float_as_uint(h0); hl[j * 4 + 1] = __float_as_uint(h1);
+        hl[j * 4 + 2] = __float_as_uint(h2); hl[j * 4 + 3] = __float_as_uint(h3);
+        hl[BLOCK_K + j * 4] = __float_as_uint(l0); hl[BLOCK_K + j * 4 + 1] = __float_as_uint(l1);
+        hl[BLOCK_K + j * 4 + 2] = __float_as_uint(l2); hl[BLOCK_K + j * 4 + 3] = __float_as_uint(l3);
       }
       // the PREVIOUS row's store is published only now: its completion latency
       // ran under this row's hi/lo split
@@ -581,7 +580,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const bool ok = cbase + e < p.cout;
-          sc[e] = (p.scale && ok) ? __ldg(p.scale + cbase + e) : 1.f;
+          sc[e] = ((p.scale && ok) ? __ldg(p.scale + cbase + e) : 1.f) * p.gain;
           bi[e] = (p.bias && ok) ? __ldg(p.bias + cbase + e) : 0.f;
         }
         const int a_ = (cbase < act_end) ? p.act : PW_ACT_NONE;     // act_end % 4 == 0
@@ -948,6 +947,8 @@ int launch_halo(HaloPlan plan /* copy: per-launch fields are filled here */,
   p.out_ld = d->out_ld; p.res_ld = d->res_ld; p.act = d->act; p.act_channels = d->act_channels;
   p.scale = scale; p.bias = bias; p.res = residual; p.y = y;
   p.dbg = knobs().dbg;
+  // one accumulator column receives n_taps * chunks * 4 / nacc dependent MMAs of K = 8
+  p.gain = umma_chain_gain((long long)p.n_taps * p.chunks * BLOCK_K / p.nacc);
   cudaStream_t st = (cudaStream_t)stream;
 
   CUtensorMap ma, mbh, mbl;

@@ -45,6 +45,7 @@ struct UmmaParams {
   int n_tile;                  // N per CTA (multiple of 16, <= 256)
   int stages;
   int out_ld, res_ld, act, act_channels;
+  float gain;                  // pwtc::umma_chain_gain(): accumulator truncation bias
   const float* scale;
   const float* bias;
   const float* res;
@@ -269,13 +270,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
       for (int j = 0; j < A_BYTES / 16 / NUM_SPLIT_THREADS; ++j) {
         const int idx = threadIdx.x + j * NUM_SPLIT_THREADS;
         float4 v = a_hi[idx];
-        float4 h;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        float4 h, l;
+        pwtc::split2_rn(v.x, v.y, h.x, h.y, l.x, l.y);     // round-to-nearest split (tc_ptx.cuh)
+        pwtc::split2_rn(v.z, v.w, h.z, h.w, l.z, l.w);
         a_hi[idx] = h;
-        a_lo[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        a_lo[idx] = l;
       }
       // generic-proxy writes -> visible to the tensor core (async proxy)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -311,7 +310,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a,
       for (int j = 0; j < 16; ++j) {
         const int c = cbase + j;
         if (c < p.cout) {
-          const float sc = p.scale ? __ldg(p.scale + c) : 1.f;
+          const float sc = (p.scale ? __ldg(p.scale + c) : 1.f) * p.gain;
           const float bi = p.bias ? __ldg(p.bias + c) : 0.f;
           v[j] = fmaf(v[j], sc, bi);
         }
@@ -450,6 +449,7 @@ PW_API int pw_conv_umma_fwd(const pw_conv_desc* d, const float* x, const float* 
   p.out_ld = c.out_ld; p.res_ld = c.res_ld; p.act = c.act; p.act_channels = c.act_channels;
   p.scale = scale; p.bias = bias; p.res = residual; p.y = y;
   const long long K = KT * BLOCK_K;
+  p.gain = pwtc::umma_chain_gain(K);      // the main accumulator takes K / 8 dependent MMAs
 
   // ---- tensor maps -----------------------------------------------------------
   CUtensorMap ma, mbh, mbl;

@@ -34,6 +34,39 @@ __device__ __forceinline__ void sub2(float ax, float ay, float bx, float by, flo
   asm("mov.b64 {%0, %1}, %2;" : "=f"(rx), "=f"(ry) : "l"(r));
 }
 
+// Round-to-nearest 3xTF32 split of two fp32 values (Veltkamp / Dekker, 13 of 24 bits):
+//   t = x * 2^13 (exact);  c = fl(x + t);  hi = c - t  -> x rounded to nearest(-even)
+//   at 11 significant bits, i.e. a tf32 value;  lo = x - hi  (exact, |lo| <= 2^-11 |x|).
+// Written with the power-of-two product so that ptxas' mul+add -> FFMA2 contraction
+// cannot change the result (the textbook form c = x * (2^13 + 1) is contracted into
+// fma(x, 8193, -x) and returns hi = x).  Four packed fp32x2 instructions for two
+// elements.  A truncating split (hi = bits & 0xFFFFE000) leaves lo up to 2x larger
+// and one-sided, and the tensor core then TRUNCATES lo to tf32: a sign-correlated
+// bias of ~3e-7 per layer (tools/accuracy_probe.py); with the rounded hi it is < 3e-8.
+__device__ __forceinline__ void split2_rn(float ax, float ay, float& hx, float& hy, float& lx,
+                                          float& ly) {
+  unsigned long long a, k, t, c, h, l;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(ax), "f"(ay));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(k) : "f"(8192.0f));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(a), "l"(k));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(t));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(h) : "l"(c), "l"(t));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(l) : "l"(a), "l"(h));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(hx), "=f"(hy) : "l"(h));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lx), "=f"(ly) : "l"(l));
+}
+
+// The tensor core's fp32 accumulation is not round-to-nearest: every
+// tcgen05.mma (K = 8 for kind::tf32) aligns its addends to the largest exponent
+// with two guard bits and TRUNCATES the sum toward zero (measured with crafted
+// inputs, tools/accuracy_probe.py / profiles/r02_accuracy.md).  Over a chain of
+// K/8 accumulating MMAs that is a multiplicative shrink of the result,
+// measured -1.85e-9 * K (+-10 %) on the path's layer shapes; the epilogues
+// multiply the accumulator by this gain to remove its expectation.
+__host__ __device__ __forceinline__ float umma_chain_gain(long long k_per_chain) {
+  return 1.0f + 1.85e-9f * (float)k_per_chain;
+}
+
 // ---- mbarrier ----------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));

@@ -72,6 +72,19 @@ def from_logical(t):
 
 
 # --------------------------------------------------------------------- conv
+def split_tf32(w):
+    """fp32 -> (hi, lo) tf32 pair of the 3xTF32 tensor-core kernels, both
+    ROUNDED to nearest (ties away): hi = rna_tf32(w), lo = rna_tf32(w - hi).
+    The tensor core truncates its operands to tf32, so un-rounded parts would
+    carry a one-sided error (see csrc/tc_ptx.cuh:split2_rn)."""
+    def rna(t):
+        return ((t.contiguous().view(torch.int32) + 0x1000) & -8192) \
+            .view(torch.float32)
+    w = w.contiguous().float()
+    hi = rna(w)
+    return hi.contiguous(), rna(w - hi).contiguous()
+
+
 class PackedConv:
     """Weights of one conv/linear in the kernel's layout: w [K, w_ld] with
     K = taps*cin_pad (tap-major), plus the folded per-channel affine."""
@@ -163,10 +176,7 @@ class PackedConv:
     def set_umma_weights(self, wt):
         """wt [cout, K] (K-major, tap-major then cin): pre-split for the
         3xTF32 tensor-core path (pw_conv_umma_fwd)."""
-        wt = wt.contiguous().float()
-        hi = (wt.view(torch.int32) & -8192).view(torch.float32)   # 0xFFFFE000
-        self.wt_hi = hi.contiguous()
-        self.wt_lo = (wt - hi).contiguous()
+        self.wt_hi, self.wt_lo = split_tf32(wt)
 
 
     def set_fold_weights(self, w5):
@@ -180,9 +190,7 @@ class PackedConv:
         wp[:cout] = w5
         wf = wp.view(slabs, fold_n, cin, kd, kh, kw).permute(0, 5, 1, 3, 4, 2) \
             .reshape(slabs * kw * fold_n, kd * kh * cin).contiguous()
-        hi = (wf.view(torch.int32) & -8192).view(torch.float32)
-        self.wf_hi = hi.contiguous()
-        self.wf_lo = (wf - hi).contiguous()
+        self.wf_hi, self.wf_lo = split_tf32(wf)
 
 
 # The tensor-core path is used whenever the layer qualifies; set to False to

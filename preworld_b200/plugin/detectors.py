@@ -590,6 +590,21 @@ class PreWorld(BEVStereo4DOCC):
         self._graph_cache = {}
         return self
 
+    # A captured graph bakes in the packed weights (and the lift workspace) of the
+    # moment of capture: it is only valid for the parameter tensors it was captured
+    # with, at the versions they had.  ``.to()`` / ``.cuda()`` (-> _apply) replace
+    # the tensors, ``load_state_dict`` / in-place updates bump their versions.
+    def _apply(self, fn, *a, **k):
+        if getattr(self, '_graph_cache', None):
+            self._graph_cache = {}
+        return super()._apply(fn, *a, **k)
+
+    def _weights_version(self, tensors):
+        v = 0
+        for t in tensors:
+            v += t._version
+        return v
+
     def _occupancy_dev(self, vf_cl):
         if self.if_post_finetune:
             return (self._occ_pair_from_head(vf_cl),)
@@ -643,8 +658,12 @@ class PreWorld(BEVStereo4DOCC):
                     g_stem[k].replay()
 
         # the images start moving before anything else happens on the host
-        key = tuple(tuple(t.shape) for t in img[:7])
+        key = (dev,) + tuple(tuple(t.shape) for t in img[:7])
         entry = self._graph_cache.get(key)
+        if entry is not None and \
+                self._weights_version(entry[9]) != entry[10]:
+            del self._graph_cache[key]           # weights changed since capture
+            entry = None
         if entry is not None:
             upload_and_stem(entry[2], entry[3], entry[4], entry[5], entry[0])
         if trace is not None:
@@ -721,9 +740,10 @@ class PreWorld(BEVStereo4DOCC):
             g_main = torch.cuda.CUDAGraph()
             with torch.no_grad(), torch.cuda.graph(g_main):
                 out_s = body(frames_s, l1_s, flat_s)
+            weights = list(self.parameters()) + list(self.buffers())
             entry = self._graph_cache[key] = (
                 g_stem, g_main, frames_s, l1_s, copy_stream, landed, packed_s,
-                packed_h, out_s)
+                packed_h, out_s, weights, self._weights_version(weights))
         g_main, packed_s, packed_h, out_s = entry[1], entry[6], entry[7], entry[8]
         self._pack_poses(flat, packed_h, packed_s)
         g_main.replay()

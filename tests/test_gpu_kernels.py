@@ -85,8 +85,10 @@ def test_conv_matches_torch_fp32(case, conv_path):
     got = ops.conv(x_cl.to(DEV), pc, act, residual=r_cl)
     got = ops.to_logical(got).cpu()
     assert got.shape == want.shape
-    # fp32 FMA accumulation in a different order than the CPU reference
-    assert _rel(got, want) < 2e-5, _rel(got, want)
+    # fp32 accumulation in a different order than the CPU reference; on the
+    # tensor-core path the MMA's truncating accumulator leaves ~1e-6 rms / 6e-6
+    # max at K = 4608 after the gain correction (tools/accuracy_probe.py)
+    assert _rel(got, want) < 8e-6, _rel(got, want)
 
 
 FOLD_CASES = [
@@ -129,8 +131,8 @@ def test_conv_fold_matches_torch_and_halo(case):
         finally:
             ops.USE_FOLD, ops.FOLD_AUTO_COUT = old
         assert _lib.launch_count() == n0 + 1
-    assert _rel(got[True], want) < 2e-5, _rel(got[True], want)
-    assert _rel(got[True], got[False]) < 2e-5
+    assert _rel(got[True], want) < 8e-6, _rel(got[True], want)
+    assert _rel(got[True], got[False]) < 8e-6
     # the folded path really was the one taken
     sp3 = (1,) * (3 - dims) + tuple(sp)
     k3 = (1,) * (3 - dims) + (k,) * dims

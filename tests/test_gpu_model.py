@@ -67,15 +67,23 @@ def _check_samples(fx, st, name):
     return worst
 
 
-def _margin_ok(occ, want, logits_ref):
-    """Every argmax mismatch must sit on a near tie of the oracle logits."""
+def _margin_ok(occ, want, logits_ref, tol=REL_TOL, verbose=False):
+    """Every argmax mismatch must sit on a near tie of the oracle logits: top-2
+    margin below ``tol`` x max|logit|."""
     bad = np.argwhere(occ != want)
     lg = logits_ref[0].permute(1, 2, 3, 0).numpy()          # [X,Y,Z,18]
     scale = np.abs(lg).max()
+    worst = 0.0
     for x, y, z in bad:
         top2 = np.sort(lg[x, y, z])[-2:]
-        assert top2[1] - top2[0] < REL_TOL * scale, \
-            ((x, y, z), top2, occ[x, y, z], want[x, y, z])
+        margin = float(top2[1] - top2[0]) / scale
+        worst = max(worst, margin)
+        if verbose:
+            print(f'   voxel ({x},{y},{z}): got {occ[x, y, z]} want {want[x, y, z]} '
+                  f'top-2 margin {margin:.2e} of max|logit|')
+        assert margin < tol, ((x, y, z), top2, occ[x, y, z], want[x, y, z])
+    if verbose and len(bad):
+        print(f'   largest top-2 margin among the {len(bad)} flips: {worst:.2e}')
     return len(bad)
 
 
@@ -214,19 +222,24 @@ def test_full_size_finetune_matches_reference(golden_dir):
     assert occ.shape == (200, 200, 16)
     n_bad = int((occ != want).sum())
     print('full_finetune argmax mismatches vs reference fixture:', n_bad)
-    assert n_bad <= 128                       # 2e-4 of 640 000 voxels
+    # round 2 (round-to-nearest split + accumulator-truncation gain):
+    # 18 of 640 000; strict-fp32 cuDNN gives 1, torch's default TF32 cuDNN 3196
+    # (test_reference_arithmetic_on_gpu_floor)
+    assert n_bad <= 32
     # every mismatch must be a near tie of the oracle's logits (top-2 margin
     # below the 1e-3 float tolerance); the oracle runs here in ~5-15 s
     pc = torch_ref.PathConfig(model_cfg_for(case))
     ost = {}
     with torch.no_grad():
         want_o = torch_ref.preworld_simple_test(sd, pc, inputs, ost)
-    n_o = _margin_ok(occ, want_o['semantic_occ'][0], ost['logits'])
     err = (st['logits'].cpu() - ost['logits']).abs().max().item() \
         / ost['logits'].abs().max().item()
+    # a flip needs the two leading logits closer than twice the logit error
+    n_o = _margin_ok(occ, want_o['semantic_occ'][0], ost['logits'],
+                     tol=2.0 * 1e-4, verbose=True)
     print(f'full_finetune vs oracle: {n_o} near-tie voxels differ, '
           f'logits max rel err {err:.2e}')
-    assert err < REL_TOL
+    assert err < 1e-4                         # north_star bar: 1e-3
     # size-independent properties
     assert ((out['geo_occ'][0] == 0) == (occ != 17)).all()
     with torch.no_grad():
@@ -236,6 +249,80 @@ def test_full_size_finetune_matches_reference(golden_dir):
     assert lifted.shape == (1, 32, 16, 200, 200)
     nz = (lifted.abs().sum(1) > 0).float().mean().item()
     assert 0.15 < nz < 0.35                   # ~142k of 640k voxels non-empty
+
+
+def _oracle_with_gpu_convs(sd, pc, inputs, allow_tf32):
+    """The CPU oracle with ONLY its conv / linear calls evaluated by cuDNN /
+    cuBLAS on the GPU (everything else stays on the CPU): what the reference's
+    own arithmetic gives when its convolutions run on a GPU, in strict fp32 or
+    with torch's default TF32 convolutions."""
+    import torch.nn.functional as F
+    o_conv, o_lin = torch_ref._conv, torch_ref._linear
+    sd_dev = {k: v.cuda() for k, v in sd.items() if v.is_floating_point()}
+
+    def conv(sd_, p, x, stride=1, padding=0, dilation=1):
+        w = sd_dev[p + '.weight']
+        f = F.conv3d if w.dim() == 5 else F.conv2d
+        return f(x.cuda(), w, sd_dev.get(p + '.bias'), stride, padding, dilation).cpu()
+
+    def lin(sd_, p, x):
+        return F.linear(x.cuda(), sd_dev[p + '.weight'], sd_dev.get(p + '.bias')).cpu()
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = allow_tf32
+    torch_ref._conv, torch_ref._linear = conv, lin
+    try:
+        st = {}
+        with torch.no_grad():
+            out = torch_ref.preworld_simple_test(sd, pc, inputs, st)
+    finally:
+        torch_ref._conv, torch_ref._linear = o_conv, o_lin
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return out, st
+
+
+@pytest.mark.timeout(900)
+def test_reference_arithmetic_on_gpu_floor(golden_dir):
+    """What 'bit-exact argmax against the CPU fixture' can mean on a GPU: the
+    reference's own path with its convolutions evaluated by cuDNN (strict fp32,
+    and torch's default TF32) differs from the CPU fixture too.  Reported next to
+    this library's result (gpurun_out/argmax_floor.json -> profiles/)."""
+    import json
+    case = CASES['full_finetune']
+    fx = np.load(os.path.join(golden_dir, 'full_finetune.npz'))
+    want = fx['out/semantic_occ']
+    model = _model(case)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    inputs, _ = build_case_inputs(case)
+    pc = torch_ref.PathConfig(model_cfg_for(case))
+    ost = {}
+    with torch.no_grad():
+        torch_ref.preworld_simple_test(sd, pc, inputs, ost)
+    ref_logits = ost['logits']
+    scale = ref_logits.abs().max().item()
+    report = {}
+    for name, tf32 in (('cudnn_fp32', False), ('cudnn_tf32_default', True)):
+        out, st = _oracle_with_gpu_convs(sd, pc, inputs, tf32)
+        report[name] = {
+            'argmax_mismatch_vs_cpu_fixture': int((out['semantic_occ'][0] != want).sum()),
+            'logits_max_rel_err_vs_cpu_oracle':
+                (st['logits'] - ref_logits).abs().max().item() / scale}
+    model = model.cuda()
+    dev_inputs = tuple(t.cuda() for t in inputs)
+    with torch.no_grad():
+        _, st = _run_stages(model, dev_inputs)
+        out = model.simple_test(None, None, img=dev_inputs)
+    report['preworld_b200'] = {
+        'argmax_mismatch_vs_cpu_fixture': int((out['semantic_occ'][0] != want).sum()),
+        'logits_max_rel_err_vs_cpu_oracle':
+            (st['logits'].cpu() - ref_logits).abs().max().item() / scale}
+    print('argmax floor (640000 voxels):', json.dumps(report))
+    os.makedirs('gpurun_out', exist_ok=True)
+    with open('gpurun_out/argmax_floor.json', 'w') as f:
+        json.dump(report, f, indent=1)
+    # this library must be at least as close to the CPU fixture as the
+    # reference's own default GPU arithmetic (TF32 convolutions)
+    assert report['preworld_b200']['argmax_mismatch_vs_cpu_fixture'] <= \
+        report['cudnn_tf32_default']['argmax_mismatch_vs_cpu_fixture']
 
 
 @pytest.mark.parametrize('name', ['tiny_finetune', 'tiny_pretrain'])
@@ -272,3 +359,32 @@ def test_cuda_graph_replay_equals_eager(name):
                         img_inputs=[tuple(t.pin_memory() for t in s)],
                         img_metas=[None])
             assert np.array_equal(out['semantic_occ'][0], want[0])
+
+
+def test_cuda_graph_follows_weight_updates():
+    """a captured graph bakes in the packed weights.  After
+    load_state_dict() with other weights (or .to()), the public call must give
+    the eager result for the NEW weights, not replay the old ones."""
+    case = CASES['tiny_finetune']
+    model = _model(case).cuda()
+    s = build_case_inputs(case)[0]
+    call = lambda: model(return_loss=False,
+                         img_inputs=[tuple(t.cuda() for t in s)],
+                         img_metas=[None])['semantic_occ'][0]
+    model.enable_cuda_graph()
+    with torch.no_grad():
+        first = call()
+        other = build_model(model_cfg_for(case)).eval()
+        S.lively_init_(other, case['seed'] + 11)
+        model.load_state_dict(other.state_dict())
+        graphed = call()
+        model.enable_cuda_graph(False)
+        eager = call()
+    assert not np.array_equal(first, eager)          # the weights do matter
+    assert np.array_equal(graphed, eager)
+    model.enable_cuda_graph()
+    with torch.no_grad():
+        call()
+        model.float()                                # _apply drops the captures
+        assert len(model._graph_cache) == 0
+        assert np.array_equal(call(), eager)
