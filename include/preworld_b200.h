@@ -108,6 +108,48 @@ int pw_conv_fold_fwd(const pw_conv_desc* desc, const float* x,
                      void* stream);
 
 /* ------------------------------------------------------------------------
+ * Fused per-voxel heads (pw_attr_mlp, pw_fusion_step,
+ * pw_occhead_argmax).
+ * ---------------------------------------------------------------------- */
+/* Fused two-layer per-row MLP on the tensor cores (tcgen05 kind::tf32, 3xTF32
+ * split, fp32-level accuracy):
+ *     y[r, 0:n2] = act2(W2 . act1(W1 . x[r, 0:c1] + b1) + b2) [+ residual[r, 0:n2]]
+ * The hidden row (`hidden` wide) never leaves the SM.  One call replaces
+ *  - the forecasting step of detectors/preworld_temporal_traj.py:329-341,368
+ *    (fusion_head = Linear(64,128)-Softplus-Linear(128,32) on cat([voxel, ego]) +
+ *    residual): W1 = fusion_head[0].weight[:, :32], b1 = the per-sample bias
+ *    fusion_head[0].weight[:, 32:] . plan_head(ego) + fusion_head[0].bias,
+ *    residual = x;
+ *  - the attribute projection of detectors/preworld.py:81-105,251-254
+ *    (density / semantic / color MLPs, each Linear(32,64)-Softplus-Linear(64,k)):
+ *    W1 = the three first layers stacked [192, 32], W2 = block diagonal [24, 192],
+ *    act2 = Softplus on the first act2_channels = 2 (density) channels.
+ * c1 == 32; hidden % 32 == 0, <= 256; n2 % 4 == 0, <= 32.  w1_hi / w1_lo
+ * [hidden, c1] and w2_hi / w2_lo [n2p, hidden] (n2p = 16 if n2 <= 16 else 32, rows
+ * >= n2 zero) are the K-major weights pre-split into rounded tf32 hi / lo parts;
+ * b1 [hidden], b2 [n2] may be NULL.  act2 applies to channels [0, act2_channels).
+ * x / residual / y are row arrays with pitches x_ld / res_ld / y_ld (multiples of
+ * 4, 16-byte aligned); y may alias residual but not x. */
+int pw_mlp2_supported(int c1, int hidden, int n2);
+int pw_mlp2(const float* x, int x_ld, long long m, int c1, const float* w1_hi,
+            const float* w1_lo, const float* b1, int hidden, int act1,
+            const float* w2_hi, const float* w2_lo, const float* b2, int n2, int act2,
+            int act2_channels, const float* residual, int res_ld, float* y, int y_ld,
+            void* stream);
+/* OccHead tail (heads/occupancy_head.py:95-105,147-162 + detectors/preworld.py:
+ * 196-221), fused: feat [zyx voxels, feat_ld] = the 16-channel output of
+ * occ_convs[0] (conv3^3 + BN + ReLU) in the library's [Z,Y,X] voxel order ->
+ * relu(scale0 * (w0 . feat) + bias0) [mid = 8] -> w1 . h + bias1 [ncls] -> argmax
+ * (first maximum wins) -> occ uint8 [X,Y,Z]; geo (may be NULL) = (class !=
+ * free_idx) ? 0 : geo_value; logits (may be NULL) [zyx voxels, logits_ld] receives
+ * the class logits.  w0 [mid, cin], w1 [ncls, mid] row-major. */
+int pw_occhead_tail(const float* feat, int feat_ld, int cin, const float* w0,
+                    const float* scale0, const float* bias0, int mid, const float* w1,
+                    const float* bias1, int ncls, float* logits, int logits_ld,
+                    unsigned char* occ, unsigned char* geo, int free_idx, int geo_value,
+                    int gx, int gy, int gz, void* stream);
+
+/* ------------------------------------------------------------------------
  * Image-side element-wise helpers (all channels-last).
  * ---------------------------------------------------------------------- */
 /* imgs [n,c,h,w] (NCHW as delivered by the loader, loading.py:1124-1134;

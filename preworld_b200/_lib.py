@@ -53,6 +53,12 @@ SIGNATURES = {
     'pw_conv_fold_supported': [ctypes.POINTER(ConvDesc)],
     'pw_conv_fold_fwd': [ctypes.POINTER(ConvDesc), c_p, c_p, c_p, c_p, c_p,
                          c_p, c_p, c_p],
+    'pw_mlp2_supported': [c_int, c_int, c_int],
+    'pw_mlp2': [c_p, c_int, c_ll, c_int, c_p, c_p, c_p, c_int, c_int, c_p, c_p,
+                c_p, c_int, c_int, c_int, c_p, c_int, c_p, c_int, c_p],
+    'pw_occhead_tail': [c_p, c_int, c_int, c_p, c_p, c_p, c_int, c_p, c_p, c_int,
+                        c_p, c_int, c_p, c_p, c_int, c_int, c_int, c_int, c_int,
+                        c_p],
     'pw_nchw_to_nhwc_pad': [c_p, c_ll, c_p, c_int, c_int, c_int, c_int, c_int,
                             c_p],
     'pw_nchw_to_s2d_nhwc': [c_p, c_ll, c_p, c_int, c_int, c_int, c_int, c_int,

@@ -282,6 +282,87 @@ def linear(x2d, pc, act=None, residual=None, out=None):
     return y[:, 0, :]
 
 
+# ------------------------------------------------------- fused per-voxel MLP
+class PackedMlp2:
+    """Weights of ``pw_mlp2``: y = act2(W2 . act1(W1 . x + b1) + b2) [+ res].
+    w1 [H, 32], w2 [n2, H] (torch Linear layout).  H is padded to a multiple of
+    32 and n2 to a multiple of 4 with zero weights (padded outputs are
+    act2(0 + 0))."""
+    __slots__ = ('w1_hi', 'w1_lo', 'b1', 'w2_hi', 'w2_lo', 'b2', 'c1', 'hidden',
+                 'n2', 'act1', 'act2', 'act2_channels')
+
+    def __init__(self, w1, b1, w2, b2, act1='softplus', act2=None,
+                 act2_channels=0):
+        w1, w2 = w1.detach().float(), w2.detach().float()
+        h, c1 = w1.shape
+        n2 = w2.shape[0]
+        assert w2.shape[1] == h and c1 == 32
+        hp, n2r = -(-h // 32) * 32, -(-n2 // 4) * 4
+        n2p = 16 if n2r <= 16 else 32
+        dev = w1.device
+        w1p = torch.zeros((hp, c1), device=dev)
+        w1p[:h] = w1
+        w2p = torch.zeros((n2p, hp), device=dev)
+        w2p[:n2, :h] = w2
+        self.w1_hi, self.w1_lo = split_tf32(w1p)
+        self.w2_hi, self.w2_lo = split_tf32(w2p)
+        b1p = torch.zeros(hp, device=dev)
+        if b1 is not None:
+            b1p[:h] = b1.detach().float()
+        # a padded hidden unit is act1(0): its W2 column is zero, so it adds nothing
+        self.b1 = b1p.contiguous()
+        b2p = torch.zeros(n2r, device=dev)
+        if b2 is not None:
+            b2p[:n2] = b2.detach().float()
+        self.b2 = b2p.contiguous()
+        self.c1, self.hidden, self.n2 = c1, hp, n2r
+        self.act1, self.act2, self.act2_channels = act1, act2, act2_channels
+
+
+def mlp2(rows, pm, bias1=None, residual=None, out=None):
+    """rows [M, 32] (row pitch = rows.stride(0)) -> [M, pm.n2] through ONE fused
+    tensor-core launch.  ``bias1`` overrides pm.b1 (per-sample bias)."""
+    _require_cuda(rows, residual, out, bias1)
+    m, c1 = rows.shape
+    assert c1 == pm.c1 and rows.stride(1) == 1 and rows.dtype == torch.float32
+    if out is None:
+        out = torch.empty((m, pm.n2), device=rows.device, dtype=torch.float32)
+    assert out.shape == (m, pm.n2) and out.stride(1) == 1
+    b1 = pm.b1
+    if bias1 is not None:
+        b1 = bias1.contiguous().float()
+        assert b1.numel() == pm.hidden
+    if residual is not None:
+        assert residual.shape == out.shape and residual.stride(1) == 1
+    check(_lib.lib().pw_mlp2(
+        _ptr(rows), rows.stride(0), m, c1, _ptr(pm.w1_hi), _ptr(pm.w1_lo),
+        _ptr(b1), pm.hidden, ACT[pm.act1], _ptr(pm.w2_hi), _ptr(pm.w2_lo),
+        _ptr(pm.b2), pm.n2, ACT[pm.act2], pm.act2_channels, _ptr(residual),
+        residual.stride(0) if residual is not None else 0, _ptr(out),
+        out.stride(0), _stream()), 'pw_mlp2')
+    return out
+
+
+def occhead_tail(feat_cl, w0, s0, b0, w1, b1, free_idx, geo_value, out=None,
+                 want_logits=False):
+    """feat_cl [1,Z,Y,X,16] (output of occ_convs[0]) -> uint8 [2,X,Y,Z]
+    (class argmax, geometry grid) [+ logits cl array [1,Z,Y,X,ncls]]."""
+    _require_cuda(feat_cl, w0, w1)
+    _, gz, gy, gx, cin = feat_cl.shape
+    ncls, mid = w1.shape
+    if out is None:
+        out = torch.empty((2, gx, gy, gz), device=feat_cl.device, dtype=torch.uint8)
+    assert out.shape == (2, gx, gy, gz) and out.is_contiguous() and \
+        out.dtype == torch.uint8
+    logits = torch.empty((1, gz, gy, gx, ncls), device=feat_cl.device,
+                         dtype=torch.float32) if want_logits else None
+    check(_lib.lib().pw_occhead_tail(
+        _ptr(feat_cl), cl_ld(feat_cl), cin, _ptr(w0), _ptr(s0), _ptr(b0), mid,
+        _ptr(w1), _ptr(b1), ncls, _ptr(logits), ncls, _ptr(out[0]), _ptr(out[1]),
+        int(free_idx), int(geo_value), gx, gy, gz, _stream()), 'pw_occhead_tail')
+    return (out, logits) if want_logits else out
+
+
 # ---------------------------------------------------------------- image side
 def nchw_to_nhwc(x, c_pad=None, out=None):
     """x [n,c,h,w]: each image dense NCHW; images may be strided (a frame

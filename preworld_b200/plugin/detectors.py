@@ -507,9 +507,21 @@ class PreWorld(BEVStereo4DOCC):
 
     def _build_packs(self):
         P = super()._build_packs()
-        P['density'] = _pack_mlp(self.density_mlp)
-        P['semantic'] = _pack_mlp(self.semantic_mlp)
-        P['color'] = _pack_mlp(self.color_mlp)
+        mlps = (self.density_mlp, self.semantic_mlp, self.color_mlp)
+        hid = [m[0].out_features for m in mlps]
+        outs = [m[2].out_features for m in mlps]             # 2, 17, 3
+        w1 = torch.cat([m[0].weight for m in mlps], 0)       # [192, 32]
+        b1 = torch.cat([m[0].bias for m in mlps], 0)
+        w2 = torch.zeros((24, sum(hid)), device=w1.device)   # block diagonal
+        b2 = torch.zeros(24, device=w1.device)
+        r = c = 0
+        for m, h, o in zip(mlps, hid, outs):
+            w2[r:r + o, c:c + h] = m[2].weight
+            b2[r:r + o] = m[2].bias
+            r, c = r + o, c + h
+        P['attr'] = ops.PackedMlp2(
+            w1, b1, w2, b2, act1='softplus',
+            act2='softplus' if self.final_softplus else None, act2_channels=2)
         return P
 
     # -- attribute projection (preworld.py:81-105,173-176,251-254) -----------
@@ -518,19 +530,12 @@ class PreWorld(BEVStereo4DOCC):
         [B,Z,Y,X,24]: channel 0-1 density (after the final Softplus),
         2-18 semantic, 19-21 colour."""
         P = self.packs()
-        ns = self.num_classes - 1
         rows = vf_cl.reshape(-1, vf_cl.shape[-1])
         attr = torch.empty((rows.shape[0], 24), device=vf_cl.device,
                            dtype=torch.float32)
-        h = ops.linear(rows, P['density'][0], 'softplus')
-        ops.linear(h, P['density'][1],
-                   'softplus' if self.final_softplus else None,
-                   out=attr[:, 0:2])
-        h = ops.linear(rows, P['semantic'][0], 'softplus')
-        ops.linear(h, P['semantic'][1], out=attr[:, 2:2 + ns])
-        if with_color:
-            h = ops.linear(rows, P['color'][0], 'softplus')
-            ops.linear(h, P['color'][1], out=attr[:, 2 + ns:5 + ns])
+        # ONE fused launch (pw_mlp2): the three 64-wide hidden rows stay on the SM;
+        # the colour head is computed either way (9 % of the arithmetic)
+        ops.mlp2(rows, P['attr'], out=attr)
         return attr.view(*vf_cl.shape[:-1], 24)
 
     def _occ_from_density(self, vf_cl):
@@ -549,12 +554,12 @@ class PreWorld(BEVStereo4DOCC):
         occ = ops.argmax_zyx_to_xyz(logits)
         return occ, logits
 
-    def _occ_pair_from_head(self, vf_cl):
+    def _occ_pair_from_head(self, vf_cl, out=None):
         """preworld.py:196-221 (nuScenes) in one kernel and one buffer:
         uint8 [2,X,Y,Z] = (argmax class, geo_occ = num_classes-1 where the
         class is 17 else 0), both computed on the device as in the reference."""
-        logits = self.occupancy_head.logits_cl(vf_cl[:1], True)
-        return ops.argmax_geo_zyx_to_xyz(logits, 17, self.num_classes - 1)
+        return self.occupancy_head.occupancy_pair_cl(
+            vf_cl[:1], 17, self.num_classes - 1, out=out)
 
     @staticmethod
     def _to_numpy_pair(occ_dev, geo_dev=None):
@@ -577,6 +582,17 @@ class PreWorld(BEVStereo4DOCC):
             vf = self.voxel_features_cl(img, **kwargs)
             occ, geo_occ = self.occupancy(vf)
         return {'semantic_occ': [occ], 'geo_occ': [geo_occ]}
+
+    # hooks of the graph route (PreWorld4DTraj overrides them)
+    def _occupancy_dev(self, vf_cl, extra=()):
+        """Device-side tail of simple_test on the voxel features: a tuple of
+        device tensors that ``_host_result`` turns into the host result."""
+        if self.if_post_finetune:
+            return (self._occ_pair_from_head(vf_cl),)
+        return self._occ_from_density(vf_cl)
+
+    def _host_result(self, out_dev):
+        return self._to_numpy_pair(*out_dev)
 
     # -- CUDA-graph replay of the whole forward ----------------------------------
     def enable_cuda_graph(self, enabled=True):
@@ -605,12 +621,7 @@ class PreWorld(BEVStereo4DOCC):
             v += t._version
         return v
 
-    def _occupancy_dev(self, vf_cl):
-        if self.if_post_finetune:
-            return (self._occ_pair_from_head(vf_cl),)
-        return self._occ_from_density(vf_cl)
-
-    def _graphed_occupancy(self, img):
+    def _graphed_occupancy(self, img, extra=()):
         """Host tensors (the loader's CPU batch, ideally pinned) take the short
         route.  The images cross PCIe chunk by chunk (the first frame in pairs
         of cameras, then whole frames) on a copy stream, straight from the
@@ -658,7 +669,9 @@ class PreWorld(BEVStereo4DOCC):
                     g_stem[k].replay()
 
         # the images start moving before anything else happens on the host
-        key = (dev,) + tuple(tuple(t.shape) for t in img[:7])
+        extra = [t.float() for t in extra]       # e.g. ego states [B,1,21]
+        key = (dev,) + tuple(tuple(t.shape) for t in img[:7]) + \
+            tuple(tuple(t.shape) for t in extra)
         entry = self._graph_cache.get(key)
         if entry is not None and \
                 self._weights_version(entry[9]) != entry[10]:
@@ -692,7 +705,7 @@ class PreWorld(BEVStereo4DOCC):
                     out.append(list(ts[i:i + n])); i += n
             return out
 
-        def body(frames_s, l1_s, flat_s):
+        def body(frames_s, l1_s, flat_s, extra_s):
             self._stereo_batch = l1_s
             try:
                 img_feats, _ = self.extract_img_feat(
@@ -701,7 +714,7 @@ class PreWorld(BEVStereo4DOCC):
                 self._stereo_batch = None
             vf = ops.conv(ops.from_logical(img_feats[0]), self.packs()['final'],
                           'relu')
-            return self._occupancy_dev(vf)
+            return self._occupancy_dev(vf, extra_s)
 
         if entry is None:
             frames_s = [torch.empty((B, N, C, H, W), device=dev, dtype=torch.float32)
@@ -719,6 +732,10 @@ class PreWorld(BEVStereo4DOCC):
                               if t is not None else None)
                 o += n
             self._pack_poses(flat, packed_h, packed_s)
+            extra_s = [torch.empty(t.shape, device=dev, dtype=torch.float32)
+                       for t in extra]
+            for d_, s_ in zip(extra_s, extra):
+                d_.copy_(s_, non_blocking=True)
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(main)
             with torch.cuda.stream(side), torch.no_grad():
@@ -728,7 +745,7 @@ class PreWorld(BEVStereo4DOCC):
                                    dtype=torch.float32)
                 for k in range(len(chunks)):
                     stem_chunk(frames_s, l1_s, k)
-                body(frames_s, l1_s, flat_s)
+                body(frames_s, l1_s, flat_s, extra_s)
             main.wait_stream(side)
             torch.cuda.synchronize(dev)
             g_stem = []
@@ -739,17 +756,20 @@ class PreWorld(BEVStereo4DOCC):
                 g_stem.append(g)
             g_main = torch.cuda.CUDAGraph()
             with torch.no_grad(), torch.cuda.graph(g_main):
-                out_s = body(frames_s, l1_s, flat_s)
+                out_s = body(frames_s, l1_s, flat_s, extra_s)
             weights = list(self.parameters()) + list(self.buffers())
             entry = self._graph_cache[key] = (
                 g_stem, g_main, frames_s, l1_s, copy_stream, landed, packed_s,
-                packed_h, out_s, weights, self._weights_version(weights))
+                packed_h, out_s, weights, self._weights_version(weights),
+                extra_s)
         g_main, packed_s, packed_h, out_s = entry[1], entry[6], entry[7], entry[8]
         self._pack_poses(flat, packed_h, packed_s)
+        for d_, s_ in zip(entry[11], extra):
+            d_.copy_(s_, non_blocking=True)
         g_main.replay()
         if trace is not None:
             trace.append(('graphs launched', time.perf_counter()))
-        res = self._to_numpy_pair(*out_s)
+        res = self._host_result(out_s)
         if trace is not None:
             trace.append(('result on host', time.perf_counter()))
         return res
@@ -816,48 +836,72 @@ class PreWorld4DTraj(PreWorld):
         # fusion_head[0] on cat([voxel, ego]) = W[:, :od] voxel + (W[:, od:]
         # ego + b): the ego half is a per-sample bias, so the [.., 64] concat
         # the reference materialises (164 MB/step) never exists.
-        P['fuse_vox'] = ops.PackedConv(f0.weight[:, :od], None)
         P['fuse_ego'] = ops.PackedConv(f0.weight[:, od:], f0.bias)
-        P['fuse_out'] = pack_linear(f2)
+        P['fuse_mlp'] = ops.PackedMlp2(f0.weight[:, :od], None, f2.weight,
+                                       f2.bias, act1='softplus')
         return P
 
-    def forecast_step(self, vf_cl, ego_states):
-        """preworld_temporal_traj.py:329-341,368: plan_head -> broadcast ->
-        cat -> fusion_head -> residual add."""
+    def ego_bias(self, ego_states, device):
+        """plan_head (21 -> 256 -> 256 -> 32, preworld_temporal_traj.py:119-123)
+        and the ego half of fusion_head[0] -> per-sample bias [B, 128].  Every
+        forecasting step feeds the same ``temporal_ego_states[0]`` (:331), so
+        this runs once per sample."""
         P = self.packs()
-        B = vf_cl.shape[0]
-        e = ego_states.reshape(B, -1).to(vf_cl.device).float()
+        e = ego_states.reshape(ego_states.shape[0], -1).to(device).float()
         e = torch.nn.functional.pad(e, (0, (-e.shape[1]) % 4)).contiguous()
         e = ops.linear(e, P['plan'][0], 'relu')
         e = ops.linear(e, P['plan'][1], 'relu')
         e = ops.linear(e, P['plan'][2])
-        ego_bias = ops.linear(e, P['fuse_ego'])              # [B, 128]
+        return ops.linear(e, P['fuse_ego'])                  # [B, 128]
+
+    def forecast_step(self, vf_cl, ego_states=None, ego_bias=None):
+        """preworld_temporal_traj.py:329-341,368: plan_head -> broadcast ->
+        cat -> fusion_head -> residual add, as ONE fused launch per sample
+        (pw_mlp2: the 128-wide hidden tile never leaves the SM)."""
+        P = self.packs()
+        if ego_bias is None:
+            ego_bias = self.ego_bias(ego_states, vf_cl.device)
         out = torch.empty_like(vf_cl)
-        for b in range(B):
-            rows = vf_cl[b].reshape(-1, vf_cl.shape[-1])
-            pc = P['fuse_vox']
-            step = ops.PackedConv.__new__(ops.PackedConv)
-            for k in ops.PackedConv.__slots__:
-                setattr(step, k, getattr(pc, k))
-            step.bias = ego_bias[b].contiguous()
-            h = ops.linear(rows, step, 'softplus')
-            ops.linear(h, P['fuse_out'], residual=rows,
-                       out=out[b].reshape(-1, vf_cl.shape[-1]))
+        C = vf_cl.shape[-1]
+        for b in range(vf_cl.shape[0]):
+            rows = vf_cl[b].reshape(-1, C)
+            ops.mlp2(rows, P['fuse_mlp'], bias1=ego_bias[b], residual=rows,
+                     out=out[b].reshape(-1, C))
         return out
+
+    def _occupancy_dev(self, vf_cl, extra=()):
+        """All 7 grids (current + 6 forecasts) on the device, in ONE uint8
+        buffer [7, 2, X, Y, Z] (semantic, geo) -> one device->host transfer."""
+        bias = self.ego_bias(extra[0], vf_cl.device)
+        _, gz, gy, gx, _ = vf_cl.shape
+        grids = torch.empty((7, 2, gx, gy, gz), device=vf_cl.device,
+                            dtype=torch.uint8)
+        for k in range(7):
+            if k:
+                vf_cl = self.forecast_step(vf_cl, ego_bias=bias)
+            if self.if_post_finetune:
+                self._occ_pair_from_head(vf_cl, out=grids[k])
+            else:
+                occ, geo = self._occ_from_density(vf_cl)
+                grids[k, 0].copy_(occ)
+                grids[k, 1].copy_(geo)
+        return (grids,)
+
+    def _host_result(self, out_dev):
+        g = out_dev[0].cpu().numpy()
+        first = 1 if self.if_post_finetune else 2     # preworld_temporal_traj.py:342-367
+        res = {'semantic_occ_0s': [g[0, 0]], 'geo_occ_0s': [g[0, 1]]}
+        for k in range(6):
+            res[f'semantic_occ_{k + first}s'] = [g[k + 1, 0]]
+            res[f'geo_occ_{k + first}s'] = [g[k + 1, 1]]
+        return res
 
     def simple_test(self, points, img_metas, img=None, rescale=False,
                     **kwargs):
         """preworld_temporal_traj.py:213-371.  Every forecasting step feeds
         ``temporal_ego_states[0]`` (:331), exactly as the reference does."""
+        ego = kwargs['temporal_ego_states'][0][0]
+        if getattr(self, '_graph_enabled', False) and len(kwargs) == 1:
+            return self._graphed_occupancy(img, extra=[ego])
         vf = self.voxel_features_cl(img)
-        temporal_ego_states = kwargs['temporal_ego_states'][0]
-        res = {}
-        occ, geo = self.occupancy(vf)
-        res['semantic_occ_0s'], res['geo_occ_0s'] = [occ], [geo]
-        first = 1 if self.if_post_finetune else 2
-        for k in range(6):
-            vf = self.forecast_step(vf, temporal_ego_states[0])
-            occ, geo = self.occupancy(vf)
-            res[f'semantic_occ_{k + first}s'] = [occ]
-            res[f'geo_occ_{k + first}s'] = [geo]
-        return res
+        return self._host_result(self._occupancy_dev(vf, [ego]))

@@ -91,10 +91,26 @@ class OccHead(BaseModule):
 
     def _build_packs(self):
         oc, pc = self.occ_convs[0], self.occ_pred_conv
+        p0, p1 = pack_conv(pc[0], pc[1]), pack_conv(pc[3])
+        mid, ncls = pc[0].out_channels, pc[3].out_channels
+        # pw_occhead_tail: plain [out, in] matrices + the folded BatchNorm affine
+        tail = (pc[0].weight.detach().float().reshape(mid, -1).contiguous(),
+                p0.scale, p0.bias,
+                pc[3].weight.detach().float().reshape(ncls, mid).contiguous(),
+                p1.bias)
         return dict(
             c0=pack_conv(oc[0], oc[1]),
             c0_rev=pack_conv(oc[0], oc[1], spatial_perm=(2, 1, 0)),
-            p0=pack_conv(pc[0], pc[1]), p1=pack_conv(pc[3]))
+            p0=p0, p1=p1, tail=tail)
+
+    def occupancy_pair_cl(self, x_cl, free_idx, geo_value, out=None):
+        """cl array [1,Z,Y,X,C] (library order) -> uint8 [2,X,Y,Z]: class argmax
+        and geometry grid (preworld.py:196-221), two launches: occ_convs[0] on the
+        tensor cores, then the fused 16->8->18->argmax tail (no 8- / 18-channel
+        tensors in HBM)."""
+        P = self.packs()
+        y = ops.conv(x_cl, P['c0_rev'], 'relu')
+        return ops.occhead_tail(y, *P['tail'], free_idx, geo_value, out=out)
 
     def logits_cl(self, x_cl, reversed_order=True):
         """cl array [B,Z,Y,X,C] (library order; weights spatially transposed)

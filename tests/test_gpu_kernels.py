@@ -888,3 +888,67 @@ def test_pts2ray_matches_reference_fixture(golden_dir):
     assert len({tuple(r) for r in pick[:, [0, 1, 4, 5, 7]].cpu().tolist()}) > 990
     assert R.pts2ray(*[t.to(DEV) for t in (coors[0][:0], depths[0][:0], segs[0][:0],
                                            imgs[0][:0], c2ws[0], Ks[0])]).shape == (0, 16)
+
+
+# --------------------------------------------------- fused per-voxel heads
+@pytest.mark.parametrize('m,hidden,n2,res,act2c', [
+    (1000, 128, 32, True, 0),      # forecasting step shape, ragged last tile
+    (128 * 149 + 5, 192, 22, False, 2),   # attribute projection shape, > 148 tiles
+    (77, 32, 4, False, 0),         # one partial tile, one hidden chunk, n2p = 16
+])
+def test_mlp2_matches_torch(m, hidden, n2, res, act2c):
+    """pw_mlp2 (fused Linear-Softplus-Linear on the tensor cores, hidden row on
+    chip) vs the same two layers in torch fp32 on the CPU."""
+    g = torch.Generator().manual_seed(m + hidden)
+    x = torch.randn(m, 32, generator=g)
+    w1 = torch.randn(hidden, 32, generator=g) / 32 ** .5
+    b1 = torch.randn(hidden, generator=g)
+    w2 = torch.randn(n2, hidden, generator=g) / hidden ** .5
+    b2 = torch.randn(n2, generator=g)
+    h = F.softplus(F.linear(x, w1, b1))
+    want = F.linear(h, w2, b2)
+    if act2c:
+        want[:, :act2c] = F.softplus(want[:, :act2c])
+    pm = ops.PackedMlp2(w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV),
+                        act1='softplus', act2='softplus' if act2c else None,
+                        act2_channels=act2c)
+    xd = x.to(DEV)
+    got = ops.mlp2(xd, pm, residual=xd if res else None)
+    if res:
+        want = want + x
+    got = got.cpu()[:, :n2]
+    assert _rel(got, want) < 5e-6, _rel(got, want)
+    # per-call bias override (the ego bias of the forecasting step)
+    b1b = torch.randn(hidden, generator=g)
+    want2 = F.linear(F.softplus(F.linear(x, w1, b1b)), w2, b2)
+    if act2c:
+        want2[:, :act2c] = F.softplus(want2[:, :act2c])
+    got2 = ops.mlp2(xd, pm, bias1=b1b.to(DEV)).cpu()[:, :n2]
+    assert _rel(got2, want2) < 5e-6
+
+
+@pytest.mark.parametrize('grid', [(40, 40, 16), (37, 9, 5), (200, 3, 16)])
+def test_occhead_tail_matches_torch(grid):
+    """pw_occhead_tail: 16 -> 8 (BN, ReLU) -> 18 -> argmax (+ geo), transposed to
+    the [X,Y,Z] grid, vs torch."""
+    gx, gy, gz = grid
+    g = torch.Generator().manual_seed(gx * 7 + gz)
+    feat = torch.relu(torch.randn(1, gz, gy, gx, 16, generator=g))
+    w0 = torch.randn(8, 16, generator=g) / 4
+    s0, b0 = torch.rand(8, generator=g) + .5, torch.randn(8, generator=g) * .1
+    w1 = torch.randn(18, 8, generator=g) / 8 ** .5
+    h = torch.relu(F.linear(feat, w0) * s0 + b0)
+    logits = F.linear(h, w1)                                  # [1,Z,Y,X,18]
+    both, lg = ops.occhead_tail(feat.to(DEV), w0.to(DEV), s0.to(DEV), b0.to(DEV),
+                                w1.to(DEV), None, 17, 17, want_logits=True)
+    assert _rel(lg.cpu(), logits) < 2e-6
+    # argmax of the kernel's own logits, exactly; the reference argmax wherever
+    # the top-2 margin is above the fp32 noise
+    own = lg.cpu()[0].argmax(-1).permute(2, 1, 0)             # [X,Y,Z]
+    occ = both[0].cpu().long()
+    assert torch.equal(occ, own)
+    top2 = logits[0].topk(2, -1).values
+    clear = ((top2[..., 0] - top2[..., 1]) > 1e-4).permute(2, 1, 0)
+    assert torch.equal(occ[clear], logits[0].argmax(-1).permute(2, 1, 0)[clear])
+    geo = both[1].cpu().long()
+    assert torch.equal(geo, torch.where(occ == 17, 17, 0))

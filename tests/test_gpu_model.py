@@ -234,9 +234,9 @@ def test_full_size_finetune_matches_reference(golden_dir):
         want_o = torch_ref.preworld_simple_test(sd, pc, inputs, ost)
     err = (st['logits'].cpu() - ost['logits']).abs().max().item() \
         / ost['logits'].abs().max().item()
-    # a flip needs the two leading logits closer than twice the logit error
+    # every flip sits on a near tie: measured top-2 margins <= 2e-6 of max|logit|
     n_o = _margin_ok(occ, want_o['semantic_occ'][0], ost['logits'],
-                     tol=2.0 * 1e-4, verbose=True)
+                     tol=1e-5, verbose=True)
     print(f'full_finetune vs oracle: {n_o} near-tie voxels differ, '
           f'logits max rel err {err:.2e}')
     assert err < 1e-4                         # north_star bar: 1e-3
