@@ -45,6 +45,23 @@ constexpr int COL_A1 = 0, COL_ACC1 = 64, COL_A2 = 128, COL_ACC2 = 192;
 constexpr int W1_CHUNK = 2 * KC * ROWB;       // hi rows then lo rows of one hidden chunk
 constexpr int STAGE_PER_WARP = 32 * ROWB;
 
+// Softplus(beta = 1, threshold = 20) of the hidden layer: max(x, 0) + ln2 * lg2(1 +
+// ex2(-|x| log2e)) -- two MUFU + four FP32 instructions, branch-free (for x > 20 the
+// second term is exactly 0, which is torch's threshold branch).  Absolute error
+// <= 2e-7 (the lg2 of 1 + t loses t's low bits only where the result is itself below
+// 1e-3): the hidden units are combined linearly by W2, so it is the absolute error
+// that matters, and it is at the level of the fp32 rounding of the sums.  (The
+// accurate log1pf(expf(x)) of common.cuh costs ~100 instructions with its range
+// branches; at 128 x H evaluations per tile it set the kernel's time.)
+__device__ __forceinline__ float softplus_fast(float x) {
+  float t, l;
+  const float a = -fabsf(x) * 1.4426950408889634f;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(a));
+  const float u = 1.0f + t;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u));
+  return fmaf(l, 0.6931471805599453f, fmaxf(x, 0.f));
+}
+
 struct Mlp2Params {
   long long M;
   int tiles;
@@ -266,7 +283,8 @@ mlp2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
           float v0 = fmaf(__uint_as_float(m1[c]) + __uint_as_float(k1[c]), p.gain1, bj[16 + c]);
           float v1 = fmaf(__uint_as_float(m1[c + 1]) + __uint_as_float(k1[c + 1]), p.gain1, bj[16 + c + 1]);
           if (p.act1 == PW_ACT_SOFTPLUS) {
-            u0 = pw_softplus(u0); u1 = pw_softplus(u1); v0 = pw_softplus(v0); v1 = pw_softplus(v1);
+            u0 = softplus_fast(u0); u1 = softplus_fast(u1);
+            v0 = softplus_fast(v0); v1 = softplus_fast(v1);
           } else if (p.act1 == PW_ACT_RELU) {
             u0 = fmaxf(u0, 0.f); u1 = fmaxf(u1, 0.f); v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f);
           }

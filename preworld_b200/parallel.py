@@ -38,22 +38,45 @@ class CameraShard:
             world = dist.get_world_size(group) if dist.is_initialized() else 1
         assert 0 <= rank < world
         self.rank, self.world, self.group = rank, world, group
+        self._bufs = {}
 
     def local_range(self, n_cams):
         return camera_split(n_cams, self.world)[self.rank]
 
+    def _plan(self, n_cams, B, F, like):
+        """Preallocated exchange buffers per (n_cams, B, F, device): the padded
+        send block, the [world, B, mx, F] receive buffer and -- for an uneven
+        split -- the row index that drops the padding."""
+        key = (n_cams, B, F, like.device, like.dtype)
+        plan = self._bufs.get(key)
+        if plan is None:
+            split = camera_split(n_cams, self.world)
+            mx = max(c for _, c in split)
+            send = like.new_zeros((B, mx, F))
+            recv = like.new_empty((self.world, B, mx, F))
+            even = all(c == mx for _, c in split)
+            idx = None
+            if not even:
+                idx = torch.tensor([r * mx + k for r, (_, c) in enumerate(split)
+                                    for k in range(c)], device=like.device)
+            plan = self._bufs[key] = (split, mx, send, recv, even, idx)
+        return plan
+
     def all_gather_cams(self, local, n_cams):
-        """local [B, n_local, F] -> [B, n_cams, F] in camera order (one
-        all-gather of equally padded blocks)."""
-        split = camera_split(n_cams, self.world)
-        start, cnt = split[self.rank]
-        assert local.shape[1] == cnt, (local.shape, cnt)
+        """local [B, n_local, F] -> [B, n_cams, F] in camera order: ONE
+        ``all_gather_into_tensor`` of equally sized blocks into a preallocated
+        buffer, then one re-ordering copy (rank-major -> sample-major; for an
+        uneven split the same copy drops the padding rows)."""
+        B, cnt_have, F = local.shape
         if self.world == 1:
             return local
-        mx = max(c for _, c in split)
-        B, _, F = local.shape
-        pad = local.new_zeros((B, mx, F))
-        pad[:, :cnt] = local
-        outs = [torch.empty_like(pad) for _ in range(self.world)]
-        dist.all_gather(outs, pad, group=self.group)
-        return torch.cat([o[:, :c] for o, (_, c) in zip(outs, split)], dim=1)
+        split, mx, send, recv, even, idx = self._plan(n_cams, B, F, local)
+        assert cnt_have == split[self.rank][1], (local.shape, split[self.rank])
+        if cnt_have == mx and local.is_contiguous():
+            src = local
+        else:
+            send[:, :cnt_have] = local            # padding rows stay zero
+            src = send
+        dist.all_gather_into_tensor(recv.view(-1), src.reshape(-1), group=self.group)
+        out = recv.permute(1, 0, 2, 3).reshape(B, self.world * mx, F)
+        return out if even else out.index_select(1, idx)

@@ -308,22 +308,24 @@ class BEVStereo4DOCC(BaseModule):
             feat_prev_iv = feat_curr_iv
         return self._fuse_frames(bev_feat_list, dev), depth_key_frame
 
-    def _lift_frames_batched(self, imgs, sensor2keyegos, ego2globals, intrins,
-                             post_rots, post_trans, bda, curr2adjsensor):
-        """DepthNet + cost volume of ALL lifted frames in one batched pass
-        (frame f is a virtual sample: batch = frames x B), then the lift and
-        pre_process_net per frame.  Same kernels on the same per-image data as
-        the frame-by-frame loop of bevdet_occ.py:219-240."""
+    def _depth_frames_batched(self, N, sensor2keyegos, ego2globals, intrins,
+                              post_rots, post_trans, bda, curr2adjsensor,
+                              cams=slice(None)):
+        """DepthNet + cost volume of ALL lifted frames of the cameras ``cams`` in
+        one batched pass over ``self._enc_batches`` (frame f is a virtual sample:
+        batch = frames x B).  Same kernels on the same per-image data as the
+        frame-by-frame loop of bevdet_occ.py:219-240.  -> depth [F*B*n,D,h,w],
+        context [F*B*n,h,w,C] (frame-major), n = cameras in ``cams``."""
         vt = self.img_view_transformer
-        dev = imgs[0].device
-        B, N = imgs[0].shape[:2]
-        bn = B * N
         l1, x, n_full = self._enc_batches
+        bn = l1.shape[0] // self.num_frame
+        B = bn // N
         frames = list(range(n_full))                     # 0 = key, 1.. adjacent
-        cat0 = lambda ts: torch.cat([ts[f] for f in frames], dim=0)
+        cat0 = lambda ts: torch.cat([ts[f][:, cams] for f in frames], dim=0)
         mlp_input = torch.cat([vt.get_mlp_input(
-            sensor2keyegos[0], ego2globals[0], intrins[f], post_rots[f],
-            post_trans[f], bda) for f in frames], dim=0)
+            sensor2keyegos[0][:, cams], ego2globals[0][:, cams],
+            intrins[f][:, cams], post_rots[f][:, cams], post_trans[f][:, cams],
+            bda) for f in frames], dim=0)
         # cost volume of frame f: current = layer1 of frame f, previous = frame f+1
         metas = dict(k2s_sensor=cat0(curr2adjsensor), intrins=cat0(intrins),
                      post_rots=cat0(post_rots), post_trans=cat0(post_trans),
@@ -332,11 +334,27 @@ class BEVStereo4DOCC(BaseModule):
                      cv_feat_list=[ops.to_logical(l1[bn:(n_full + 1) * bn]),
                                    ops.to_logical(l1[:n_full * bn])])
         _, cdim, oh, ow = x.shape
-        depth, tran = vt.depth_stage(x.view(n_full * B, N, cdim, oh, ow),
-                                     mlp_input, metas)
+        return vt.depth_stage(x.view(n_full * B, N, cdim, oh, ow), mlp_input, metas)
+
+    def _lift_frames_batched(self, imgs, sensor2keyegos, ego2globals, intrins,
+                             post_rots, post_trans, bda, curr2adjsensor):
+        """Batched depth stage, then the lift and pre_process_net per frame."""
+        B, N = imgs[0].shape[:2]
+        depth, tran = self._depth_frames_batched(
+            N, sensor2keyegos, ego2globals, intrins, post_rots, post_trans, bda,
+            curr2adjsensor)
+        return self._lift_and_fuse(depth, tran, sensor2keyegos, intrins,
+                                   post_rots, post_trans, bda, B, N,
+                                   imgs[0].device)
+
+    def _lift_and_fuse(self, depth, tran, sensor2keyegos, intrins, post_rots,
+                       post_trans, bda, B, N, dev):
+        vt = self.img_view_transformer
+        bn = B * N
+        n_full = depth.shape[0] // bn
         bev_feat_list = []
         depth_key_frame = None
-        for fid in reversed(frames):                     # [adjacent.., key]
+        for fid in reversed(range(n_full)):              # [adjacent.., key]
             d_f = depth[fid * bn:(fid + 1) * bn]
             bev = vt.lift_stage(d_f, tran[fid * bn:(fid + 1) * bn],
                                 sensor2keyegos[fid], intrins[fid],
@@ -361,65 +379,44 @@ class BEVStereo4DOCC(BaseModule):
     def _extract_img_feat_sharded(self, shard, imgs, sensor2keyegos,
                                   ego2globals, intrins, post_rots, post_trans,
                                   bda, curr2adjsensor):
-        """This rank encodes its block of cameras for every frame, ONE
-        all-gather exchanges depth + context features, then every rank lifts
-        all cameras (same deterministic kernel -> identical voxel features)."""
+        """This rank runs backbone + neck + DepthNet + cost volume for its block
+        of cameras (all frames, batched), ONE all-gather exchanges every lifted
+        frame's depth distribution and context feature per camera (0.33 MB
+        each), then every rank lifts all cameras with the same deterministic
+        kernel -> bit-identical voxel features on all ranks."""
         vt = self.img_view_transformer
         dev = imgs[0].device
-        nf = self.num_frame
         B, N = imgs[0].shape[:2]
         c0, cn = shard.local_range(N)
         sl = slice(c0, c0 + cn)
-        lifted = [f for f in range(nf - 1, -1, -1)
-                  if f != nf - self.extra_ref_frames]      # [adjacent.., key]
+        n_full = self.num_frame - self.extra_ref_frames
         D, C = vt.D, vt.out_channels
         h, w = [int(v) for v in vt.frustum.shape[1:3]]
-        per_frame = D * h * w + h * w * C
-        local = torch.empty((B, cn, per_frame * len(lifted)), device=dev,
+        nd, nt = D * h * w, h * w * C
+        local = torch.empty((B, cn, n_full, nd + nt), device=dev,
                             dtype=torch.float32)
         if cn > 0:
             enc = self.encode_frames([im[:, sl] for im in imgs])
-            feat_prev = None
-            k = 0
-            for fid in range(nf - 1, -1, -1):
-                x, stereo = enc[0][fid], enc[1][fid]
-                if fid in lifted:
-                    mlp_input = vt.get_mlp_input(
-                        sensor2keyegos[0][:, sl], ego2globals[0][:, sl],
-                        intrins[fid][:, sl], post_rots[fid][:, sl],
-                        post_trans[fid][:, sl], bda)
-                    metas = dict(k2s_sensor=curr2adjsensor[fid][:, sl],
-                                 intrins=intrins[fid][:, sl],
-                                 post_rots=post_rots[fid][:, sl],
-                                 post_trans=post_trans[fid][:, sl],
-                                 frustum=vt.cv_frustum, cv_downsample=4,
-                                 downsample=vt.downsample,
-                                 grid_config=vt.grid_config,
-                                 cv_feat_list=[feat_prev, stereo])
-                    depth, tran = vt.depth_stage(x, mlp_input, metas)
-                    o = k * per_frame
-                    local[:, :, o:o + D * h * w] = depth.reshape(B, cn, -1)
-                    local[:, :, o + D * h * w:o + per_frame] = \
-                        tran.reshape(B, cn, -1)
-                    k += 1
-                feat_prev = stereo
-        full = shard.all_gather_cams(local, N)                 # [B, N, F]
-        bev_feat_list = []
-        depth_key_frame = None
-        for k, fid in enumerate(lifted):
-            o = k * per_frame
-            depth = full[:, :, o:o + D * h * w].reshape(B * N, D, h, w) \
-                .contiguous()
-            tran = full[:, :, o + D * h * w:o + per_frame] \
-                .reshape(B * N, h, w, C).contiguous()
-            bev = vt.lift_stage(depth, tran, sensor2keyegos[fid], intrins[fid],
-                                post_rots[fid], post_trans[fid], bda, B, N)
-            if self.pre_process:
-                bev = self.pre_process_net(bev)[0]
-            bev_feat_list.append(bev)
-            if fid == 0:
-                depth_key_frame = depth
-        return self._fuse_frames(bev_feat_list, dev), depth_key_frame
+            if enc is None:
+                raise NotImplementedError(
+                    'camera sharding needs a backbone with the batched stem + '
+                    'layer1 path (run_stem_cl, out_indices containing 0)')
+            # frames of the pose lists beyond the lifted ones are never indexed
+            depth, tran = self._depth_frames_batched(
+                cn, [t[:, sl] for t in sensor2keyegos],
+                [t[:, sl] for t in ego2globals], [t[:, sl] for t in intrins],
+                [t[:, sl] for t in post_rots], [t[:, sl] for t in post_trans],
+                bda, [t[:, sl] if t is not None else None
+                      for t in curr2adjsensor])
+            local[..., :nd] = depth.reshape(n_full, B, cn, nd).permute(1, 2, 0, 3)
+            local[..., nd:] = tran.reshape(n_full, B, cn, nt).permute(1, 2, 0, 3)
+        full = shard.all_gather_cams(local.view(B, cn, n_full * (nd + nt)), N) \
+            .view(B, N, n_full, nd + nt)
+        full = full.permute(2, 0, 1, 3)                       # [F, B, N, nd+nt]
+        depth = full[..., :nd].reshape(n_full * B * N, D, h, w)
+        tran = full[..., nd:].reshape(n_full * B * N, h, w, C)
+        return self._lift_and_fuse(depth, tran, sensor2keyegos, intrins,
+                                   post_rots, post_trans, bda, B, N, dev)
 
     def _fuse_frames(self, bev_feat_list, dev):
         # torch.cat(bev_feat_list, dim=1): [adjacent, key] order (:240,266)

@@ -70,7 +70,7 @@ def _worker(rank, world, port, n_cams, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,n_cams', [(2, 6), (3, 7), (4, 6)])
+@pytest.mark.parametrize('world,n_cams', [(2, 6), (3, 7), (4, 6), (8, 6)])
 def test_all_gather_cams_gloo(world, n_cams):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
