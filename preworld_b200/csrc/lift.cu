@@ -9,6 +9,10 @@
 //                                      in-range mask, argsort, intervals)
 //   ops/bev_pool_v2/bev_pool.py:17-41,86-92 + src/bev_pool_cuda.cu:21-48
 //   (zero-fill of `out`, the pooling kernel, the permute(0,4,1,2,3) copy)
+#include <stdlib.h>
+
+#include <mutex>
+
 #include "common.cuh"
 #include "../../include/preworld_b200.h"
 
@@ -28,11 +32,14 @@ struct LiftGeom {
 
 // Voxel rank (or -1) of frustum point p = (((b*N+n)*D+d)*H+h)*W+w.
 // Arithmetic order is pinned to oracle/oracle_ref.c:pw_ref_lift_ranks.
-__device__ __forceinline__ int lift_rank_of(const LiftGeom& g, long long p) {
-  int w = (int)(p % g.W);
-  long long t = p / g.W;
-  int h = (int)(t % g.H); t /= g.H;
-  int d = (int)(t % g.D); t /= g.D;
+__device__ __forceinline__ int lift_rank_of(const LiftGeom& g, long long p64) {
+  // P < 2^31 (checked by the callers): 32-bit index arithmetic (four 64-bit divisions
+  // were a third of the instructions of a rank)
+  const unsigned p = (unsigned)p64;
+  int w = (int)(p % (unsigned)g.W);
+  unsigned t = p / (unsigned)g.W;
+  int h = (int)(t % (unsigned)g.H); t /= (unsigned)g.H;
+  int d = (int)(t % (unsigned)g.D); t /= (unsigned)g.D;
   int bn = (int)t;
   int b = bn / g.N;
   const float* c = g.cam + (long long)bn * PW_LIFT_CAM_FLOATS;
@@ -84,7 +91,12 @@ struct LiftFused {
   float* out;
   int* rank; int* slot; int* count; int* start; int* list;
   unsigned* ctrl;               // [0] grid-barrier counter, [1] list cursor, [2] work-queue
-                                // length, [3] exit counter, [4] group ticket: zero on entry, re-zeroed on exit
+                                // length, [3] exit counter, [4] group ticket: zero on entry,
+                                // re-zeroed on exit; [5] bin overflow flag of the current build
+                                // (cleared by the fallback), [6] pool units of the schedule,
+                                // [7] which lists a pool-only call uses: 1 schedule, 2 fallback
+  unsigned* bin_count;          // scheduled path (below); NULL = persistent kernel only
+  int n_bins;
   long long P, V;
 };
 
@@ -144,6 +156,14 @@ lift_fused_kernel(const LiftFused a) {
   const long long n4 = a.V * a.C / 4;                // host guarantees V*C % 4 == 0
   unsigned* bar = a.ctrl;
   unsigned nbar = 0;                                   // grid barriers passed so far
+  // As the fallback of the scheduled path: MODE 0 / 1 run only if a bin overflowed
+  // while the schedule was built, MODE 2 only if the lists in the workspace are the
+  // fallback's.  The words are read by every CTA before any CTA can reach the
+  // clean-up at the end (which needs all of them), so the decision is uniform.
+  if (a.bin_count != nullptr) {
+    if (MODE != 2 && __ldcg(a.ctrl + 5) == 0u) return;
+    if (MODE == 2 && __ldcg(a.ctrl + 7) != 2u) return;
+  }
 
   lift_stamp(a.ctrl, 0);
   if (MODE != 2) {
@@ -472,7 +492,313 @@ lift_fused_kernel(const LiftFused a) {
     __threadfence();
     if (atomicAdd(a.ctrl + 3, 1u) == G - 1) {
       a.ctrl[0] = 0; a.ctrl[1] = 0; a.ctrl[2] = 0; a.ctrl[3] = 0; a.ctrl[4] = 0;
+      if (a.bin_count != nullptr && MODE != 2) {       // the schedule build gave up: clean up
+        a.ctrl[5] = 0;                                   // after it, lists = the fallback's
+        if (MODE == 1) a.ctrl[7] = 2;
+        for (int i = 0; i < a.n_bins; ++i) a.bin_count[i] = 0;
+      }
       __threadfence();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The scheduled lift (round 2): plain launches, no grid barrier, every output row
+// written exactly once, and the pooling pass -- the reference's bev_pool_v2 proper,
+// which takes the sorted ranks and intervals as INPUTS (bev_pool.py:17-41) -- is a
+// perfectly balanced streaming kernel.
+//
+//   pass A  lift_bin_kernel: rank of every frustum point; kept points are appended
+//           (voxel-in-bin, point) to the bin that owns their voxel.  A block counts
+//           its 2048 points per bin in shared memory and reserves ONE range per
+//           touched bin (a fraction of the 218 k per-point global atomics).
+//   pass B  lift_sort_bins_kernel: one CTA per bin; counting sort by voxel in shared
+//           memory, point order inside a voxel (the oracle's stable sort), and the
+//           SCHEDULE goes to global memory: sorted entries (point, voxel | first-of-
+//           voxel flag), one descriptor per 32 entries, one empty-row mask per group.
+//   pass C  lift_pool_sched_kernel: every warp of the grid takes descriptors with a
+//           fixed stride (a unit owns the voxels whose first entry lies in it and
+//           follows the last one past its end; lane = channel, sequential fmaf chain
+//           per voxel as bev_pool_cuda.cu:38-42, 32 feature rows in flight), then
+//           groups of 32 voxels whose empty rows it zeroes with float4 stores.
+//
+// pw_lift_fused = A + B + C (+ the persistent kernel above as fallback: an
+// immediate exit unless a bin overflowed BIN_CAP entries -- cameras looking at one
+// spot); pw_lift_prepare = A + B, pw_lift_pool = C (LSSViewTransformer
+// accelerate=True: the schedule is built once).
+//
+// A bin is NOT a contiguous voxel range (the points crowd around the cameras) but
+// every n_bins-th group of 32 consecutive voxels, n_bins prime: group g -> bin
+// g % n_bins, slot g / n_bins.
+constexpr int BIN_VOX = 1024;
+constexpr int BIN_GROUPS = BIN_VOX / 32;
+constexpr int BIN_CAP = 4096;
+constexpr int BIN_UNITS = BIN_CAP / 32;
+constexpr int SORT_THREADS = 256;
+constexpr size_t SORT_SMEM = (size_t)(BIN_VOX + 4 + BIN_VOX + BIN_CAP) * 4 + BIN_CAP * 2;
+constexpr int BINA_THREADS = 256;                         // 2048 points per CTA: 182 CTAs at the
+                                                         // BASELINE size (46 CTAs of 8192 left 2/3 of the SMs idle)
+constexpr int BINA_PTS = 8;                              // points per thread
+constexpr int POOL_THREADS = 256;
+constexpr unsigned FIRST_FLAG = 0x80000000u;
+
+__device__ __forceinline__ int bin_of_voxel(int v, int n_bins, int& local) {
+  const int g = v >> 5;
+  const int bin = g % n_bins;
+  local = ((g / n_bins) << 5) | (v & 31);
+  return bin;
+}
+__device__ __forceinline__ long long voxel_of_local(int bin, int local, int n_bins) {
+  return (((long long)(local >> 5) * n_bins + bin) << 5) | (local & 31);
+}
+
+__global__ void __launch_bounds__(BINA_THREADS)
+lift_bin_kernel(const LiftGeom g, long long P, int n_bins, int2* __restrict__ entries,
+                unsigned* __restrict__ bin_count, unsigned* __restrict__ ctrl) {
+  extern __shared__ unsigned bina_smem[];                // hist[n_bins], then base[n_bins]
+  unsigned* hist = bina_smem;
+  unsigned* base = bina_smem + n_bins;
+  for (int i = threadIdx.x; i < n_bins; i += BINA_THREADS) hist[i] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl[6] = 0; ctrl[7] = 0; }   // a new schedule
+  __syncthreads();
+  const long long p0 = (long long)blockIdx.x * (BINA_THREADS * BINA_PTS) + threadIdx.x;
+  int bin[BINA_PTS], local[BINA_PTS];
+  unsigned slot[BINA_PTS];
+#pragma unroll
+  for (int k = 0; k < BINA_PTS; ++k) {
+    const long long p = p0 + (long long)k * BINA_THREADS;
+    const int r = p < P ? lift_rank_of(g, p) : -1;
+    local[k] = 0;
+    bin[k] = r >= 0 ? bin_of_voxel(r, n_bins, local[k]) : -1;
+  }
+#pragma unroll
+  for (int k = 0; k < BINA_PTS; ++k)
+    slot[k] = bin[k] >= 0 ? atomicAdd(hist + bin[k], 1u) : 0u;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_bins; i += BINA_THREADS)
+    base[i] = hist[i] ? atomicAdd(bin_count + i, hist[i]) : 0u;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < BINA_PTS; ++k) {
+    if (bin[k] < 0) continue;
+    const unsigned pos = base[bin[k]] + slot[k];
+    if (pos < BIN_CAP)
+      entries[(long long)bin[k] * BIN_CAP + pos] =
+          make_int2(local[k], (int)(p0 + (long long)k * BINA_THREADS));
+    else
+      ctrl[5] = 1u;                                      // overflow: the fallback takes the call
+  }
+}
+
+struct LiftSched {
+  int2* entries;                // [n_bins * BIN_CAP] pass A: (voxel in bin, point), unordered
+  int2* sorted;                 // [n_bins * BIN_CAP] pass B: (point, voxel in bin | FIRST_FLAG)
+  int* bin_n;                   // [n_bins] entries of each bin
+  unsigned* desc;               // [n_bins * BIN_UNITS] pool units: bin << 8 | unit
+  unsigned* empty;              // [groups] bit r: row r of the group has no point
+};
+
+__global__ void __launch_bounds__(SORT_THREADS)
+lift_sort_bins_kernel(const LiftFused a, const LiftSched sc) {
+  extern __shared__ __align__(16) int sort_smem[];
+  int* s_start = sort_smem;                              // [BIN_VOX + 1 (+3)] counts, then offsets
+  int* s_cursor = s_start + BIN_VOX + 4;                 // [BIN_VOX]
+  int* s_tp = s_cursor + BIN_VOX;                        // [BIN_CAP] points in slot order
+  unsigned short* s_tv = reinterpret_cast<unsigned short*>(s_tp + BIN_CAP);   // [BIN_CAP]
+  __shared__ int s_wsum[SORT_THREADS / 32];
+  __shared__ unsigned s_ubase;
+  if (__ldcg(a.ctrl + 5) != 0u) return;                  // a bin overflowed: fallback launch
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bin = blockIdx.x;
+  const int n_bins = a.n_bins;
+  const long long n_groups = (a.V + 31) >> 5;
+  const int nslots = (int)((n_groups - bin + n_bins - 1) / n_bins);   // groups of this bin
+  const int n = (int)min(__ldcg(a.bin_count + bin), (unsigned)BIN_CAP);
+  const int2* ent = sc.entries + (long long)bin * BIN_CAP;
+
+  for (int i = threadIdx.x; i <= BIN_VOX; i += SORT_THREADS) s_start[i] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a.bin_count[bin] = 0;                                // leave the counter clean for the next build
+    sc.bin_n[bin] = n;
+    a.ctrl[7] = 1u;                                      // pool-only calls use the schedule
+    const int n_units = (n + 31) >> 5;
+    s_ubase = n_units ? atomicAdd(a.ctrl + 6, (unsigned)n_units) : 0u;
+  }
+  // the first entries stay in registers between the counting and the filling pass
+  constexpr int KEEP = 4;
+  int2 e[KEEP];
+#pragma unroll
+  for (int k = 0; k < KEEP; ++k) {
+    const int i = threadIdx.x + k * SORT_THREADS;
+    e[k] = i < n ? __ldcg(&ent[i]) : make_int2(0, 0);
+  }
+#pragma unroll
+  for (int k = 0; k < KEEP; ++k)
+    if (threadIdx.x + k * SORT_THREADS < n) atomicAdd(&s_start[e[k].x], 1);
+  for (int i = threadIdx.x + KEEP * SORT_THREADS; i < n; i += SORT_THREADS)
+    atomicAdd(&s_start[__ldcg(&ent[i].x)], 1);
+  __syncthreads();
+  // empty-row masks of the bin's groups + exclusive scan of the BIN_VOX counts
+  for (int sl = warp; sl < nslots; sl += SORT_THREADS / 32) {
+    const unsigned m = __ballot_sync(0xffffffffu, s_start[sl * 32 + lane] == 0);
+    if (lane == 0) sc.empty[(long long)sl * n_bins + bin] = m;
+  }
+  {
+    constexpr int PER = BIN_VOX / SORT_THREADS;
+    int c[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { c[k] = s_start[threadIdx.x * PER + k]; sum += c[k]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int off = incl - sum;
+    for (int w = 0; w < warp; ++w) off += s_wsum[w];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      s_start[threadIdx.x * PER + k] = off;
+      s_cursor[threadIdx.x * PER + k] = off;
+      off += c[k];
+    }
+    if (threadIdx.x == SORT_THREADS - 1) s_start[BIN_VOX] = off;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < KEEP; ++k) {
+    if (threadIdx.x + k * SORT_THREADS < n) {
+      const int slot = atomicAdd(&s_cursor[e[k].x], 1);
+      s_tp[slot] = e[k].y;
+      s_tv[slot] = (unsigned short)e[k].x;
+    }
+  }
+  for (int i = threadIdx.x + KEEP * SORT_THREADS; i < n; i += SORT_THREADS) {
+    const int2 ee = __ldcg(&ent[i]);
+    const int slot = atomicAdd(&s_cursor[ee.x], 1);
+    s_tp[slot] = ee.y;
+    s_tv[slot] = (unsigned short)ee.x;
+  }
+  __syncthreads();
+  // order inside a voxel: ascending point index (position = number of smaller points);
+  // the sorted entry goes straight to the schedule
+  int2* out = sc.sorted + (long long)bin * BIN_CAP;
+  for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+    const int v = s_tv[i], pnt = s_tp[i];
+    const int b = s_start[v], en = s_start[v + 1];
+    int pos = b;
+    for (int k = b; k < en; ++k) pos += s_tp[k] < pnt ? 1 : 0;
+    out[pos] = make_int2(pnt, (int)((unsigned)v | (pos == b ? FIRST_FLAG : 0u)));
+  }
+  const unsigned ub = s_ubase;
+  for (int k = threadIdx.x; k * 32 < n; k += SORT_THREADS) sc.desc[ub + k] = ((unsigned)bin << 8) | (unsigned)k;
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(POOL_THREADS, 3)
+lift_pool_sched_kernel(const LiftFused a, const LiftSched sc, int pool_only, int dbg) {
+  // which lists are valid?  (per-call build: no overflow; pool-only: schedule present)
+  if (pool_only ? __ldcg(a.ctrl + 7) != 1u : __ldcg(a.ctrl + 5) != 0u) return;
+  const int lane = threadIdx.x & 31;
+  const long long gwarp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int n_bins = a.n_bins;
+  const int HW = a.g.H * a.g.W;
+  const unsigned n_units = __ldcg(a.ctrl + 6);
+
+  // ---- pool units -----------------------------------------------------------------------
+  if (!(dbg & 1))
+  for (long long ui = gwarp; ui < n_units; ui += nwarps) {
+    const unsigned dsc = __ldcg(sc.desc + ui);
+    const int bin = (int)(dsc >> 8), unit = (int)(dsc & 255u);
+    const int n = __ldcg(sc.bin_n + bin);
+    const int2* ent = sc.sorted + (long long)bin * BIN_CAP;
+    const int nominal_end = min(n, unit * 32 + 32);
+    int pos = unit * 32;
+    bool started = false;
+    float acc[CPL];
+#pragma unroll
+    for (int qc = 0; qc < CPL; ++qc) acc[qc] = 0.f;
+    int cur = -1;
+    for (;;) {
+      const int idx = pos + lane;
+      int2 e = make_int2(0, 0);
+      if (idx < n) e = __ldcg(&ent[idx]);
+      const bool first = idx < n && ((unsigned)e.y & FIRST_FLAG);
+      int t0 = 0;
+      if (!started) {                                    // skip entries of an earlier unit's voxel
+        const unsigned sm = __ballot_sync(0xffffffffu, first && idx < nominal_end);
+        if (sm == 0u) break;                             // no voxel starts in this unit
+        t0 = __ffs(sm) - 1;
+        started = true;
+      }
+      // stop in front of the first voxel that starts at or after the unit's end
+      const unsigned stop = __ballot_sync(0xffffffffu, idx >= n || (first && idx >= nominal_end));
+      const int t1 = stop ? __ffs(stop) - 1 : 32;
+      int row = 0;
+      float dv = 0.f;
+      const int vx = (int)((unsigned)e.y & ~FIRST_FLAG);
+      if (lane >= t0 && lane < t1) {
+        // p = (bn*D + d)*HW + hw  ->  feature row bn*HW + hw
+        row = (e.x / HW / a.g.D) * HW + e.x % HW;
+        dv = __ldg(a.depth + e.x);
+      }
+#pragma unroll
+      for (int qc = 0; qc < CPL; ++qc) {
+        const int ch = lane + 32 * qc;
+        const bool chok = ch < a.C;
+        float f[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const int rt = __shfl_sync(0xffffffffu, row, t);
+          f[t] = (t >= t0 && t < t1 && chok) ? __ldg(a.feat + (long long)rt * a.feat_ld + ch) : 0.f;
+        }
+        int cq = cur;
+        float aq = acc[qc];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          if (t >= t0 && t < t1) {
+            const int vt = __shfl_sync(0xffffffffu, vx, t);
+            const float dt = __shfl_sync(0xffffffffu, dv, t);
+            if (vt != cq) {
+              if (cq >= 0 && chok) a.out[voxel_of_local(bin, cq, n_bins) * a.C + ch] = aq;
+              cq = vt;
+              aq = 0.f;
+            }
+            aq = fmaf(f[t], dt, aq);
+          }
+        }
+        acc[qc] = aq;
+        if (qc == CPL - 1) cur = cq;
+      }
+      if (t1 < 32) break;
+      pos += 32;
+    }
+    if (cur >= 0) {
+#pragma unroll
+      for (int qc = 0; qc < CPL; ++qc) {
+        const int ch = lane + 32 * qc;
+        if (ch < a.C) a.out[voxel_of_local(bin, cur, n_bins) * a.C + ch] = acc[qc];
+      }
+    }
+  }
+
+  // ---- zero rows of the empty voxels (every output row is written exactly once) --------
+  const long long n_groups = (a.V + 31) >> 5;
+  const int c4 = a.C >> 2;                               // float4 per row (C % 4 == 0)
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!(dbg & 2))
+  for (long long g = gwarp; g < n_groups; g += nwarps) {
+    const unsigned empty = __ldcg(sc.empty + g);
+    if (empty == 0u) continue;
+    const long long v0 = g << 5;
+    for (int i = lane; i < 32 * c4; i += 32) {
+      const int row = i / c4;
+      if (((empty >> row) & 1u) && v0 + row < a.V)
+        __stcs(reinterpret_cast<float4*>(a.out + v0 * a.C) + i, z);
     }
   }
 }
@@ -507,20 +833,46 @@ struct LiftWs {
   int* list;    // [P]
   int* count;   // [V]
   int* start;   // [V]
-  unsigned* ctrl;  // 256 bytes: grid-barrier counter, list cursor
+  unsigned* ctrl;  // 256 bytes: control words (LiftFused::ctrl)
+  unsigned* bin_count;   // [n_bins]
+  LiftSched sc;
+  int n_bins;
 };
 
 inline long long align256(long long x) { return (x + 255) / 256 * 256; }
 
+// Bins per call: enough for <= BIN_GROUPS groups each, and PRIME so that the
+// group -> bin map (g % n_bins) does not resonate with the rows / slabs of the grid
+// (with 625 bins a 200x200x16 grid sends the same (x, y) column of every z slab to
+// one bin).
+inline int lift_n_bins(long long V) {
+  const long long groups = (V + 31) / 32;
+  long long n = (groups + BIN_GROUPS - 1) / BIN_GROUPS;
+  if (n < 2) return 1;
+  for (;; ++n) {
+    bool prime = true;
+    for (long long d = 2; d * d <= n && prime; ++d) prime = n % d != 0;
+    if (prime) return (int)n;
+  }
+}
+
 inline LiftWs carve(void* ws, long long P, long long V) {
   char* p = (char*)ws;
   LiftWs w;
+  w.n_bins = lift_n_bins(V);
+  const long long groups = (V + 31) / 32;
   w.ctrl = (unsigned*)p; p += 256;
+  w.bin_count = (unsigned*)p; p += align256((long long)w.n_bins * 4);
   w.rank = (int*)p; p += align256(P * 4);
   w.slot = (int*)p; p += align256(P * 4);
   w.list = (int*)p; p += align256(P * 4);
   w.count = (int*)p; p += align256(V * 4);
-  w.start = (int*)p;
+  w.start = (int*)p; p += align256(V * 4);
+  w.sc.bin_n = (int*)p; p += align256((long long)w.n_bins * 4);
+  w.sc.empty = (unsigned*)p; p += align256(groups * 4);
+  w.sc.desc = (unsigned*)p; p += align256((long long)w.n_bins * BIN_UNITS * 4);
+  w.sc.entries = (int2*)p; p += (long long)w.n_bins * BIN_CAP * (long long)sizeof(int2);
+  w.sc.sorted = (int2*)p;
   return w;
 }
 
@@ -537,21 +889,84 @@ inline LiftGeom make_geom(const float* cam, const float* bda, const float* xs, c
 
 template <int CPL, int MODE>
 int launch_lift_fused(const LiftFused& a, cudaStream_t st) {
-  // persistent grid: every CTA must be co-resident (grid barriers)
-  static int ctas_per_sm = 0, sms = 0;
-  if (ctas_per_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &ctas_per_sm, lift_fused_kernel<CPL, MODE>, LIFT_THREADS, 0);
-    if (e != cudaSuccess) return (int)e;
-    if (ctas_per_sm < 1) return PW_ERR_INVALID_ARGUMENT;
-    if (ctas_per_sm > 2) ctas_per_sm = 2;
+  // persistent grid with spin-wait grid barriers: every CTA must be co-resident.
+  // A COOPERATIVE launch makes the driver check that (it fails with
+  // cudaErrorCooperativeLaunchTooLarge under an SM partition / MPS limit instead of
+  // hanging); occupancy is cached per device.
+  static std::mutex mu;
+  static int cached_ctas[64], cached_sms[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  PW_REQUIRE(dev >= 0 && dev < 64);
+  int ctas_per_sm, sms;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cached_ctas[dev] == 0) {
+      e = cudaDeviceGetAttribute(&cached_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+      if (e != cudaSuccess) return (int)e;
+      int c = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, lift_fused_kernel<CPL, MODE>,
+                                                        LIFT_THREADS, 0);
+      if (e != cudaSuccess) return (int)e;
+      if (c < 1) return PW_ERR_INVALID_ARGUMENT;
+      cached_ctas[dev] = c > 2 ? 2 : c;
+    }
+    ctas_per_sm = cached_ctas[dev];
+    sms = cached_sms[dev];
   }
-  // grid == resident capacity, so all CTAs are co-resident as soon as the SMs
-  // drain (same guarantee a cooperative launch checks, without its launch cost)
-  lift_fused_kernel<CPL, MODE><<<sms * ctas_per_sm, LIFT_THREADS, 0, st>>>(a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(sms * ctas_per_sm));
+  cfg.blockDim = dim3(LIFT_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, lift_fused_kernel<CPL, MODE>, a);
+  if (e != cudaSuccess) return (int)e;
+  return 0;
+}
+
+int lift_sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+    n = 148;
+  return n;
+}
+
+// passes A + B: build the schedule
+int launch_lift_schedule(const LiftFused& a, const LiftWs& ws, cudaStream_t st) {
+  const int blocks_a = (int)((a.P + BINA_THREADS * BINA_PTS - 1) / (BINA_THREADS * BINA_PTS));
+  const size_t smem_a = (size_t)ws.n_bins * 8;
+  PW_REQUIRE(smem_a <= 200 * 1024);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(lift_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(lift_sort_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SORT_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  lift_bin_kernel<<<blocks_a, BINA_THREADS, smem_a, st>>>(a.g, a.P, ws.n_bins, ws.sc.entries,
+                                                        ws.bin_count, ws.ctrl);
+  PW_LAUNCH_CHECK();
+  lift_sort_bins_kernel<<<ws.n_bins, SORT_THREADS, SORT_SMEM, st>>>(a, ws.sc);
+  PW_LAUNCH_CHECK();
+  return 0;
+}
+
+// pass C: pool with the schedule
+template <int CPL>
+int launch_lift_pool(const LiftFused& a, const LiftWs& ws, int pool_only, cudaStream_t st) {
+  const int blocks = lift_sm_count() * 3;               // 3 CTAs per SM resident: one wave
+  static const int dbg = [] { const char* e = getenv("PW_LIFT_DBG"); return e ? atoi(e) : 0; }();
+  lift_pool_sched_kernel<CPL><<<blocks, POOL_THREADS, 0, st>>>(a, ws.sc, pool_only, dbg);
   PW_LAUNCH_CHECK();
   return 0;
 }
@@ -561,7 +976,10 @@ int launch_lift_fused(const LiftFused& a, cudaStream_t st) {
 PW_API long long pw_lift_workspace_bytes(int b, int n, int d, int h, int w, int gx, int gy,
                                          int gz) {
   long long P = (long long)b * n * d * h * w, V = (long long)b * gx * gy * gz;
-  return 256 + 3 * align256(P * 4) + 2 * align256(V * 4);
+  const long long n_bins = lift_n_bins(V), groups = (V + 31) / 32;
+  return 256 + 2 * align256(n_bins * 4) + 3 * align256(P * 4) + 2 * align256(V * 4) +
+         align256(groups * 4) + align256(n_bins * BIN_UNITS * 4) +
+         2 * n_bins * BIN_CAP * (long long)sizeof(int2);
 }
 
 PW_API int pw_lift_ranks(const float* cam, const float* bda, const float* xs, const float* ys,
@@ -594,10 +1012,19 @@ PW_API int pw_lift_fused(const float* depth, const float* feat, int feat_ld, con
   a.depth = depth; a.feat = feat; a.feat_ld = feat_ld; a.C = c; a.out = out;
   a.rank = ws.rank; a.slot = ws.slot; a.count = ws.count; a.start = ws.start; a.list = ws.list;
   a.ctrl = ws.ctrl; a.P = P; a.V = V;
-  int rc = c <= 32 ? launch_lift_fused<1, 0>(a, st)
-                   : (c <= 64 ? launch_lift_fused<2, 0>(a, st) : launch_lift_fused<4, 0>(a, st));
+  a.bin_count = ws.bin_count; a.n_bins = ws.n_bins;
+  PW_REQUIRE((c & 3) == 0);
+  // schedule (A, B), pool (C), and the persistent kernel as fallback: an immediate
+  // exit unless a bin overflowed
+  int rc = launch_lift_schedule(a, ws, st);
   if (rc != 0) return rc;
-  pw_count_launch(1);
+  rc = c <= 32 ? launch_lift_pool<1>(a, ws, 0, st)
+               : (c <= 64 ? launch_lift_pool<2>(a, ws, 0, st) : launch_lift_pool<4>(a, ws, 0, st));
+  if (rc != 0) return rc;
+  rc = c <= 32 ? launch_lift_fused<1, 0>(a, st)
+               : (c <= 64 ? launch_lift_fused<2, 0>(a, st) : launch_lift_fused<4, 0>(a, st));
+  if (rc != 0) return rc;
+  pw_count_launch(4);
   return 0;
 }
 
@@ -633,9 +1060,12 @@ PW_API int pw_lift_prepare(const float* cam, const float* bda, const float* xs, 
   a.C = 4;
   a.rank = ws.rank; a.slot = ws.slot; a.count = ws.count; a.start = ws.start; a.list = ws.list;
   a.ctrl = ws.ctrl; a.P = P; a.V = V;
-  int rc = launch_lift_fused<1, 1>(a, (cudaStream_t)stream);
+  a.bin_count = ws.bin_count; a.n_bins = ws.n_bins;
+  int rc = launch_lift_schedule(a, ws, (cudaStream_t)stream);
   if (rc != 0) return rc;
-  pw_count_launch(1);
+  rc = launch_lift_fused<1, 1>(a, (cudaStream_t)stream);    // fallback lists (overflow only)
+  if (rc != 0) return rc;
+  pw_count_launch(3);
   return 0;
 }
 
@@ -655,10 +1085,14 @@ PW_API int pw_lift_pool(const float* depth, const float* feat, int feat_ld, int 
   a.depth = depth; a.feat = feat; a.feat_ld = feat_ld; a.C = c; a.out = out;
   a.rank = ws.rank; a.slot = ws.slot; a.count = ws.count; a.start = ws.start; a.list = ws.list;
   a.ctrl = ws.ctrl; a.P = P; a.V = V;
+  a.bin_count = ws.bin_count; a.n_bins = ws.n_bins;
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = c <= 32 ? launch_lift_fused<1, 2>(a, st)
-                   : (c <= 64 ? launch_lift_fused<2, 2>(a, st) : launch_lift_fused<4, 2>(a, st));
+  int rc = c <= 32 ? launch_lift_pool<1>(a, ws, 1, st)
+                   : (c <= 64 ? launch_lift_pool<2>(a, ws, 1, st) : launch_lift_pool<4>(a, ws, 1, st));
   if (rc != 0) return rc;
-  pw_count_launch(1);
+  rc = c <= 32 ? launch_lift_fused<1, 2>(a, st)          // only if the lists are the fallback's
+               : (c <= 64 ? launch_lift_fused<2, 2>(a, st) : launch_lift_fused<4, 2>(a, st));
+  if (rc != 0) return rc;
+  pw_count_launch(2);
   return 0;
 }

@@ -952,3 +952,44 @@ def test_occhead_tail_matches_torch(grid):
     assert torch.equal(occ[clear], logits[0].argmax(-1).permute(2, 1, 0)[clear])
     geo = both[1].cpu().long()
     assert torch.equal(geo, torch.where(occ == 17, 17, 0))
+
+
+def test_lift_bin_overflow_falls_back_bit_exact():
+    """pw_lift_fused bins the kept points by voxel range (1024 voxels per bin, 4096
+    entries); when a bin overflows -- here a coarse 8x8x16 grid over +-64 m: ONE bin for every
+    kept point -- the call is taken by the persistent fallback kernel.  Both give
+    the bits of the C oracle, and the workspace is left clean for the next call
+    (a second, non-overflowing lift with the same workspace cache)."""
+    geo, s2k, intr, pr, pt, bda = _lift_setup(1, seed=7)
+    coarse = dict(geo.grid_config, x=[-64, 64, 16.0], y=[-64, 64, 16.0], z=[-20, 44, 4.0])
+    geo2 = torch_ref.LiftGeometry(coarse, (64, 176), 16, 32)
+    B, N = s2k.shape[:2]
+    D, H, W = geo2.frustum.shape[:3]
+    xs, ys, ds = geo2.frustum[0, 0, :, 0], geo2.frustum[0, :, 0, 1], geo2.frustum[:, 0, 0, 2]
+    g = torch.Generator().manual_seed(1)
+    depth = torch.rand(B * N, D, H, W, generator=g).softmax(1)
+    feat = torch.randn(B * N, H, W, 32, generator=g)
+    cam = ops.lift_camera_params(s2k.to(DEV), intr.to(DEV), pr.to(DEV), pt.to(DEV))
+    cam_ref = cam.cpu().numpy()
+    for gg in (geo2, geo):                      # overflow first, then the normal path
+        grid = tuple(int(v) for v in gg.grid_size)
+        rank_ref = c_ref.lift_ranks(B, N, xs.numpy(), ys.numpy(), ds.numpy(), cam_ref,
+                                    bda.numpy(), gg.lower.numpy(), gg.interval.numpy(), grid)
+        valid = np.where(rank_ref >= 0)[0]
+        if gg is geo2:
+            assert len(valid) > 4096 and grid[0] * grid[1] * grid[2] <= 1024
+        order = valid[np.argsort(rank_ref[valid], kind='stable')]
+        rb = rank_ref[order].astype(np.int32)
+        hw = H * W
+        rf = ((order // (D * hw)) * hw + order % hw).astype(np.int32)
+        kept = np.ones(len(rb), bool)
+        kept[1:] = rb[1:] != rb[:-1]
+        starts = np.where(kept)[0].astype(np.int32)
+        lengths = np.diff(np.append(starts, len(rb))).astype(np.int32)
+        want = c_ref.bev_pool_v2_fwd(depth.numpy().ravel(), feat.numpy().reshape(-1, 32),
+                                     order.astype(np.int32), rf, rb, starts, lengths,
+                                     B * grid[0] * grid[1] * grid[2])
+        got = ops.lift_fused(depth.to(DEV), feat.to(DEV), cam, bda.reshape(B, 9).to(DEV),
+                             xs.to(DEV), ys.to(DEV), ds.to(DEV), gg.lower.tolist(),
+                             gg.interval.tolist(), B, N, grid)
+        assert np.array_equal(got.cpu().numpy().reshape(-1, 32), want)
