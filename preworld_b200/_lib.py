@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libpreworld_b200.so')
+# PW_LIB selects another build of the SAME library (the instrumented `make debug` one)
+LIB_PATH = os.environ.get('PW_LIB') or os.path.join(_HERE, 'lib', 'libpreworld_b200.so')
 
 c_int = ctypes.c_int
 c_ll = ctypes.c_longlong

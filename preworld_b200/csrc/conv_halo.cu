@@ -99,6 +99,8 @@ struct HaloParams {
   int stage_off;               // byte offset of the epilogue staging (0: aliases the halo ring)
   int stage_bytes;             // bytes reserved between the weight ring and the barriers
   int cps;                     // CTAs per SM the plan counts on (1 or 2)
+  int zero;                    // always 0: added to values read through a scoreboarded load so that
+                               // later uses depend on an ALU result (see tmem_base below)
   int dbg;                     // PW_HALO_DBG knock-out bits (timing experiments only)
   long long* ts;               // PW_HALO_TS: per-CTA clock64 milestones (debug)
   int out_ld, res_ld, act, act_channels;
@@ -115,6 +117,11 @@ struct HaloParams {
 #ifdef PW_HALO_DEBUG
 #define PW_TSON (p.ts != nullptr)
 #define PW_DBG(bit) ((p.dbg & (bit)) != 0)
+#elif defined(PW_HALO_KO)
+// compile-time knock-outs (make ko KO=<bits>): no run-time checks in the loops, so
+// the variant runs at the product build's speed minus the removed work
+#define PW_TSON false
+#define PW_DBG(bit) (((PW_HALO_KO) & (bit)) != 0)
 #else
 #define PW_TSON false
 #define PW_DBG(bit) false
@@ -142,6 +149,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
   const uint32_t accum_bar = a_full + 8 * p.nb * p.mt;
   const uint32_t acc_empty = accum_bar + 8;      // epilogue done reading the accumulators
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * p.nh + p.nb * (2 + p.mt) + 2);
+  // halo-row offset of every tap (the split loop indexes it instead of carrying kx/ky/kz)
+  int* tap_tab = reinterpret_cast<int*>(tmem_holder + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -162,13 +171,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     mbar_init(acc_empty, 4 * SPLIT_SETS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int t = threadIdx.x; t < p.n_taps; t += blockDim.x) {
+    const int kx = t % p.kw, ky = (t / p.kw) % p.kh, kz = t / (p.kw * p.kh);
+    tap_tab[t] = ((kz * p.dd) * p.hy + ky * p.dh) * p.hx + kx * p.dw;
+  }
   if (warp == 2) tmem_alloc(smem_u32(tmem_holder), (uint32_t)p.tmem_cols);
   if (warp == 0 && lane == 0) prefetch_tensormap(&map_a);
   if (warp == 1 && lane == 0) { prefetch_tensormap(&map_bh); prefetch_tensormap(&map_bl); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
+  // `+ p.zero`: the sum is an ALU result.  Used directly, every later use of the loaded
+  // register statically depends on the load's scoreboard slot, which ptxas re-uses for the
+  // epilogue's residual loads -- the TMEM loads then waited for the residual prefetch
+  // (17 % of all stall samples on the 64->256 pointwise layer).
+  const uint32_t tmem_base = *tmem_holder + (uint32_t)p.zero;
   if (threadIdx.x == 0) PW_TS(1);
   const int tile_cols = p.nacc * 2 * p.n_tile;          // TMEM columns of one M tile's accumulators
   const uint32_t a_ring_col = (uint32_t)(p.mt * tile_cols);
@@ -225,7 +242,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       for (int c = 0; c < p.chunks; ++c) {
         for (int t = 0; t < T; ++t) {
           mbar_wait(ring_empty + 8 * s, ph);
-          if (leader) {
+          if (leader && PW_DBG(64)) mbar_arrive(b_full + 8 * s);   // (64: no weight loads)
+          else if (leader) {
             mbar_expect_tx(b_full + 8 * s, (uint32_t)b_stage);
             const uint32_t dst = b_ring_u32 + (uint32_t)(s * b_stage);
             const int k0 = (t * p.chunks + c) * BLOCK_K; // weights are tap-major in K
@@ -268,7 +286,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
         if (PW_TSON) { cyc_a += clock64() - tq; tq = clock64(); }
         const uint32_t a_hi = tbase + a_ring_col + (uint32_t)((r * p.mt + m) * A_SLOT_COLS);
         const uint32_t acc = tbase + (uint32_t)(m * tile_cols);
-        if (leader) {
+        if (leader && !PW_DBG(1)) {                              // (1: commits only, no MMA)
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 8; ++k) {
             const uint64_t bd = bdesc + (uint64_t)(k * 2);     // +32 bytes inside the swizzle row
@@ -284,7 +302,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
         if (PW_TSON) cyc_i += clock64() - tq;
       }
       accumulate = 1;
-      if (leader) umma_commit(ring_empty + 8 * r);   // weight stage + A slots free on retire
+      if (leader) {                                  // weight stage + A slots free on retire
+        if (PW_DBG(8)) mbar_arrive(ring_empty + 8 * r);      // (8, with 1: plain arrive, no commit)
+        else umma_commit(ring_empty + 8 * r);
+      }
       __syncwarp();
       if (++r == p.nb) { r = 0; ph ^= 1; }
     }
@@ -312,24 +333,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     // This set builds the A tiles of M tile `m_set` for taps tap0, tap0+tstep, ...
     // of every chunk (it = (c*T + t)*mt + m; sets take it = set, set+SETS, ...).  All state advances incrementally -- the loop body
     // is the critical instruction stream of the kernel (8 warps on 4 schedulers).
-    int m_cur = set % p.mt;                              // M tile of the current iteration
-    int c = 0, kx = 0, ky = 0, kz = 0, r = 0, hs = 0;
+    int m_cur = set & (p.mt - 1);                        // M tile of the current iteration (mt is 1 or 2)
+    const int lmt = p.mt - 1;                            // log2(mt)
+    int c = 0, t = 0, r = 0, hs = 0;                     // chunk, tap, ring entry, halo slot
     uint32_t eph = 1u, hph = 0u;                         // parities: ring_empty, halo_full
-    auto step_tap = [&]() {                              // advance (c, tap, ring entry) by one tap
-      if (++r == p.nb) { r = 0; eph ^= 1u; }
-      if (++kx < p.kw) return;
-      kx = 0;
-      if (++ky < p.kh) return;
-      ky = 0;
-      if ((++kz) * p.kh * p.kw < T) return;
-      kz = 0;
-      ++c;
-      if (++hs == p.nh) { hs = 0; hph ^= 1u; }
+    const uint32_t tap_tab_u32 = smem_u32(tap_tab);
+    auto advance_taps = [&](int n) {                     // n <= nb (enforced by the planner)
+      r += n;
+      if (r >= p.nb) { r -= p.nb; eph ^= 1u; }
+      t += n;
+      while (t >= T) {                                   // next chunk (T may be 1: twice)
+        t -= T;
+        ++c;
+        if (++hs == p.nh) { hs = 0; hph ^= 1u; }
+      }
     };
     float4 raw[8];
     auto load_row = [&]() {
-      const int hrow = row_base + m_cur * p.mt_halo_off +
-                       ((kz * p.dd) * p.hy + ky * p.dh) * p.hx + kx * p.dw;
+      int toff;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(toff) : "r"(tap_tab_u32 + (uint32_t)(t << 2)));
+      const int hrow = row_base + m_cur * p.mt_halo_off + toff;
       // 16-byte chunk j of row hrow sits at ((j ^ (hrow & 7)) << 4) (TMA 128B swizzle)
       const uint32_t b2 = (smem_base_u32 + (uint32_t)(hs * p.halo_stride + hrow * ROW_BYTES)) ^
                           (uint32_t)((hrow & 7) << 4);
@@ -349,7 +372,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       __syncwarp();
       if (lane == 0) mbar_arrive(halo_empty + 8 * slot);
     };
-    for (int q = 0; q < set / p.mt; ++q) step_tap();     // first tap of this set
+    advance_taps(set >> lmt);                            // first tap of this set
     // The (chunk, tap, M tile) sequence of a persistent CTA simply runs on across its
     // tiles: a set whose stride overshoots a tile's end starts the next one mid-way.
     int iter = 0;
@@ -377,6 +400,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       const uint32_t ring_ph = eph;
       // hi (columns 0..31) and lo (32..63) of this row, stored by ONE tcgen05.st
       uint32_t hl[64];
+      if (!PW_DBG(2))                                      // (2: no hi/lo split)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 v = raw[j];
@@ -389,10 +413,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
         hl[BLOCK_K + j * 4] = __float_as_uint(l0); hl[BLOCK_K + j * 4 + 1] = __float_as_uint(l1);
         hl[BLOCK_K + j * 4 + 2] = __float_as_uint(l2); hl[BLOCK_K + j * 4 + 3] = __float_as_uint(l3);
       }
+      // raw[] is consumed: advance to this set's next row (it += SPLIT_SETS in (tap, m)
+      // space) and, inside the same chunk (the common case), fetch it NOW -- the
+      // shared-memory latency then runs under the barrier traffic below instead of
+      // heading the next iteration's dependency chain
+      const int c_prev = c;
+      {
+        const int mm = m_cur + SPLIT_SETS;
+        m_cur = mm & (p.mt - 1);
+        advance_taps(mm >> lmt);
+      }
+      const bool same_chunk = c == c_prev;
+      if (same_chunk && !PW_DBG(4)) load_row();            // (4: no halo row loads)
       // the PREVIOUS row's store is published only now: its completion latency
       // ran under this row's hi/lo split
       if (pending >= 0) {
-        tmem_st_wait();
+        if (!PW_DBG(16)) tmem_st_wait();                   // (16: no TMEM store, no wait for it)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full + 8 * pending);
@@ -406,28 +442,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
         if (PW_TSON) { sp_wait += clock64() - tw; sp_t0 = clock64(); }
       }
       if (PW_DBG(1024)) tmem_st32(a_col, hl);            // (timing experiment: half the bytes)
-      else if (!PW_DBG(2048)) tmem_st64(a_col, hl);    // (2048: no store at all)
+      else if (!PW_DBG(2048) && !PW_DBG(16)) tmem_st64(a_col, hl);    // (2048: no store at all)
       pending = slot;
-      // hl[] is handed to the store: only now fetch this set's next row (keeps
-      // raw[] and hl[] from being live together: 4 sets = 608 threads = 104 regs)
-      const int c_prev = c;
-      {                                                  // it += SPLIT_SETS in (tap, m) space
-        const int mm = m_cur + SPLIT_SETS;
-        const int taps = mm / p.mt;                      // mt is 1 or 2
-        m_cur = mm - taps * p.mt;
-#pragma unroll 1
-        for (int q = 0; q < taps; ++q) step_tap();
-      }
-      if (c != c_prev) {                                 // chunk boundary (rare)
+      if (!same_chunk) {                                 // chunk boundary (rare)
         const int upto = c < p.chunks ? c : p.chunks;
 #pragma unroll 1
         while (released < upto) {                        // chunks this warp is done reading
           release_chunk(released);
           ++released;
         }
-        if (c < p.chunks) mbar_wait(halo_full + 8 * hs, hph);
+        if (c < p.chunks) {
+          mbar_wait(halo_full + 8 * hs, hph);
+          if (!PW_DBG(4)) load_row();
+        }
       }
-      if (c < p.chunks) load_row();
     }
     if (pending >= 0) {
       tmem_st_wait();
@@ -499,7 +527,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     mbar_wait(accum_bar, (uint32_t)(iter & 1));
     tc_fence_after();
     if (sw_id == 0 && lane == 0) PW_TS(7);
-    for (int item = set; item < items; item += SPLIT_SETS) {
+    for (int item = set; item < items && !PW_DBG(32); item += SPLIT_SETS) {   // (32: no epilogue)
       const int m = item / ncg;
       const int col0 = (item - m * ncg) * cgw;
       const int ncol = min(cgw, n_real - col0);          // 16 or 32 (warp-uniform)
@@ -658,7 +686,9 @@ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int SMEM_LIMIT_2CTA = (228 * 1024 - 2 * 1024) / 2;   // two CTAs + 1 KB reserved each
-constexpr int SMEM_SLACK = 1024 /*align*/ + (6 * MAX_RING + 1) * 8 + 16;   // barriers: 2nh + nb(2+mt) + 2
+constexpr int MAX_TAPS = 64;                 // tap table entries (7x7 stem, 3x3x3 volume convs)
+constexpr int SMEM_SLACK = 1024 /*align*/ + (6 * MAX_RING + 1) * 8 + 16 +   // barriers: 2nh + nb(2+mt) + 2
+                           MAX_TAPS * 4;                                   // + tap table
 
 struct HaloPlan {
   bool ok = false;
@@ -704,7 +734,19 @@ const HaloPlan& make_plan(const pw_conv_desc& in) {
   std::string k(reinterpret_cast<const char*>(&key), sizeof(key));
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(k);
-  if (it == cache.end()) it = cache.emplace(k, make_plan_uncached(key)).first;
+  if (it == cache.end()) {
+    it = cache.emplace(k, make_plan_uncached(key)).first;
+    static const bool show = getenv("PW_HALO_PLAN") != nullptr;
+    if (show && it->second.ok) {
+      const HaloPlan& pl = it->second;
+      const HaloParams& p = pl.p;
+      fprintf(stderr, "[halo plan] %dx%dx%dx%d cin %d cout %d k %dx%dx%d: grid %u mt %d(axis %d) n_tile %d nh %d nb %d "
+              "box %dx%dx%d halo %dx%dx%d (%d B) smem %zu tmem %d sets %d tiles %d\n",
+              in.n, in.d, in.h, in.w, in.cin, in.cout, in.kd, in.kh, in.kw, pl.grid.x, p.mt, p.mt_axis,
+              p.n_tile, p.nh, p.nb, p.cbx, p.cby, p.cbz, p.hx, p.hy, p.hz, p.halo_stride, pl.smem,
+              p.tmem_cols, pl.sets, p.total_tiles);
+    }
+  }
   return it->second;
 }
 
@@ -787,6 +829,7 @@ HaloPlan search_plan(const pw_conv_desc& in, const int SPLIT_SETS, const int tme
   }
   const int chunks = c.cin / BLOCK_K;
   const int T = c.kd * c.kh * (fold ? 1 : c.kw);         // taps the main loop iterates
+  if (T > MAX_TAPS) return plan;
   static const int boxes3[][3] = {{8, 4, 4}, {8, 8, 2}, {16, 4, 2}, {16, 8, 1}, {8, 16, 1},
                                   {32, 4, 1}, {16, 2, 4}, {32, 2, 2}, {8, 2, 8}};
   static const int boxes2[][3] = {{16, 8, 1}, {8, 16, 1}, {32, 4, 1}, {64, 2, 1}, {128, 1, 1}};
