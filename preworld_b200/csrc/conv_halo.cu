@@ -65,6 +65,25 @@ constexpr int A_SLOT_COLS = 2 * BLOCK_K;     // hi | lo
 constexpr int STAGE_BYTES_PER_WARP = 32 * ROW_BYTES;
 constexpr int MAX_RING = 8;
 
+// n / d for 0 <= n < 2^31 with a precomputed multiplier (the tile decode runs once per
+// tile in three warp roles; four hardware divisions were ~140 instructions)
+struct FastDiv {
+  uint32_t mul, shift;
+  int d;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t s = 0;
+  while ((1u << s) < (uint32_t)d) ++s;
+  f.shift = s;
+  f.mul = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << s) - (uint64_t)d)) / (uint64_t)d + 1);
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+  return (int)((__umulhi((uint32_t)n, f.mul) + (uint32_t)n) >> f.shift);
+}
+
 struct HaloParams {
   int od, oh, ow, cout;
   int kh, kw, n_taps, chunks;
@@ -96,6 +115,7 @@ struct HaloParams {
   // weight stages of the next tile load under the current tile's taps and epilogue),
   // and the epilogue stages through its own shared-memory region (stage_off).
   int total_tiles, sp_tiles, slabs;
+  FastDiv fd_sp, fd_tx, fd_ty, fd_tz;   // dividers of the tile decode
   int stage_off;               // byte offset of the epilogue staging (0: aliases the halo ring)
   int stage_bytes;             // bytes reserved between the weight ring and the barriers
   int cps;                     // CTAs per SM the plan counts on (1 or 2)
@@ -194,12 +214,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
   struct Tile { int x0, y0, z0, img, slab; };
   auto decode = [&](int t) {
     Tile tl;
-    tl.slab = t / p.sp_tiles;
+    tl.slab = fdiv(t, p.fd_sp);
     int tt = t - tl.slab * p.sp_tiles;
-    const int tx = tt % p.tiles_x; tt /= p.tiles_x;
-    const int ty = tt % p.tiles_y; tt /= p.tiles_y;
-    const int tz = tt % p.tiles_z;
-    tl.img = tt / p.tiles_z;
+    int qd = fdiv(tt, p.fd_tx);
+    const int tx = tt - qd * p.tiles_x; tt = qd;
+    qd = fdiv(tt, p.fd_ty);
+    const int ty = tt - qd * p.tiles_y; tt = qd;
+    tl.img = fdiv(tt, p.fd_tz);
+    const int tz = tt - tl.img * p.tiles_z;
     tl.x0 = tx * p.cbx; tl.y0 = ty * p.cby; tl.z0 = tz * p.cbz;
     return tl;
   };
@@ -238,7 +260,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     int s = 0;
     uint32_t ph = 1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int n0w = (tile / p.sp_tiles) * p.n_tile;    // weight rows of this N slab
+      const int n0w = fdiv(tile, p.fd_sp) * p.n_tile;    // weight rows of this N slab
       for (int c = 0; c < p.chunks; ++c) {
         for (int t = 0; t < T; ++t) {
           mbar_wait(ring_empty + 8 * s, ph);
@@ -514,7 +536,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       const int m = item / ncg;
       const int cb = n0 + (item - m * ncg) * cgw + ch4 * 4;
       const bool on = p.res != nullptr && vec_ok && cb + 4 <= p.cout && ch4 * 4 < cgw &&
-                      (item - m * ncg) * cgw + ch4 * 4 < n_real;
+                      (item - m * ncg) * cgw + ch4 * 4 < n_real && !PW_DBG(256);   // (256: no residual loads)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int pixi = m == 0 ? rowpix[0][i] : rowpix[1][i];
@@ -633,7 +655,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
             o.y = relu ? fmaxf(o.y, 0.f) : o.y;
             o.z = relu ? fmaxf(o.z, 0.f) : o.z;
             o.w = relu ? fmaxf(o.w, 0.f) : o.w;
-            if (pixi >= 0)
+            if (pixi >= 0 && !PW_DBG(128))                     // (128: no output stores)
               *reinterpret_cast<float4*>(const_cast<float*>(yb) + (size_t)pixi * ldo) = o;
           }
         } else {
@@ -941,6 +963,8 @@ HaloPlan search_plan(const pw_conv_desc& in, const int SPLIT_SETS, const int tme
             p.out_bx = fold ? cb[0] : b[0];
             p.tiles_x = pw_ceil_div(c.ow, cb[0]); p.tiles_y = pw_ceil_div(c.oh, cb[1]);
             p.tiles_z = pw_ceil_div(c.od, cb[2]);
+            p.fd_sp = make_fastdiv(p.sp_tiles); p.fd_tx = make_fastdiv(p.tiles_x);
+            p.fd_ty = make_fastdiv(p.tiles_y); p.fd_tz = make_fastdiv(p.tiles_z);
             p.n_tile = n_tile; p.nh = nh; p.nb = nb; p.nacc = nacc;
             int cols = acc_cols + nb * mt * A_SLOT_COLS, pw2 = 32;
             while (pw2 < cols) pw2 <<= 1;
