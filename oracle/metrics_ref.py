@@ -1,8 +1,11 @@
 """TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): numpy restatement of
 Metric_mIoU (mmdet3d/datasets/occ_metrics.py:93-185) used to check
 preworld_b200.metrics / pw_occ_confusion.  Parity pin: the reference ships no
-test for it; the restatement follows the reference line by line and is
-checked against a brute-force loop in tests/test_oracle.py."""
+test for it; the restatement is pinned against the reference's own file --
+occ_metrics.py imported by path in the build container (oracle/make_metrics_golden.py)
+and the committed tests/golden/occ_metrics.json it produced (confusion matrices
+bit-equal, mIoU / IoU to the reference's rounding; tests/test_oracle.py) -- and
+against a brute-force loop."""
 import numpy as np
 
 

@@ -105,6 +105,10 @@ def loss_voxel(output_voxels, target_voxels, class_weights, empty_idx,
     focal loss unless ``use_focal_loss=False``, as in the reference):
     ``class_weights`` are the per-class weights WITHOUT the empty class (a zero
     is appended, preworld.py:150)."""
+    # preworld.py:130-131: non-finite logits are zeroed before any term is formed (one
+    # NaN would otherwise poison all four losses and their gradients); the gradient
+    # of a sanitised logit is zero, as with the reference's in-place assignment
+    output_voxels = torch.nan_to_num(output_voxels, nan=0.0, posinf=0.0, neginf=0.0)
     cw = torch.cat([class_weights.to(output_voxels.device).float(),
                     torch.zeros(1, device=output_voxels.device)])
     t = voxel_loss_terms(output_voxels, target_voxels, cw, 255, empty_idx,

@@ -26,15 +26,29 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _ptr(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
-
-
 def _require_cuda(*ts):
+    """Every operand on ONE CUDA device, and that device current: the kernels are
+    launched on the current device's current stream (`_stream`), so a tensor of
+    another device would be a wrong-device launch, not an error, without this."""
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError(
                 'preworld_b200 ops run on CUDA tensors only (no CPU fallback)')
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f'operands on different devices: {dev} and {t.device}')
+    if dev is not None and dev.index != torch.cuda.current_device():
+        raise RuntimeError(
+            f'tensors live on {dev} but the current device is cuda:'
+            f'{torch.cuda.current_device()}: wrap the call in torch.cuda.device({dev.index})')
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
 def cl_ld(t):

@@ -80,3 +80,61 @@ class CameraShard:
         dist.all_gather_into_tensor(recv.view(-1), src.reshape(-1), group=self.group)
         out = recv.permute(1, 0, 2, 3).reshape(B, self.world * mx, F)
         return out if even else out.index_select(1, idx)
+
+
+# ---- end of evaluation: result gather (mmdet3d/apis/test.py:165-195) -----------------
+def interleave_parts(part_list, size):
+    """The reference's ordering: the sampler deals samples round-robin, so rank r holds
+    samples r, r + world, ...; ``zip`` the parts, flatten, drop the dataloader's padding."""
+    ordered = []
+    for res in zip(*part_list):
+        ordered.extend(list(res))
+    return ordered[:size]
+
+
+def collect_occupancy(grids, size, group=None):
+    """``collect_results_gpu`` for what this path produces -- a list of equally shaped
+    uint8 occupancy grids per rank (device tensors or arrays) -- WITHOUT the pickle round
+    trip: the grids are stacked, exchanged by ONE ``all_gather_into_tensor`` and re-ordered
+    on rank 0.  Returns the ordered list of ``size`` grids on rank 0, ``None`` elsewhere
+    (the reference's contract).  Every rank must hold the same number of grids (the
+    reference's DistributedSampler pads to that)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    part = torch.stack([torch.as_tensor(g) for g in grids])
+    if world == 1:
+        return list(part[:size])
+    recv = part.new_empty((world,) + tuple(part.shape))
+    dist.all_gather_into_tensor(recv.view(-1), part.contiguous().view(-1), group=group)
+    if rank != 0:
+        return None
+    return interleave_parts([list(recv[r]) for r in range(world)], size)
+
+
+def collect_results(result_part, size, group=None):
+    """Generic form (arbitrary picklable per-sample results, e.g. the detectors' dicts):
+    same contract and ordering as ``collect_results_gpu`` (apis/test.py:165-195)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world == 1:
+        return list(result_part)[:size]
+    parts = [None] * world
+    dist.all_gather_object(parts, list(result_part), group=group)
+    if rank != 0:
+        return None
+    return interleave_parts(parts, size)
+
+
+def reduce_confusion(hists, group=None):
+    """Sum the ranks' confusion matrices in place (ONE all-reduce of the concatenated
+    counters): with `Metric_mIoU` accumulated on each rank's device this replaces the
+    gather of every prediction for the evaluation itself."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return hists
+    flat = torch.cat([h.reshape(-1) for h in hists])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    o = 0
+    for h in hists:
+        h.copy_(flat[o:o + h.numel()].view_as(h))
+        o += h.numel()
+    return hists

@@ -234,53 +234,3 @@ def test_no_cpu_fallback():
     det = build_model(model_cfg('finetune', 'r50', (64, 176)))
     with pytest.raises(NotImplementedError):
         det(return_loss=True)
-
-
-def _reference_prepare_image_inputs(reference_root):
-    """The PrepareImageInputs class of the reference, executed from its own file
-    (only that ClassDef: the module imports mmcv / pyquaternion at the top)."""
-    import ast
-    import numpy as np
-    path = os.path.join(reference_root, 'mmdet3d', 'datasets', 'pipelines', 'loading.py')
-    tree = ast.parse(open(path).read())
-    node = next(n for n in tree.body
-                if isinstance(n, ast.ClassDef) and n.name == 'PrepareImageInputs')
-    node.decorator_list = []
-    ns = dict(torch=torch, np=np, mmlabNormalize=None, Image=None, os=os)
-    exec(compile(ast.Module(body=[node], type_ignores=[]), path, 'exec'), ns)
-    return ns['PrepareImageInputs']
-
-
-def test_image_augmentation_matrices_match_reference(reference_root):
-    """preworld_b200/inputs.py against PrepareImageInputs.sample_augmentation /
-    img_transform (loading.py:925-1000): test branch, flipped / scaled test
-    branch, and the training branch under the same numpy seed."""
-    import numpy as np
-    from preworld_b200 import inputs
-    cls = _reference_prepare_image_inputs(reference_root)
-    cfg = dict(cams=['a'] * 6, Ncams=6, input_size=(256, 704), src_size=(900, 1600),
-               resize=(-0.06, 0.11), rot=(-5.4, 5.4), flip=True, crop_h=(0.0, 0.0),
-               resize_test=0.0)
-    for is_train, flip, scale, seed in ((False, None, None, 0), (False, True, 0.04, 0),
-                                        (True, None, None, 1), (True, None, None, 2)):
-        ref = cls(cfg, is_train=is_train)
-        ref.img_transform_core = lambda img, *a, **k: img
-        np.random.seed(seed)
-        r_aug = ref.sample_augmentation(H=900, W=1600, flip=flip, scale=scale)
-        resize, resize_dims, crop, fl, rotate = r_aug
-        _, r_rot, r_tran = ref.img_transform(None, torch.eye(2), torch.zeros(2), resize=resize,
-                                             resize_dims=resize_dims, crop=crop, flip=fl,
-                                             rotate=rotate)
-        np.random.seed(seed)
-        m_aug = inputs.sample_augmentation(900, 1600, cfg, is_train, flip, scale)
-        assert tuple(m_aug[1]) == tuple(resize_dims) and tuple(m_aug[2]) == tuple(crop)
-        assert m_aug[0] == resize and bool(m_aug[3]) == bool(fl) and m_aug[4] == rotate
-        rot3, tran3 = inputs.aug_matrices(*[m_aug[i] for i in (0, 2, 3, 4)])
-        assert torch.equal(rot3[:2, :2], r_rot) and torch.equal(tran3[:2], r_tran)
-        assert rot3[2, 2] == 1 and tran3[2] == 0
-    # the bench's synthetic rig is the test branch of this function
-    rots, trans, params = inputs.camera_augmentations([(900, 1600)] * 6, cfg, num_frames=3)
-    assert rots.shape == (18, 3, 3) and trans.shape == (18, 3)
-    assert torch.allclose(rots[0], torch.diag(torch.tensor([0.44, 0.44, 1.0])))
-    assert torch.equal(trans[0], torch.tensor([0., -140., 0.]))
-    assert params[0]['crop'] == (0, 140, 704, 396)

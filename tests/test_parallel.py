@@ -11,7 +11,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from preworld_b200.parallel import CameraShard, camera_split
+from preworld_b200.parallel import (CameraShard, camera_split, collect_occupancy,
+                                    collect_results, reduce_confusion)
 
 
 def test_camera_split_covers_every_camera_once():
@@ -84,3 +85,55 @@ def test_all_gather_cams_gloo(world, n_cams):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(res) == [(r, True) for r in range(world)]
+
+
+def _gather_worker(rank, world, port, size, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        per_rank = -(-size // world)                   # the sampler pads to this
+        # sample s sits on rank s % world at position s // world (DistributedSampler)
+        ids = [rank + k * world for k in range(per_rank)]
+        grids = [torch.full((4, 3, 2), i % 251, dtype=torch.uint8) for i in ids]
+        got = collect_occupancy(grids, size)
+        dicts = [dict(semantic_occ=[g.numpy()], idx=i) for g, i in zip(grids, ids)]
+        got2 = collect_results(dicts, size)
+        ok = True
+        if rank == 0:
+            ok = len(got) == size and all(int(g[0, 0, 0]) == s % 251 for s, g in enumerate(got))
+            ok = ok and [d['idx'] for d in got2] == list(range(size))
+        else:
+            ok = got is None and got2 is None
+        hist = torch.full((18, 18), rank + 1, dtype=torch.int64)
+        occ = torch.arange(4, dtype=torch.int64) * (rank + 1)
+        reduce_confusion([hist, occ])
+        tot = world * (world + 1) // 2
+        ok = ok and bool((hist == tot).all()) and occ.tolist() == [0, tot, 2 * tot, 3 * tot]
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,size', [(2, 7), (3, 9)])
+def test_result_gather_gloo(world, size):
+    """collect_occupancy / collect_results keep the reference's ordering and truncation
+    (mmdet3d/apis/test.py:165-195); reduce_confusion sums the ranks' matrices."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, size, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(r, True) for r in range(world)]
+
+
+def test_result_gather_single_rank():
+    grids = [torch.full((2, 2), i, dtype=torch.uint8) for i in range(3)]
+    assert [int(g[0, 0]) for g in collect_occupancy(grids, 2)] == [0, 1]
+    assert collect_results([1, 2, 3], 2) == [1, 2]
