@@ -409,6 +409,18 @@ int pw_render_rays(const pw_render_desc* desc, const float* rays, int n_rays,
                    int col_ld, float* out_depth, float* out_sem, float* out_col,
                    float* out_last, unsigned char* out_valid, void* stream);
 
+/* NerfHead.compute_loss's reductions over the renderings of pw_render_rays
+ * (mmdet3d/models/nerf/nerf_head.py:271-291; silog_loss / l1_loss,
+ * nerf/utils.py:71-87; nn.CrossEntropyLoss(weight, 'mean')), masked rays only.
+ * sums [9] fp64 (zeroed inside): n, sum d, sum d^2 (d = log(depth + 1e-7) -
+ * log(rays[:,2])), sum w[t] nll, sum w[t] (t = rays[:,3]), sum |color - rays[:,13:16]|
+ * per channel, sum p log p + (1-p) log(1-p) of clamp(alphainv_last, 1e-6, 1-1e-6).
+ * The five loss values follow on the host from these nine numbers. */
+int pw_render_loss_sums(const float* rays, int n_rays, int n_sem, const float* depth,
+                        const float* sem, const float* col, const float* last,
+                        const unsigned char* valid, const float* class_weights,
+                        double* sums, void* stream);
+
 /* ------------------------------------------------------------------------
  * Evaluation: confusion matrices of Metric_mIoU.add_batch,
  * mmdet3d/datasets/occ_metrics.py:93-157, accumulated on the device.

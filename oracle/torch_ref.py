@@ -573,6 +573,26 @@ def forecast_step(sd, voxel_feats, ego_states):
     return res + voxel_feats
 
 
+def plan_trajectory(sd, fused_voxel_feats, ego_states):
+    """The planning branch of one forecasting step, preworld_temporal_traj.py:454-472
+    with DownScaleModule3DCustom (heads/occupancy_head.py:180-200): fused voxel
+    features [B,X,Y,Z,C] (reference layout) -> predicted displacement [B, 2]."""
+    e = ego_states.reshape(ego_states.shape[0], -1)
+    e = F.relu(_linear(sd, 'plan_head.0', e))
+    e = F.relu(_linear(sd, 'plan_head.2', e))
+    identity = _linear(sd, 'plan_head.4', e)
+    x = fused_voxel_feats.permute(0, 4, 1, 2, 3).contiguous()
+    for i in (1, 2, 3):
+        x = F.conv3d(x, sd[f'downscale.downscale{i}.weight'],
+                     sd[f'downscale.downscale{i}.bias'], stride=2)
+    scene = F.adaptive_avg_pool3d(x, (1, 1, 1)).flatten(1)
+    u = torch.cat([identity, scene], dim=-1)
+    for i in (0, 2, 4):
+        u = F.softplus(_linear(sd, f'ego_fusion_head.{i}', u))
+    fused = identity + _linear(sd, 'ego_fusion_head.6', u)
+    return _linear(sd, 'traj_head.2', F.softplus(_linear(sd, 'traj_head.0', fused)))
+
+
 def preworld4d_simple_test(sd, pc, inputs, temporal_ego_states, stages=None):
     """PreWorld4DTraj.simple_test, preworld_temporal_traj.py:213-371.  Every
     step feeds ``temporal_ego_states[0]`` (:331), as the reference does."""
@@ -693,3 +713,24 @@ def render_rays(ng, rays, bda, density, semantic, color):
     return dict(render_depth=depth * ng.radius, render_semantic=r_sem,
                 render_color=r_col, alphainv_last=last, ray_mask=mask,
                 n_samples=int(keep.sum()))
+
+
+def nerf_compute_loss(res, target_depth, target_semantic, target_color, class_weights,
+                      weight_depth=1.0, weight_semantic=1.0, weight_color=1.0,
+                      weight_entropy_last=0.01, use_depth_sup=True):
+    """NerfHead.compute_loss, nerf/nerf_head.py:271-291 (silog_loss / l1_loss,
+    nerf/utils.py:71-87), without the distortion term.  ``res`` holds the MASKED rays'
+    render_depth / render_semantic / render_color / alphainv_last."""
+    out = {}
+    if use_depth_sup:
+        d = torch.log(res['render_depth'] + 1e-7) - torch.log(target_depth)
+        out['loss_render_depth'] = torch.sqrt((d ** 2).mean() - 0.85 * d.mean() ** 2) * weight_depth
+    crit = torch.nn.CrossEntropyLoss(weight=class_weights.type_as(res['render_semantic']),
+                                     reduction='mean')
+    out['loss_render_semantic'] = crit(res['render_semantic'], target_semantic.long()) * weight_semantic
+    out['loss_render_color'] = torch.sum(torch.mean(torch.abs(res['render_color'] - target_color),
+                                                    dim=0)) * weight_color
+    if weight_entropy_last > 0:
+        p = res['alphainv_last'].clamp(1e-6, 1 - 1e-6)
+        out['loss_sdf_entropy'] = -(p * torch.log(p) + (1 - p) * torch.log(1 - p)).mean() * weight_entropy_last
+    return out

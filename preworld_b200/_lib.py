@@ -136,6 +136,7 @@ SIGNATURES = {
     'pw_render_rays': [ctypes.POINTER(RenderDesc), c_p, c_int, c_p, c_int, c_p,
                        c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_p, c_p, c_p,
                        c_p, c_p],
+    'pw_render_loss_sums': [c_p, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
 }
 _LONGLONG_RET = {'pw_launch_count', 'pw_lift_workspace_bytes',
                  'pw_lovasz_workspace_bytes'}

@@ -363,3 +363,77 @@ PW_API int pw_render_rays(const pw_render_desc* desc, const float* rays, int n_r
   PW_LAUNCH_CHECK(); pw_count_launch(1);
   return 0;
 }
+
+// ---------------------------------------------------------------------------
+// Reduction of the renderings to NerfHead.compute_loss's sums
+// (nerf/nerf_head.py:271-291 with silog_loss / l1_loss, nerf/utils.py:71-87, and
+// nn.CrossEntropyLoss(weight, reduction='mean')): one thread per ray, masked rays
+// (0 < depth <= 52, the kernel's `valid`) only, fp64 accumulation.
+//   sums[0] n   [1] sum d   [2] sum d^2        d = log(depth + 1e-7) - log(gt_depth)
+//   sums[3] sum w[t] * nll  [4] sum w[t]       nll = logsumexp(sem) - sem[t]
+//   sums[5..7] sum |color - gt_color| per channel
+//   sums[8] sum p log p + (1 - p) log(1 - p),  p = clamp(alphainv_last, 1e-6, 1 - 1e-6)
+namespace {
+constexpr int RL_SUMS = 9;
+
+__global__ void render_loss_kernel(const float* __restrict__ rays, int n_rays, int n_sem,
+                                   const float* __restrict__ depth, const float* __restrict__ sem,
+                                   const float* __restrict__ col, const float* __restrict__ last,
+                                   const unsigned char* __restrict__ valid,
+                                   const float* __restrict__ class_w, double* __restrict__ sums) {
+  double v[RL_SUMS];
+#pragma unroll
+  for (int k = 0; k < RL_SUMS; ++k) v[k] = 0.0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rays; r += gridDim.x * blockDim.x) {
+    if (!valid[r]) continue;
+    const float* ray = rays + (size_t)r * 16;
+    const float d = logf(depth[r] + 1e-7f) - logf(ray[2]);
+    v[0] += 1.0; v[1] += d; v[2] += (double)d * d;
+    const int t = (int)ray[3];                            // target_semantic.long()
+    const float* s = sem + (size_t)r * n_sem;
+    float mx = s[0];
+    for (int c = 1; c < n_sem; ++c) mx = fmaxf(mx, s[c]);
+    float se = 0.f;
+    for (int c = 0; c < n_sem; ++c) se += expf(s[c] - mx);
+    if (t >= 0 && t < n_sem) {
+      const float w = class_w[t];
+      v[3] += (double)(w * (logf(se) + mx - s[t]));
+      v[4] += w;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[5 + c] += fabsf(col[(size_t)r * 3 + c] - ray[13 + c]);
+    const float p = fminf(fmaxf(last[r], 1e-6f), 1.f - 1e-6f);
+    v[8] += (double)(p * logf(p) + (1.f - p) * logf(1.f - p));
+  }
+  __shared__ double red[RL_SUMS][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < RL_SUMS; ++k) {
+    double x = v[k];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) red[k][warp] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < RL_SUMS) {
+    double x = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) x += red[threadIdx.x][w];
+    atomicAdd(sums + threadIdx.x, x);
+  }
+}
+}  // namespace
+
+PW_API int pw_render_loss_sums(const float* rays, int n_rays, int n_sem, const float* depth,
+                               const float* sem, const float* col, const float* last,
+                               const unsigned char* valid, const float* class_weights,
+                               double* sums, void* stream) {
+  PW_REQUIRE(n_rays >= 0 && n_sem > 0 && sums);
+  cudaError_t e = cudaMemsetAsync(sums, 0, RL_SUMS * sizeof(double), (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  if (n_rays == 0) return 0;
+  PW_REQUIRE(rays && depth && sem && col && last && valid && class_weights);
+  const int blocks = min(pw_ceil_div(n_rays, 256), 148 * 4);
+  render_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rays, n_rays, n_sem, depth, sem,
+                                                              col, last, valid, class_weights, sums);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}

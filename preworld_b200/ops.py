@@ -825,6 +825,20 @@ def render_rays(desc, rays, t_vals, bda, density_cl, semantic_cl, color_cl):
     return o_d, o_s, o_c, o_l, o_v
 
 
+def render_loss_sums(rays, depth, sem, col, last, valid, class_weights):
+    """The nine fp64 sums NerfHead.compute_loss needs (pw_render_loss_sums)."""
+    _require_cuda(rays, depth, sem, col, last, valid, class_weights)
+    rays = rays.contiguous()
+    sums = torch.empty(9, device=rays.device, dtype=torch.float64)
+    cw = class_weights.float().contiguous()
+    assert cw.numel() == sem.shape[-1] and valid.dtype in (torch.bool, torch.uint8)
+    check(_lib.lib().pw_render_loss_sums(
+        _ptr(rays), rays.shape[0], sem.shape[-1], _ptr(depth.contiguous()),
+        _ptr(sem.contiguous()), _ptr(col.contiguous()), _ptr(last.contiguous()),
+        _ptr(valid.contiguous()), _ptr(cw), _ptr(sums), _stream()), 'pw_render_loss_sums')
+    return sums
+
+
 # ------------------------------------------------------------------ losses
 def voxel_loss_stats(rows, target, camera_mask, class_weights, empty_idx,
                      ignore_index=255):

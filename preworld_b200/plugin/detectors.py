@@ -833,23 +833,47 @@ class PreWorld4DTraj(PreWorld):
         # fusion_head[0] on cat([voxel, ego]) = W[:, :od] voxel + (W[:, od:]
         # ego + b): the ego half is a per-sample bias, so the [.., 64] concat
         # the reference materialises (164 MB/step) never exists.
+        P['ego_fusion'] = _pack_mlp(self.ego_fusion_head)
+        P['traj'] = _pack_mlp(self.traj_head)
         P['fuse_ego'] = ops.PackedConv(f0.weight[:, od:], f0.bias)
         P['fuse_mlp'] = ops.PackedMlp2(f0.weight[:, :od], None, f2.weight,
                                        f2.bias, act1='softplus')
         return P
+
+    def ego_feats(self, ego_states, device):
+        """plan_head (21 -> 256 -> 256 -> 32, preworld_temporal_traj.py:119-123,
+        454-457) -> [B, 32]."""
+        P = self.packs()
+        e = ego_states.reshape(ego_states.shape[0], -1).to(device).float()
+        e = torch.nn.functional.pad(e, (0, (-e.shape[1]) % 4)).contiguous()
+        e = ops.linear(e, P['plan'][0], 'relu')
+        e = ops.linear(e, P['plan'][1], 'relu')
+        return ops.linear(e, P['plan'][2])
+
+    def plan_trajectory(self, fused_vf_cl, ego_states):
+        """The planning branch of one forecasting step
+        (preworld_temporal_traj.py:464-472): downscale(fused voxel features) ->
+        cat with the ego feature -> ego_fusion_head (+ identity) -> traj_head ->
+        predicted displacement [B, 2].  ``fused_vf_cl`` is the step's fused volume as
+        ``forecast_step`` returns it ([B,Z,Y,X,C], library order).  The reference runs
+        this in forward_train only; here it is an inference-time call."""
+        P = self.packs()
+        identity = self.ego_feats(ego_states, fused_vf_cl.device)          # [B, 32]
+        scene = self.downscale.pooled_cl(fused_vf_cl, True)                # [B, 128]
+        x = torch.cat([identity, scene], dim=-1).contiguous()              # [B, 160]
+        for i, pc in enumerate(P['ego_fusion']):
+            x = ops.linear(x, pc, 'softplus' if i < len(P['ego_fusion']) - 1 else None)
+        fused = identity + x
+        t = ops.linear(fused, P['traj'][0], 'softplus')
+        return ops.linear(t, P['traj'][1])[:, :2]
 
     def ego_bias(self, ego_states, device):
         """plan_head (21 -> 256 -> 256 -> 32, preworld_temporal_traj.py:119-123)
         and the ego half of fusion_head[0] -> per-sample bias [B, 128].  Every
         forecasting step feeds the same ``temporal_ego_states[0]`` (:331), so
         this runs once per sample."""
-        P = self.packs()
-        e = ego_states.reshape(ego_states.shape[0], -1).to(device).float()
-        e = torch.nn.functional.pad(e, (0, (-e.shape[1]) % 4)).contiguous()
-        e = ops.linear(e, P['plan'][0], 'relu')
-        e = ops.linear(e, P['plan'][1], 'relu')
-        e = ops.linear(e, P['plan'][2])
-        return ops.linear(e, P['fuse_ego'])                  # [B, 128]
+        return ops.linear(self.ego_feats(ego_states, device),
+                          self.packs()['fuse_ego'])                        # [B, 128]
 
     def forecast_step(self, vf_cl, ego_states=None, ego_bias=None):
         """preworld_temporal_traj.py:329-341,368: plan_head -> broadcast ->

@@ -132,11 +132,11 @@ class OccHead(BaseModule):
         return {'output_voxels': [out]}
 
 
-class DownScaleModule3DCustom(nn.Module):
-    """Parameter container of heads/occupancy_head.py:180-200.  It feeds the
-    planning branch, which the reference runs only in forward_train
-    (preworld_temporal_traj.py:464-470) -- out of the forward-only scope; the
-    parameters exist so reference checkpoints load without missing keys."""
+class DownScaleModule3DCustom(BaseModule):
+    """heads/occupancy_head.py:180-200: three ``Conv3d(k=2, s=2)`` (C -> 2C -> 4C -> 4C)
+    and a global average pool -- the scene descriptor of the planning branch
+    (preworld_temporal_traj.py:464-470).  Same parameter keys as the reference
+    (``downscale{1,2,3}.{weight,bias}``)."""
 
     def __init__(self, in_dim):
         super().__init__()
@@ -145,9 +145,29 @@ class DownScaleModule3DCustom(nn.Module):
         self.downscale2 = nn.Conv3d(in_dim * 2, in_dim * 4, 2, stride=2)
         self.downscale3 = nn.Conv3d(in_dim * 4, in_dim * 4, 2, stride=2)
 
+    def _build_packs(self):
+        convs = (self.downscale1, self.downscale2, self.downscale3)
+        return dict(ref=[pack_conv(c) for c in convs],
+                    # the library's volumes are [Z,Y,X]: spatially transposed kernels
+                    rev=[pack_conv(c, spatial_perm=(2, 1, 0)) for c in convs])
+
+    def pooled_cl(self, x_cl, reversed_order=True):
+        """cl array [B,Z,Y,X,C] (library order) or [B,X,Y,Z,C] -> [B, 4C]."""
+        P = self.packs()['rev' if reversed_order else 'ref']
+        for pc in P:
+            x_cl = ops.conv(x_cl, pc)
+        return ops.global_avgpool(x_cl)
+
     def forward(self, feats):
-        raise NotImplementedError(
-            'the planning branch runs only in training (out of scope)')
+        """feats [b, X, Y, Z, C] (the reference's layout) -> [b, 1, 1, 1, 4C]."""
+        b = feats.shape[0]
+        return self.pooled_cl(feats.contiguous(), False).view(b, 1, 1, 1, -1)
+
+
+# occ3d-nuscenes class frequencies (nerf_head.py:22-24)
+NUSC_CLASS_FREQUENCIES = np.array([
+    1163161, 2309034, 188743, 2997643, 20317180, 852476, 243808, 2457947, 497017, 2731022,
+    7224789, 214411435, 5565043, 63191967, 76098082, 128860031, 141625221, 2307405309])
 
 
 @HEADS.register_module()
@@ -187,6 +207,9 @@ class NerfHead(nn.Module):
         self.weight_depth = weight_depth
         self.weight_semantic = weight_semantic
         self.weight_color = weight_color
+        # nerf_head.py:160-163
+        self.class_weights = (torch.from_numpy(1 / np.log(NUSC_CLASS_FREQUENCIES[:17] + 0.001))
+                              if balance_cls_weight else torch.ones(17) / 17)
         self._t_cache = {}
 
     def ray_parameters(self, device):
@@ -239,15 +262,45 @@ class NerfHead(nn.Module):
         return dict(render_depth=d, render_semantic=s, render_color=c,
                     alphainv_last=last, ray_mask=valid)
 
+    def compute_loss(self, results, rays, interval=None):
+        """nerf_head.py:271-291 (``interval`` given: compute_loss_temporal, :301-329,
+        the same terms under ``_{interval}s`` keys): the renderings of ONE sample
+        reduced to loss values by one kernel (nine fp64 sums) + a few scalar
+        operations.  Values only -- the fused ray march has no backward pass.  The
+        distortion term (flatten_eff_distloss over every sample's weight) needs the
+        per-sample weights the fused march never materialises and is not produced."""
+        s = ops.render_loss_sums(rays, results['render_depth'], results['render_semantic'],
+                                 results['render_color'], results['alphainv_last'],
+                                 results['ray_mask'], self.class_weights.to(rays.device))
+        n = s[0]
+        sfx = '' if interval is None else f'_{int(interval)}s'
+        out = {}
+        if self.use_depth_sup:
+            silog = torch.sqrt(s[2] / n - 0.85 * (s[1] / n) ** 2)       # utils.py:76-78
+            out['loss_render_depth' + sfx] = (silog * self.weight_depth).float()
+        out['loss_render_semantic' + sfx] = (s[3] / s[4] * self.weight_semantic).float()
+        out['loss_render_color' + sfx] = ((s[5] + s[6] + s[7]) / n * self.weight_color).float()
+        if self.weight_entropy_last > 0:
+            out['loss_sdf_entropy' + sfx] = (-(s[8] / n) * self.weight_entropy_last).float()
+        return out
+
     def forward(self, density, semantic, color, if_pretrain=False,
                 if_temporal=False, dataset_type='Nuscenes', rays=None,
-                bda=None, interval=0, library_order=False, **kwargs):
-        """Forward part of nerf_head.py:361-420: renders every batch element.
-        The reference goes on to reduce the renderings to training losses
-        (compute_loss, :271-299), which are outside the forward-only scope;
-        this returns the per-ray renderings (list of dicts, one per sample)."""
+                bda=None, interval=0, library_order=False, return_loss=False,
+                **kwargs):
+        """nerf_head.py:361-420: renders every batch element; returns the per-ray
+        renderings (list of dicts, one per sample) or, with ``return_loss=True``, the
+        reference's dict of losses averaged over the batch (:410-418)."""
         if dataset_type != 'Nuscenes':
             raise NotImplementedError('only the nuScenes ray layout is on the path')
-        return [self.render(density[b], semantic[b], color[b], rays[b],
-                            bda[b], library_order)
-                for b in range(rays.shape[0])]
+        renders = [self.render(density[b], semantic[b], color[b], rays[b],
+                               bda[b], library_order)
+                   for b in range(rays.shape[0])]
+        if not return_loss:
+            return renders
+        losses = {}
+        for b, res in enumerate(renders):
+            one = self.compute_loss(res, rays[b], interval if if_temporal else None)
+            for k, v in one.items():
+                losses[k] = losses[k] + v if k in losses else v
+        return {k: v / len(renders) for k, v in losses.items()}

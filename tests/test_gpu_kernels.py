@@ -993,3 +993,36 @@ def test_lift_bin_overflow_falls_back_bit_exact():
                              xs.to(DEV), ys.to(DEV), ds.to(DEV), gg.lower.tolist(),
                              gg.interval.tolist(), B, N, grid)
         assert np.array_equal(got.cpu().numpy().reshape(-1, 32), want)
+
+
+def test_render_loss_matches_oracle():
+    """NerfHead.compute_loss (nerf_head.py:271-291) on the device -- one reduction kernel
+    (nine fp64 sums) -- against the CPU restatement on the masked rays; 1e-5 relative
+    (fp32 log / exp per ray, fp64 accumulation)."""
+    from preworld_b200.plugin.heads import NerfHead
+    head = NerfHead([-40., -40., -1., 40., 40., 5.4], 0.4).to(DEV)
+    g = torch.Generator().manual_seed(3)
+    n = 4097
+    rays = torch.zeros(n, 16)
+    rays[:, 2] = torch.rand(n, generator=g) * 60                       # some > 52: masked out
+    rays[:, 3] = torch.randint(0, 17, (n,), generator=g).float()
+    rays[:, 13:16] = torch.randn(n, 3, generator=g)
+    valid = (rays[:, 2] > 0) & (rays[:, 2] <= 52)
+    res = dict(render_depth=torch.rand(n, generator=g) * 50 + 0.5,
+               render_semantic=torch.randn(n, 17, generator=g) * 2,
+               render_color=torch.randn(n, 3, generator=g),
+               alphainv_last=torch.rand(n, generator=g), ray_mask=valid)
+    want = torch_ref.nerf_compute_loss({k: v[valid] for k, v in res.items() if k != 'ray_mask'},
+                                       rays[valid, 2], rays[valid, 3], rays[valid, 13:16],
+                                       head.class_weights)
+    got = head.compute_loss({k: v.to(DEV) for k, v in res.items()}, rays.to(DEV))
+    assert sorted(got) == sorted(want)
+    for k in want:
+        assert abs(float(got[k]) - float(want[k])) <= 1e-5 * abs(float(want[k])), (k, got[k], want[k])
+    # temporal keys (compute_loss_temporal, :301-329)
+    got_t = head.compute_loss({k: v.to(DEV) for k, v in res.items()}, rays.to(DEV), interval=2)
+    assert sorted(got_t) == sorted(k + '_2s' for k in want)
+    # no valid ray: nothing to average (nan, as the reference's empty mean)
+    none = head.compute_loss({k: v.to(DEV) for k, v in res.items() if k != 'ray_mask'} |
+                             {'ray_mask': torch.zeros(n, dtype=torch.bool, device=DEV)}, rays.to(DEV))
+    assert all(torch.isnan(v) for v in none.values())

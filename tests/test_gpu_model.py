@@ -167,6 +167,36 @@ def test_forecast_step_matches_oracle():
     assert (got - want).abs().max().item() / want.abs().max().item() < 1e-5
 
 
+def test_plan_trajectory_matches_oracle():
+    """a18, the planning branch (preworld_temporal_traj.py:454-472 +
+    DownScaleModule3DCustom, occupancy_head.py:180-200): three stride-2 2x2x2 convs on
+    the library's [Z,Y,X] volume (spatially transposed kernels), global pool, ego fusion
+    MLP, trajectory head -- against the CPU restatement, 1e-5 of max|ref|."""
+    case = CASES['tiny_traj']
+    model = _model(case)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    g = torch.Generator().manual_seed(5)
+    vf = torch.randn(2, 40, 40, 16, 32, generator=g)         # [B,X,Y,Z,C]
+    ego = torch.randn(2, 1, 21, generator=g)
+    fused = torch_ref.forecast_step(sd, vf, ego)
+    want = torch_ref.plan_trajectory(sd, fused, ego)
+    assert want.shape == (2, 2)
+    with torch.no_grad():
+        fused_cl = model.forecast_step(vf.permute(0, 3, 2, 1, 4).contiguous().cuda(), ego.cuda())
+        got = model.plan_trajectory(fused_cl, ego.cuda()).cpu()
+        # the module's own forward takes the reference's [b,X,Y,Z,C] layout
+        pooled = model.downscale(fused.cuda()).cpu()
+    assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+    x = fused.permute(0, 4, 1, 2, 3)
+    for i in (1, 2, 3):
+        x = torch.nn.functional.conv3d(x, sd[f'downscale.downscale{i}.weight'],
+                                       sd[f'downscale.downscale{i}.bias'], stride=2)
+    ref_pool = x.mean(dim=(2, 3, 4))
+    assert pooled.shape == (2, 1, 1, 1, 128)
+    assert (pooled.view(2, -1) - ref_pool).abs().max().item() <= 1e-5 * ref_pool.abs().max().item()
+
+
 def test_attribute_projection_matches_oracle():
     case = CASES['tiny_pretrain']
     model = _model(case)
