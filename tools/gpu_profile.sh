@@ -7,4 +7,4 @@ echo "ncu step exit $?" >> gpurun_out/ncu_step.log
 timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on \
     -f -o gpurun_out/prof_hot python tools/profile_step.py --part hot > gpurun_out/ncu_hot.log 2>&1
 echo "ncu hot exit $?" >> gpurun_out/ncu_hot.log
-tail -3 gpurun_out/ncu_step.log gpurun_out/ncu_hot.log; ls -la gpurun_out
+tail -n 3 gpurun_out/ncu_step.log; tail -n 3 gpurun_out/ncu_hot.log; ls -la gpurun_out

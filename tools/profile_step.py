@@ -24,14 +24,9 @@ def main():
     ap.add_argument('--part', default='step', choices=['step', 'hot'])
     args = ap.parse_args()
     dev = torch.device('cuda', 0)
-    cfg, model, samples = bench.build_workload(2)
-    model = model.to(dev)
-    dev_samples = [tuple(t.to(dev) for t in s) for s in samples]
-
-    def step(i):
-        with torch.no_grad():
-            vf = model.voxel_features_cl(dev_samples[i % 2])
-            return model._occ_from_head(vf)[0]
+    wl = bench.Workload('finetune', dev, n_variants=2).to_device()
+    model, dev_samples = wl.model, wl.dev_samples
+    step = wl.step_resident
 
     for i in range(3):
         step(i)
