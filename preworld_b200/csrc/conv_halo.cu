@@ -205,7 +205,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
   // register statically depends on the load's scoreboard slot, which ptxas re-uses for the
   // epilogue's residual loads -- the TMEM loads then waited for the residual prefetch
   // (17 % of all stall samples on the 64->256 pointwise layer).
-  const uint32_t tmem_base = *tmem_holder + (uint32_t)p.zero;
+  uint32_t tmem_base;
+  {
+    const uint32_t loaded = *tmem_holder + (uint32_t)p.zero;
+    asm volatile("mov.u32 %0, %1;" : "=r"(tmem_base) : "r"(loaded));   // not re-materialised later
+  }
   if (threadIdx.x == 0) PW_TS(1);
   const int tile_cols = p.nacc * 2 * p.n_tile;          // TMEM columns of one M tile's accumulators
   const uint32_t a_ring_col = (uint32_t)(p.mt * tile_cols);
@@ -362,9 +366,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     const uint32_t tap_tab_u32 = smem_u32(tap_tab);
     auto advance_taps = [&](int n) {                     // n <= nb (enforced by the planner)
       r += n;
-      if (r >= p.nb) { r -= p.nb; eph ^= 1u; }
+      const int wrap = r >= p.nb ? 1 : 0;                // (selects: a branch here cost ~6 % of the
+      r -= wrap ? p.nb : 0;                              //  split warps' samples in branch resolution)
+      eph ^= (uint32_t)wrap;
       t += n;
-      while (t >= T) {                                   // next chunk (T may be 1: twice)
+      while (__builtin_expect(t >= T, 0)) {              // next chunk (T may be 1: twice)
         t -= T;
         ++c;
         if (++hs == p.nh) { hs = 0; hph ^= 1u; }
