@@ -186,6 +186,30 @@ int pw_global_avgpool(const float* x, int x_ld, float* y, int n,
  * a 1x1 map == broadcast.  y[n,p,c0:c0+c] = v[n,c]. */
 int pw_broadcast_channels(const float* v, float* y, int y_ld, int n,
                           long long pixels, int c, void* stream);
+/* Chains of small dense layers on a few row vectors, ONE launch: DepthNet's
+ * camera-parameter branch (necks/view_transformer.py:421-470,606-617: Mlp(27->mid->mid)
+ * + SELayer reduce / expand -> sigmoid gate, for the context and the depth branch).
+ * Every chain reads the same input rows x [rows, x_ld]; layer l computes
+ * act(scale * (in . w[:, c]) + bias) with w [cin, w_ld] (PackedConv's SIMT layout; a
+ * layer's cin may exceed the previous cout by its padding to 4 -- those inputs are 0).
+ * Widths <= 1024. */
+#define PW_MAX_CHAINS 4
+#define PW_MAX_CHAIN_LAYERS 4
+typedef struct {
+  const float* w;
+  const float* scale;          /* may be NULL (1) */
+  const float* bias;           /* may be NULL (0) */
+  int cin, cout, w_ld, act;    /* act: PW_ACT_* */
+} pw_dense_layer;
+typedef struct {
+  pw_dense_layer layer[PW_MAX_CHAIN_LAYERS];
+  int n_layers;
+  float* out;                  /* [rows, out_ld] */
+  int out_ld;
+} pw_dense_chain;
+int pw_dense_chains(const pw_dense_chain* chains, int n_chains, const float* x,
+                    int x_ld, int rows, void* stream);
+
 /* view_transformer.py:801: depth = softmax over the D logits of every pixel.
  * logits [rows, in_ld] (first d channels) -> prob_cl [rows, d] (channels-last,
  * may be NULL) and prob_planar [n, d, pixels] (the reference's [B*N,D,H,W]

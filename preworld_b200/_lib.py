@@ -38,6 +38,18 @@ class RenderDesc(ctypes.Structure):
                 ('vs_x', c_ll), ('vs_y', c_ll), ('vs_z', c_ll)]
 
 
+class DenseLayer(ctypes.Structure):
+    """struct pw_dense_layer"""
+    _fields_ = [('w', c_p), ('scale', c_p), ('bias', c_p), ('cin', c_int),
+                ('cout', c_int), ('w_ld', c_int), ('act', c_int)]
+
+
+class DenseChain(ctypes.Structure):
+    """struct pw_dense_chain"""
+    _fields_ = [('layer', DenseLayer * 4), ('n_layers', c_int), ('out', c_p),
+                ('out_ld', c_int)]
+
+
 # name -> argtypes (restype is int unless noted); mirrors preworld_b200.h
 SIGNATURES = {
     'pw_abi_version': [],
@@ -136,6 +148,7 @@ SIGNATURES = {
     'pw_render_rays': [ctypes.POINTER(RenderDesc), c_p, c_int, c_p, c_int, c_p,
                        c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_p, c_p, c_p,
                        c_p, c_p],
+    'pw_dense_chains': [ctypes.POINTER(DenseChain), c_int, c_p, c_int, c_int, c_p],
     'pw_render_loss_sums': [c_p, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
 }
 _LONGLONG_RET = {'pw_launch_count', 'pw_lift_workspace_bytes',

@@ -269,15 +269,16 @@ __global__ void upsample_trilinear2_kernel(const float* __restrict__ x1, int x1_
                                            int w1, const float* __restrict__ x2, int x2_ld, int z2,
                                            int y2, int w2, float* __restrict__ y, int y_ld, int b,
                                            int c4, int oz, int oy, int ox) {
-  long long total = (long long)b * oz * oy * ox * c4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int ch = (int)(i % c4);
-    long long t = i / c4;
-    int x_o = (int)(t % ox); t /= ox;
-    int y_o = (int)(t % oy); t /= oy;
-    int z_o = (int)(t % oz);
-    int bb = (int)(t / oz);
+  // total < 2^31 (checked by the caller): 32-bit index arithmetic (four 64-bit divisions
+  // per thread were a large part of this kernel's instructions)
+  const unsigned total = (unsigned)b * oz * oy * ox * c4;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int ch = (int)(i % (unsigned)c4);
+    unsigned t = i / (unsigned)c4;
+    int x_o = (int)(t % (unsigned)ox); t /= (unsigned)ox;
+    int y_o = (int)(t % (unsigned)oy); t /= (unsigned)oy;
+    int z_o = (int)(t % (unsigned)oz);
+    int bb = (int)(t / (unsigned)oz);
     const float4 a = trilerp4(x1, x1_ld, bb, z1, y1, w1, oz, oy, ox, z_o, y_o, x_o, ch);
     const float4 c = trilerp4(x2, x2_ld, bb, z2, y2, w2, oz, oy, ox, z_o, y_o, x_o, ch);
     __stcs(reinterpret_cast<float4*>(
@@ -471,8 +472,101 @@ PW_API int pw_upsample_trilinear2(const float* x1, int x1_ld, int z1, int y1, in
                                   int y_ld, int b, int c, int oz, int oy, int ox, void* stream) {
   PW_REQUIRE(x1 && x2 && y && (c & 3) == 0 && (x1_ld & 3) == 0 && (x2_ld & 3) == 0 &&
              (y_ld & 3) == 0);
+  PW_REQUIRE((long long)b * oz * oy * ox * (c / 4) < (1ll << 31));
   upsample_trilinear2_kernel<<<grid_for((long long)b * oz * oy * ox * (c / 4)), TPB, 0, ST>>>(
       x1, x1_ld, z1, y1, w1, x2, x2_ld, z2, y2, w2, y, y_ld, b, c / 4, oz, oy, ox);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+// ---- chains of small dense layers on a handful of row vectors ------------------
+// DepthNet's camera-parameter branch (view_transformer.py:421-470,606-617): per image,
+// Mlp(27 -> mid -> mid) and SELayer's reduce / expand on a [mid] vector, for the
+// context and the depth gate -- eight 12-row GEMMs as separate launches were 0.13 ms
+// of launch latency.  One CTA per (row, chain): the activations stay in shared
+// memory, thread c owns output channel c (weights [cin, w_ld]: coalesced over c).
+namespace {
+struct ChainPack {
+  pw_dense_chain c[PW_MAX_CHAINS];
+};
+constexpr int CHAIN_MAX_WIDTH = 1024;
+constexpr int CHAIN_WARPS = 8;
+
+__global__ void __launch_bounds__(CHAIN_WARPS * 32)
+dense_chains_kernel(const ChainPack pack, const float* __restrict__ x, int x_ld, int rows) {
+  // K is split over the 8 warps (a thread that walks all of K alone waits one L2 round
+  // trip per weight: the chain was latency bound), lane = channel within a group of 32:
+  // every weight load is one coalesced 128-byte row segment, the groups of a warp are
+  // independent accumulation chains; the 8 partial sums are added in warp order.
+  __shared__ float buf[2][CHAIN_MAX_WIDTH];
+  __shared__ float part[CHAIN_WARPS][CHAIN_MAX_WIDTH];
+  const pw_dense_chain& ch = pack.c[blockIdx.y];
+  const int row = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cin0 = ch.layer[0].cin;
+  for (int k = threadIdx.x; k < cin0; k += blockDim.x) buf[0][k] = x[(size_t)row * x_ld + k];
+  __syncthreads();
+  int cur = 0;
+  for (int l = 0; l < ch.n_layers; ++l) {
+    const pw_dense_layer& L = ch.layer[l];
+    const bool last = l == ch.n_layers - 1;
+    const int kper = (L.cin + CHAIN_WARPS - 1) / CHAIN_WARPS;
+    const int k0 = warp * kper, k1 = min(L.cin, k0 + kper);
+    for (int g0 = 0; g0 < L.cout; g0 += 32 * 8) {          // 8 groups of 32 channels at a time
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int k = k0; k < k1; ++k) {
+        const float xv = buf[cur][k];
+        const float* w = L.w + (size_t)k * L.w_ld + g0 + lane;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (g0 + j * 32 + lane < L.cout) acc[j] = fmaf(xv, __ldg(w + j * 32), acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (g0 + j * 32 + lane < L.cout) part[warp][g0 + j * 32 + lane] = acc[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < L.cout; c += blockDim.x) {
+      float acc = part[0][c];
+#pragma unroll
+      for (int w = 1; w < CHAIN_WARPS; ++w) acc += part[w][c];
+      const float sc = L.scale ? __ldg(L.scale + c) : 1.f;
+      const float bi = L.bias ? __ldg(L.bias + c) : 0.f;
+      const float v = pw_activate(fmaf(acc, sc, bi), L.act);
+      if (last) ch.out[(size_t)row * ch.out_ld + c] = v;
+      else buf[cur ^ 1][c] = v;
+    }
+    // a layer's cin may exceed the previous cout by its padding to 4: zero those inputs
+    if (!last)
+      for (int c = L.cout + threadIdx.x; c < ch.layer[l + 1].cin; c += blockDim.x) buf[cur ^ 1][c] = 0.f;
+    __syncthreads();
+    cur ^= 1;
+  }
+}
+}  // namespace
+
+PW_API int pw_dense_chains(const pw_dense_chain* chains, int n_chains, const float* x, int x_ld,
+                           int rows, void* stream) {
+  PW_REQUIRE(chains && x && n_chains >= 1 && n_chains <= PW_MAX_CHAINS && rows >= 0);
+  if (rows == 0) return 0;
+  ChainPack pack;
+  for (int i = 0; i < n_chains; ++i) {
+    const pw_dense_chain& c = chains[i];
+    PW_REQUIRE(c.n_layers >= 1 && c.n_layers <= PW_MAX_CHAIN_LAYERS && c.out);
+    PW_REQUIRE(c.layer[0].cin == chains[0].layer[0].cin && c.layer[0].cin <= x_ld);
+    for (int l = 0; l < c.n_layers; ++l) {
+      PW_REQUIRE(c.layer[l].w && c.layer[l].cin > 0 && c.layer[l].cout > 0 &&
+                 c.layer[l].cin <= CHAIN_MAX_WIDTH && c.layer[l].cout <= CHAIN_MAX_WIDTH &&
+                 c.layer[l].w_ld >= c.layer[l].cout);
+      PW_REQUIRE(l == 0 || (c.layer[l].cin >= c.layer[l - 1].cout &&
+                            c.layer[l].cin <= c.layer[l - 1].cout + 3));
+    }
+    PW_REQUIRE(c.out_ld >= c.layer[c.n_layers - 1].cout);
+    pack.c[i] = c;
+  }
+  dense_chains_kernel<<<dim3((unsigned)rows, (unsigned)n_chains), CHAIN_WARPS * 32, 0, ST>>>(pack, x, x_ld, rows);
   PW_LAUNCH_CHECK(); pw_count_launch(1);
   return 0;
 }

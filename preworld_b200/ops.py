@@ -465,6 +465,32 @@ def scale_channels(x, gate, out=None):
     return out
 
 
+def dense_chains(x2d, chains):
+    """x2d [rows, C]; ``chains``: list of lists of (PackedConv, act) -- every chain a
+    stack of dense layers applied to the same rows.  ONE launch (pw_dense_chains);
+    returns a list with one [rows, cout_last] tensor per chain."""
+    _require_cuda(x2d)
+    assert x2d.dim() == 2 and x2d.stride(1) == 1 and 1 <= len(chains) <= 4
+    rows = x2d.shape[0]
+    arr = (_lib.DenseChain * len(chains))()
+    outs = []
+    for ci, layers in enumerate(chains):
+        assert 1 <= len(layers) <= 4
+        for li, (pc, act) in enumerate(layers):
+            assert pc.k == (1, 1, 1)
+            L = arr[ci].layer[li]
+            L.w = pc.w.data_ptr()
+            L.scale = pc.scale.data_ptr() if pc.scale is not None else None
+            L.bias = pc.bias.data_ptr() if pc.bias is not None else None
+            L.cin, L.cout, L.w_ld, L.act = pc.cin, pc.cout, pc.w_ld, ACT[act]
+        out = torch.empty((rows, layers[-1][0].cout), device=x2d.device, dtype=torch.float32)
+        arr[ci].n_layers, arr[ci].out, arr[ci].out_ld = len(layers), out.data_ptr(), out.stride(0)
+        outs.append(out)
+    check(_lib.lib().pw_dense_chains(arr, len(chains), _ptr(x2d), x2d.stride(0), rows,
+                                     _stream()), 'pw_dense_chains')
+    return outs
+
+
 def global_avgpool(x):
     n, c = x.shape[0], x.shape[-1]
     pixels = x[0, ..., 0].numel()

@@ -354,6 +354,9 @@ class BEVStereo4DOCC(BaseModule):
         n_full = depth.shape[0] // bn
         bev_feat_list = []
         depth_key_frame = None
+        # torch.cat(bev_feat_list, dim=1) of the reference (:240,266) is never a copy: the
+        # last conv of each frame's pre_process_net writes its channel slice of `cat`
+        cat = None
         for fid in reversed(range(n_full)):              # [adjacent.., key]
             d_f = depth[fid * bn:(fid + 1) * bn]
             bev = vt.lift_stage(d_f, tran[fid * bn:(fid + 1) * bn],
@@ -364,10 +367,18 @@ class BEVStereo4DOCC(BaseModule):
             for hook in list(vt._forward_hooks.values()):
                 hook(vt, None, (bev, d_f))
             if self.pre_process:
-                bev = self.pre_process_net(bev)[0]
+                C = vt.out_channels
+                if cat is None:
+                    b_, _, gz, gy, gx = bev.shape
+                    cat = torch.empty((b_, gz, gy, gx, C * n_full), device=dev,
+                                      dtype=torch.float32)
+                k = len(bev_feat_list)
+                bev = self.pre_process_net(bev, out=cat[..., k * C:(k + 1) * C])[0]
             bev_feat_list.append(bev)
             if fid == 0:
                 depth_key_frame = d_f
+        if cat is not None and all(f.shape[1] == vt.out_channels for f in bev_feat_list):
+            return [self.bev_encoder(ops.to_logical(cat))], depth_key_frame
         return self._fuse_frames(bev_feat_list, dev), depth_key_frame
 
     def set_camera_shard(self, shard):

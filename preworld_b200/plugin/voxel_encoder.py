@@ -66,13 +66,15 @@ class BasicBlock3D(nn.Module):
         return dict(c1=f, c2=c2, fused=True, split=c1.cout)
 
     @staticmethod
-    def run(p, x):
+    def run(p, x, out=None):
+        """``out``: optional destination of the block's result (may be a channel slice of
+        a wider cl array -- the caller's concatenation buffer)."""
         if p['fused']:
             y = ops.conv(x, p['c1'], 'relu', act_channels=p['split'])
             s = p['split']
-            return ops.conv(y[..., :s], p['c2'], 'relu', residual=y[..., s:])
+            return ops.conv(y[..., :s], p['c2'], 'relu', residual=y[..., s:], out=out)
         y = ops.conv(x, p['c1'], 'relu')
-        return ops.conv(y, p['c2'], 'relu', residual=x)
+        return ops.conv(y, p['c2'], 'relu', residual=x, out=out)
 
 
 @BACKBONES.register_module()
@@ -106,13 +108,17 @@ class CustomResNet3D(BaseModule):
     def _build_packs(self):
         return [[blk.pack() for blk in layer] for layer in self.layers]
 
-    def forward(self, x):
-        """[B,C,Z,Y,X] (channels_last_3d) -> list of the same."""
+    def forward(self, x, out=None):
+        """[B,C,Z,Y,X] (channels_last_3d) -> list of the same.  ``out`` (a cl array, e.g.
+        a channel slice of the frame-concatenation buffer) receives the LAST block's
+        result in place of a fresh tensor."""
         x = ops.from_logical(x)
         feats = []
-        for lid, layer in enumerate(self.packs()):
-            for bp in layer:
-                x = BasicBlock3D.run(bp, x)
+        packs = self.packs()
+        for lid, layer in enumerate(packs):
+            for bi, bp in enumerate(layer):
+                last = out is not None and lid == len(packs) - 1 and bi == len(layer) - 1
+                x = BasicBlock3D.run(bp, x, out if last else None)
             if lid in self.backbone_output_ids:
                 feats.append(ops.to_logical(x))
         return feats

@@ -1026,3 +1026,33 @@ def test_render_loss_matches_oracle():
     none = head.compute_loss({k: v.to(DEV) for k, v in res.items() if k != 'ray_mask'} |
                              {'ray_mask': torch.zeros(n, dtype=torch.bool, device=DEV)}, rays.to(DEV))
     assert all(torch.isnan(v) for v in none.values())
+
+
+def test_dense_chains_match_torch():
+    """pw_dense_chains (DepthNet's Mlp + SE gate vectors, view_transformer.py:421-470,
+    606-617): two 4-layer chains on 12 rows in one launch vs torch fp32, incl. the
+    27 -> 28 input padding and a folded input affine (BatchNorm1d in front of fc1)."""
+    g = torch.Generator().manual_seed(11)
+    rows, cin, mid = 12, 27, 256
+    x = torch.randn(rows, cin, generator=g)
+    s_in, t_in = torch.rand(cin, generator=g) + 0.5, torch.randn(cin, generator=g) * 0.1
+    acts = ['relu', None, 'relu', 'sigmoid']
+    chains, refs = [], []
+    for c in range(2):
+        ws = [torch.randn(mid, cin if i == 0 else mid, generator=g) / (cin if i == 0 else mid) ** .5
+              for i in range(4)]
+        bs = [torch.randn(mid, generator=g) * 0.1 for _ in range(4)]
+        layers = []
+        y = x * s_in + t_in
+        for i in range(4):
+            kw = dict(in_scale=s_in.to(DEV), in_shift=t_in.to(DEV)) if i == 0 else {}
+            layers.append((ops.PackedConv(ws[i].to(DEV), bs[i].to(DEV), None, **kw), acts[i]))
+            y = y @ ws[i].t() + bs[i]
+            y = torch.relu(y) if acts[i] == 'relu' else (torch.sigmoid(y) if acts[i] == 'sigmoid' else y)
+        chains.append(layers)
+        refs.append(y)
+    xp = F.pad(x, (0, 1)).to(DEV).contiguous()
+    outs = ops.dense_chains(xp, chains)
+    for got, want in zip(outs, refs):
+        assert got.shape == want.shape
+        assert (got.cpu() - want).abs().max().item() < 2e-6
