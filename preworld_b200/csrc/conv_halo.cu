@@ -472,6 +472,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
       if (PW_DBG(1024)) tmem_st32(a_col, hl);            // (timing experiment: half the bytes)
       else if (!PW_DBG(2048) && !PW_DBG(16)) tmem_st64(a_col, hl);    // (2048: no store at all)
       pending = slot;
+      if (!PW_DBG(4096)) {
+        // Published at once: the main loop is bound by the ring round trip (MMA retire ->
+        // commit -> store -> publish -> MMA) with 3 entries in flight, not by the split
+        // warps' issue rate -- deferring the publication by one row to hide the store's
+        // completion latency (round 1; bit 4096 restores it) lengthened that loop: +2 %.
+        if (!PW_DBG(16)) tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + 8 * pending);
+        pending = -1;
+      }
       if (!same_chunk) {                                 // chunk boundary (rare)
         const int upto = c < p.chunks ? c : p.chunks;
 #pragma unroll 1
