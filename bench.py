@@ -40,10 +40,12 @@ UNIT = 'frames/s'
 WORKLOAD = ('preworld-7frame-finetune, derived ResNet-50 @ 6x3x256x704 -> '
             '200x200x16, bs=1/GPU, forward-only')
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full
-# (profiles/r01n_hot_kernels.md), for the layer shapes that can lead the step
+# (profiles/r02f_hot_kernels.md: the capture of the same build, taken by
+# tools/gpu_profile.sh), for the layer shapes that can lead the step; algorithmic
+# bytes of the two shapes: 246 MB (32->32 + residual) and 246 MB (32->64)
 NCU_TRAFFIC = {
-    'conv_halo 1x16x200x200x32->32 k333 s1 d1': 243.0e6,
-    'conv_halo 1x16x200x200x32->64 k333 s1 d1': 198.2e6,
+    'conv_halo 1x16x200x200x32->32 k333 s1 d1': 241.3e6,
+    'conv_halo 1x16x200x200x32->64 k333 s1 d1': 196.7e6,
 }
 FALLBACK_PEAKS = dict(hbm_gbs=6650.0, bf16_tflops=1590.0,
                       bf16_tflops_sustained=1400.0)
@@ -616,8 +618,10 @@ def main():
                     'frac': lay['tflops'] / peaks['bf16_tflops_sustained'],
                     'frac_of_3xtf32_ceiling': lay['tflops'] * 6 / peaks['bf16_tflops_sustained'],
                     'traffic': NCU_TRAFFIC.get(lname),
-                    'traffic_source': 'ncu --set full capture of this layer shape committed '
-                                      'under profiles/ (not measured by this run)',
+                    'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of this layer '
+                                      'shape from the ncu --set full capture of the same build, '
+                                      'profiles/r02f_hot_kernels.md (a profiler pass cannot run '
+                                      'inside the timed bench)',
                     'peak_source': peak_src,
                     'launch_us': 1e3 * lay['ms_per_step'] / lay['launches_per_step'],
                     'share_of_step': k['ms_per_step'] / step_ms,
