@@ -164,7 +164,6 @@ class Sim:
         items = mt                             # epilogue items of one tile (one column group)
         for tile in range(self.tiles):
             released = 0
-            pending = None
             if self.fixed:
                 while released < min(st['c'], chunks):
                     yield from release(released)
@@ -178,31 +177,34 @@ class Sim:
                 g = (gc0 + st['c']) * T + st['t']
                 slot = st['r'] * mt + m_cur
                 ring_r, ring_ph = st['r'], st['eph']
+                m_now = m_cur
                 yield ('step',)                   # hi/lo split
-                if pending is not None:
-                    self.a_full[pending].arrive()
-                yield ('wait', self.ring_empty[ring_r], ring_ph)
-                self.a_slot[slot][quad] = (g, m_cur)
-                pending = slot
+                # advance; inside the same chunk the next row is fetched BEFORE the
+                # barrier traffic (round 2)
                 c_prev = st['c']
                 mm = m_cur + self.sets
                 taps = mm // mt
                 m_cur = mm - taps * mt
                 for _ in range(taps):
                     step_tap()
-                if st['c'] != c_prev:
+                same_chunk = st['c'] == c_prev
+                if same_chunk:
+                    begin_read()
+                    yield ('step',)
+                    end_read()
+                yield ('wait', self.ring_empty[ring_r], ring_ph)
+                self.a_slot[slot][quad] = (g, m_now)
+                self.a_full[slot].arrive()        # published at once (round 2)
+                if not same_chunk:
                     upto = min(st['c'], chunks)
                     while released < upto:
                         yield from release(released)
                         released += 1
                     if st['c'] < chunks:
                         yield ('wait', self.halo_full[st['hs']], st['hph'])
-                if st['c'] < chunks:
-                    begin_read()
-                    yield ('step',)
-                    end_read()
-            if pending is not None:
-                self.a_full[pending].arrive()
+                        begin_read()
+                        yield ('step',)
+                        end_read()
             while released < chunks:
                 yield from release(released)
                 released += 1
