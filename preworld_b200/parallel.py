@@ -104,6 +104,8 @@ def collect_occupancy(grids, size, group=None):
     part = torch.stack([torch.as_tensor(g) for g in grids])
     if world == 1:
         return list(part[:size])
+    if dist.get_backend(group) == 'nccl' and not part.is_cuda:
+        part = part.cuda()                   # NCCL moves device memory only
     recv = part.new_empty((world,) + tuple(part.shape))
     dist.all_gather_into_tensor(recv.view(-1), part.contiguous().view(-1), group=group)
     if rank != 0:
