@@ -812,19 +812,20 @@ __global__ void bev_pool_v2_kernel(int c, int n_intervals, const float* __restri
                                    const int* __restrict__ interval_starts,
                                    const int* __restrict__ interval_lengths,
                                    float* __restrict__ out) {
-  long long total = (long long)n_intervals * c;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    int index = (int)(idx / c);
-    int cur_c = (int)(idx - (long long)index * c);
-    int s = __ldg(interval_starts + index);
-    int len = __ldg(interval_lengths + index);
-    float psum = 0.f;
-    for (int i = 0; i < len; ++i)
-      psum = fmaf(__ldg(feat + (long long)__ldg(ranks_feat + s + i) * c + cur_c),
-                  __ldg(depth + __ldg(ranks_depth + s + i)), psum);
-    out[(long long)__ldg(ranks_bev + s) * c + cur_c] = psum;
-  }
+  // one thread per (interval, channel) as the reference (mean interval length 1.5: a
+  // warp per interval with shuffled rank triples measured slower, 57 vs 45 us), 32-bit
+  // index arithmetic (n_intervals * c < 2^31 is checked by the caller)
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned index = idx / (unsigned)c;
+  if (index >= (unsigned)n_intervals) return;
+  const int cur_c = (int)(idx - index * (unsigned)c);
+  const int s = __ldg(interval_starts + index);
+  const int len = __ldg(interval_lengths + index);
+  float psum = 0.f;
+  for (int i = 0; i < len; ++i)
+    psum = fmaf(__ldg(feat + (long long)__ldg(ranks_feat + s + i) * c + cur_c),
+                __ldg(depth + __ldg(ranks_depth + s + i)), psum);
+  out[(long long)__ldg(ranks_bev + s) * c + cur_c] = psum;
 }
 
 struct LiftWs {
@@ -1037,7 +1038,8 @@ PW_API int pw_bev_pool_v2(int c, int n_intervals, const float* depth, const floa
   PW_REQUIRE(depth && feat && ranks_depth && ranks_feat && ranks_bev && interval_starts &&
              interval_lengths && out);
   long long total = (long long)n_intervals * c;
-  int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
+  PW_REQUIRE(total < (1ll << 31));
+  int blocks = (int)((total + 255) / 256);
   bev_pool_v2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
       c, n_intervals, depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,
       interval_lengths, out);

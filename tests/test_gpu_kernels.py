@@ -404,6 +404,15 @@ def test_lift_matches_oracle_bit_exact(batch):
     ops.bev_pool_v2_(depth.to(DEV), feat[..., 4:36].contiguous().to(DEV),
                      t(rd), t(rf), t(rb), t(st), t(ln), out)
     assert np.array_equal(out.cpu().numpy(), want)
+    # ... and so is the REFERENCE's own CUDA kernel (bev_pool_cuda.cu:21-48 compiled
+    # unmodified for sm_100a by oracle/build_ref.sh): a second, GPU-side oracle
+    from oracle import gpu_ref
+    if gpu_ref.available():
+        out_r = torch.zeros(nvox, 32, device=DEV)
+        gpu_ref.bev_pool_v2_forward(depth.to(DEV), feat[..., 4:36].contiguous().to(DEV), out_r,
+                                    t(rd), t(rf), t(rb), t(ln), t(st))
+        torch.cuda.synchronize()
+        assert np.array_equal(out_r.cpu().numpy(), want)
     # linearity in the features (size-independent property)
     got2 = ops.lift_fused(depth.to(DEV), (feat * 2).to(DEV)[..., 4:36], cam,
                           bda.reshape(B, 9).to(DEV), xs.to(DEV), ys.to(DEV),
