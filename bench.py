@@ -394,7 +394,7 @@ def run_reference(args, rank, world):
                           'config 5 is not timed on the CPU (4 x R101 400x400x16 forwards '
                           'take minutes each); see --config finetune'}), flush=True)
         return
-    budget = float(os.environ.get('PW_REF_BUDGET_S', '420'))
+    budget = float(os.environ.get('PW_REF_BUDGET_S', '240'))
     t_begin = time.perf_counter()
     for i in range(args.warmup):
         wl.cpu_seconds(i % 2)
