@@ -17,9 +17,8 @@ import bench
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     dev = torch.device('cuda', 0)
-    cfg, model, samples = bench.build_workload(4)
-    model = model.to(dev)
-    pins = [tuple(t.pin_memory() for t in s) for s in samples]
+    wl = bench.Workload('finetune', dev, n_variants=4).to_device()
+    model, pins = wl.model, wl.pin_samples
     model.enable_cuda_graph()
 
     def step(i):

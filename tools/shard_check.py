@@ -35,7 +35,8 @@ def main():
         S.lively_init_(model, case['seed'])
         samples = [S.make_img_inputs(1, case['input_size'], seed=s) for s in range(2)]
     else:
-        cfg, model, samples = bench.build_workload(2)
+        wl = bench.Workload('finetune', None, n_variants=2)
+        cfg, model, samples = wl.cfg, wl.model, wl.samples
     model = model.to(dev)
     dev_samples = [tuple(t.to(dev) for t in s) for s in samples]
 
