@@ -791,14 +791,32 @@ lift_pool_sched_kernel(const LiftFused a, const LiftSched sc, int pool_only, int
   const int c4 = a.C >> 2;                               // float4 per row (C % 4 == 0)
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!(dbg & 2))
-  for (long long g = gwarp; g < n_groups; g += nwarps) {
-    const unsigned empty = __ldcg(sc.empty + g);
-    if (empty == 0u) continue;
-    const long long v0 = g << 5;
-    for (int i = lane; i < 32 * c4; i += 32) {
-      const int row = i / c4;
-      if (((empty >> row) & 1u) && v0 + row < a.V)
-        __stcs(reinterpret_cast<float4*>(a.out + v0 * a.C) + i, z);
+  {
+    // the next group's mask is fetched while this group's rows are stored (a dependent
+    // load per group headed every iteration); C == 32: row / chunk of a lane by shifts
+    long long g = gwarp;
+    unsigned empty = g < n_groups ? __ldcg(sc.empty + g) : 0u;
+    while (g < n_groups) {
+      const long long gn = g + nwarps;
+      const unsigned empty_n = gn < n_groups ? __ldcg(sc.empty + gn) : 0u;
+      if (empty != 0u) {
+        const long long v0 = g << 5;
+        float4* dst = reinterpret_cast<float4*>(a.out + v0 * a.C);
+        if (c4 == 8) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int i = k * 32 + lane, row = i >> 3;
+            if (((empty >> row) & 1u) && v0 + row < a.V) __stcs(dst + i, z);
+          }
+        } else {
+          for (int i = lane; i < 32 * c4; i += 32) {
+            const int row = i / c4;
+            if (((empty >> row) & 1u) && v0 + row < a.V) __stcs(dst + i, z);
+          }
+        }
+      }
+      g = gn;
+      empty = empty_n;
     }
   }
 }
