@@ -119,6 +119,7 @@ struct HaloParams {
   int stage_off;               // byte offset of the epilogue staging (0: aliases the halo ring)
   int stage_bytes;             // bytes reserved between the weight ring and the barriers
   int cps;                     // CTAs per SM the plan counts on (1 or 2)
+  int pdl;                     // launched with programmatic stream serialization
   int zero;                    // always 0: added to values read through a scoreboarded load so that
                                // later uses depend on an ALU result (see tmem_base below)
   int dbg;                     // PW_HALO_DBG knock-out bits (timing experiments only)
@@ -211,6 +212,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
     asm volatile("mov.u32 %0, %1;" : "=r"(tmem_base) : "r"(loaded));   // not re-materialised later
   }
   if (threadIdx.x == 0) PW_TS(1);
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map
+  // prefetch, tap table) may run while the previous kernel of the stream drains; nothing below
+  // touches global memory before that kernel has completed and flushed.  Our own dependents
+  // may be scheduled as soon as every CTA of this grid is running.
+  if (p.pdl) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
   const int tile_cols = p.nacc * 2 * p.n_tile;          // TMEM columns of one M tile's accumulators
   const uint32_t a_ring_col = (uint32_t)(p.mt * tile_cols);
 
@@ -1078,10 +1087,24 @@ int launch_halo(HaloPlan plan /* copy: per-launch fields are filled here */,
     cudaMalloc(&p.ts, n_cta * 16 * sizeof(long long));
     cudaMemset(p.ts, 0, n_cta * 16 * sizeof(long long));
   }
-  if (plan.sets == 1)
-    conv_halo_kernel<1, 2><<<plan.grid, halo_threads(1), plan.smem, st>>>(ma, mbh, mbl, p);
-  else
-    conv_halo_kernel<2, 1><<<plan.grid, halo_threads(2), plan.smem, st>>>(ma, mbh, mbl, p);
+  static const int pdl_knob = getenv("PW_HALO_PDL") ? atoi(getenv("PW_HALO_PDL")) : 1;
+  p.pdl = pdl_knob && !want_ts;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = plan.grid;
+    cfg.blockDim = dim3((unsigned)halo_threads(plan.sets == 1 ? 1 : 2));
+    cfg.dynamicSmemBytes = plan.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p.pdl ? 1 : 0;
+    cudaError_t e = plan.sets == 1
+                        ? cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, 2>, ma, mbh, mbl, p)
+                        : cudaLaunchKernelEx(&cfg, conv_halo_kernel<2, 1>, ma, mbh, mbl, p);
+    if (e != cudaSuccess) return (int)e;
+  }
   PW_LAUNCH_CHECK();
   if (want_ts) {
     cudaStreamSynchronize(st);
