@@ -45,7 +45,7 @@ long long pw_launch_count(void);
  * x: [n,d,h,w,in_ld] (first `cin` channels used); w: [kd*kh*kw*cin, w_ld]
  * (k ordered tap-major then cin; w_ld >= cout padded with zeros, w_ld%4==0);
  * scale/bias/residual may be NULL.  act: 0 none, 1 relu, 2 softplus
- * (threshold 20), 3 sigmoid.  cin%4 == 0, in_ld%4 == 0, x and w 16-byte
+ * (threshold 20), 3 sigmoid, 4 gelu (erf form).  cin%4 == 0, in_ld%4 == 0, x and w 16-byte
  * aligned.
  * ---------------------------------------------------------------------- */
 typedef struct pw_conv_desc {
@@ -549,6 +549,38 @@ int pw_focal_loss_grad(const float* logits, int ld, const unsigned char* target,
 int pw_pts2ray(const float* coor, const float* label_depth, const float* label_seg,
                const float* label_img, const float* c2w, const float* cam_intrinsic,
                long long n, float* rays, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Swin image backbone of the shipped config (mmdet3d/models/backbones/swin.py:
+ * 679-976; configs/preworld/nuscenes/bevstereo-occ.py:45-67).  Tokens are the
+ * channels-last image [b,h,w,C] (== the reference's [b, h*w, C]); the linears
+ * (qkv, proj, FFN, reduction) are pw_conv_* 1x1 convs (act 4 = GELU).
+ * ---------------------------------------------------------------------- */
+/* torch.nn.LayerNorm over the last dim: y[r,:] = (x[r,:] - mean) * rsqrt(var +
+ * eps) * gamma + beta (biased variance), rows [r, c], c % 4 == 0, c <= 2048. */
+int pw_layernorm(const float* x, int x_ld, const float* gamma, const float* beta,
+                 float eps, float* y, int y_ld, long long rows, int c, void* stream);
+/* PatchMerging.forward up to its reduction (swin.py:185-206): y[b,Y,X, s*c + ch]
+ * = LayerNorm_{4c}( x[b, 2Y + s/2, 2X + s%2, ch] ), zeros beyond an odd h / w
+ * (F.pad, :198-199).  nn.Unfold orders the 4c channels (ch, ky, kx); this kernel
+ * orders them (ky, kx, ch): gamma / beta and the columns of the reduction weight
+ * are permuted accordingly by the caller.  y: [b,(h+1)/2,(w+1)/2,y_ld]. */
+int pw_patch_merge_ln(const float* x, int x_ld, int b, int h, int w, int c,
+                      const float* gamma, const float* beta, float eps, float* y,
+                      int y_ld, void* stream);
+/* ShiftWindowMSA.forward + WindowMSA.forward between the qkv and the proj linear
+ * (swin.py:262-300, 364-427): zero padding to a multiple of ws, cyclic shift,
+ * window partition, softmax(q*scale k^T + relative position bias + shift mask) v,
+ * window reverse, shift back, crop -- as index arithmetic, no copies.
+ * qkv [b,h,w,qkv_ld] = q|k|v (c channels each, head-major, head dim 32), qkv_bias
+ * [3c] or NULL (k / v of the padding rows, which the reference pads BEFORE the
+ * linear), table [heads][(2ws-1)^2] = relative_position_bias_table transposed
+ * (entry (dy+ws-1)*(2ws-1) + dx+ws-1 for query - key offset (dy,dx), the layout
+ * relative_position_index encodes, :246-252), out [b,h,w,out_ld] (c channels).
+ * c == heads*32, ws*ws <= 256, 0 <= shift < ws. */
+int pw_window_attention(const float* qkv, int qkv_ld, const float* qkv_bias,
+                        const float* table, float* out, int out_ld, int b, int h, int w,
+                        int c, int heads, int ws, int shift, float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,11 @@ CASES = {
     'tiny_pretrain_traj': dict(variant='pretrain-traj', backbone='r50',
                                input_size=(64, 176), grid=TINY_GRID, seed=7,
                                input_seed=8, detector='PreWorld4DTraj'),
+    # the SHIPPED image side (SwinTransformer + FPN_LSS, bevstereo-occ.py:45-74) at reduced
+    # depth / window; width 128 as Swin-B (the stereo feature must be 128 channels wide)
+    'tiny_swin_finetune': dict(variant='finetune', backbone='swin',
+                               input_size=(64, 192), grid=TINY_GRID, seed=9,
+                               input_seed=10, detector='PreWorld'),
     'full_finetune': dict(variant='finetune', backbone='r50',
                           input_size=(256, 704), grid=None, seed=0,
                           input_seed=0, detector='PreWorld'),
@@ -37,8 +42,14 @@ RENDER_CASE = dict(num_rays=768, seed=11)
 
 
 def model_cfg_for(case, reference_root=None):
-    return C.model_cfg(case['variant'], case['backbone'], case['input_size'],
-                       case['grid'])
+    cfg = C.model_cfg(case['variant'], case['backbone'], case['input_size'],
+                      case['grid'])
+    if case['backbone'] == 'swin':
+        cfg['img_backbone'].update(depths=[2, 2, 2, 2], window_size=6, with_cp=False)
+        cfg['img_neck'].update(out_channels=128)
+        cfg['img_view_transformer'].update(in_channels=128,
+                                           input_size=tuple(case['input_size']))
+    return cfg
 
 
 def build_case_inputs(case, batch=1):

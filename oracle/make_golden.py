@@ -33,6 +33,11 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(
 
 def _ref_model(case):
     from preworld_b200 import synthetic as S
+    if case['backbone'] == 'swin':
+        # the real swin.py must be in place before detectors/bevdet.py binds its
+        # isinstance() target (bevdet.py:11,589)
+        from oracle import swin_shim
+        swin_shim.load()
     builder = ref_shim.load_all()
     from preworld_b200.config import ConfigDict
     model = builder.build_model(ConfigDict(model_cfg_for(case)))

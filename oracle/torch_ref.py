@@ -436,8 +436,11 @@ class PathConfig:
         self.geo = LiftGeometry(vt['grid_config'], tuple(vt['input_size']),
                                 vt['downsample'], vt['out_channels'])
         self.cv_bias = vt['depthnet_cfg'].get('bias', 0.0)
-        self.depth = model_cfg['img_backbone']['depth']
-        self.out_indices = tuple(model_cfg['img_backbone']['out_indices'])
+        self.backbone_cfg = dict(model_cfg['img_backbone'])
+        self.neck_cfg = dict(model_cfg['img_neck'])
+        self.swin = self.backbone_cfg['type'] == 'SwinTransformer'
+        self.depth = self.backbone_cfg.get('depth')
+        self.out_indices = tuple(self.backbone_cfg['out_indices'])
         enc = model_cfg['img_bev_encoder_backbone']
         self.enc_layers, self.enc_stride = enc['num_layer'], enc['stride']
         pre = model_cfg['pre_process']
@@ -451,6 +454,14 @@ class PathConfig:
 def image_encoder(sd, pc, img):
     """detectors/bevdet.py:34-50 (stereo=True)."""
     B, N, C, H, W = img.shape
+    if pc.swin:                      # the shipped image side (oracle/swin_ref.py)
+        from . import swin_ref
+        outs = swin_ref.backbone_forward(
+            swin_ref.backbone_from_state_dict(sd, 'img_backbone', pc.backbone_cfg),
+            img.view(B * N, C, H, W))
+        x = swin_ref.neck_forward(
+            swin_ref.neck_from_state_dict(sd, 'img_neck', pc.neck_cfg), outs[1:])
+        return x.view(B, N, *x.shape[1:]), outs[0]
     x = resnet(sd, 'img_backbone', img.view(B * N, C, H, W), pc.depth,
                pc.out_indices)
     stereo_feat, x = x[0], x[1:]
@@ -461,6 +472,11 @@ def image_encoder(sd, pc, img):
 def extract_stereo_ref_feat(sd, pc, img):
     """detectors/bevdet.py:573-588 (mmdet ResNet branch)."""
     B, N, C, H, W = img.shape
+    if pc.swin:                      # bevdet.py:589-604
+        from . import swin_ref
+        return swin_ref.stage0_forward(
+            swin_ref.backbone_from_state_dict(sd, 'img_backbone', pc.backbone_cfg),
+            img.view(B * N, C, H, W))
     x = resnet_stem(sd, 'img_backbone', img.view(B * N, C, H, W))
     return resnet_layer(sd, 'img_backbone', x, 0, pc.depth)
 

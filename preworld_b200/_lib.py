@@ -120,6 +120,11 @@ SIGNATURES = {
     'pw_argmax_geo_zyx_to_xyz': [c_p, c_int, c_int, c_int, c_int, c_p, c_p,
                                  c_int, c_int, c_int, c_p],
     'pw_copy_rows': [c_p, c_ll, c_p, c_ll, c_ll, c_ll, c_p],
+    'pw_layernorm': [c_p, c_int, c_p, c_p, c_f, c_p, c_int, c_ll, c_int, c_p],
+    'pw_patch_merge_ln': [c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_f,
+                          c_p, c_int, c_p],
+    'pw_window_attention': [c_p, c_int, c_p, c_p, c_p, c_int, c_int, c_int, c_int,
+                            c_int, c_int, c_int, c_int, c_f, c_p],
     'pw_density_occ_zyx_to_xyz': [c_p, c_int, c_p, c_int, c_int, c_f, c_int,
                                   c_p, c_p, c_int, c_int, c_int, c_p],
     'pw_zyx_to_xyz': [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],

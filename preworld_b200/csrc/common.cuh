@@ -24,7 +24,8 @@ void pw_count_launch(int k);
 
 static inline int pw_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-enum PwAct { PW_ACT_NONE = 0, PW_ACT_RELU = 1, PW_ACT_SOFTPLUS = 2, PW_ACT_SIGMOID = 3 };
+enum PwAct { PW_ACT_NONE = 0, PW_ACT_RELU = 1, PW_ACT_SOFTPLUS = 2, PW_ACT_SIGMOID = 3,
+             PW_ACT_GELU = 4 };
 
 __device__ __forceinline__ float pw_softplus(float v) {
   // torch.nn.Softplus(beta=1, threshold=20)
@@ -36,6 +37,8 @@ __device__ __forceinline__ float pw_activate(float v, int act) {
     case PW_ACT_RELU: return fmaxf(v, 0.f);
     case PW_ACT_SOFTPLUS: return pw_softplus(v);
     case PW_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    // torch.nn.GELU() (approximate='none'): x * 0.5 * (1 + erf(x / sqrt(2)))
+    case PW_ACT_GELU: return v * 0.5f * (1.f + erff(v * 0.70710678118654752440f));
     default: return v;
   }
 }

@@ -701,8 +701,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
               if (cbase + 2 < p.cout) vc += __ldg(rrow + 2);
               if (cbase + 3 < p.cout) vd += __ldg(rrow + 3);
             }
-            va = pw_activate_slow(va, a_); vb = pw_activate_slow(vb, a_);
-            vc = pw_activate_slow(vc, a_); vd = pw_activate_slow(vd, a_);
+            if (a_ == PW_ACT_GELU) {                   // Swin FFN (fc1, 4C wide): erff inline
+              va = pw_activate(va, PW_ACT_GELU); vb = pw_activate(vb, PW_ACT_GELU);
+              vc = pw_activate(vc, PW_ACT_GELU); vd = pw_activate(vd, PW_ACT_GELU);
+            } else {
+              va = pw_activate_slow(va, a_); vb = pw_activate_slow(vb, a_);
+              vc = pw_activate_slow(vc, a_); vd = pw_activate_slow(vd, a_);
+            }
+            if (vec) {
+              *reinterpret_cast<float4*>(yrow) = make_float4(va, vb, vc, vd);
+              continue;
+            }
             yrow[0] = va;
             if (cbase + 1 < p.cout) yrow[1] = vb;
             if (cbase + 2 < p.cout) yrow[2] = vc;

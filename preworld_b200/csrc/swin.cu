@@ -1,0 +1,325 @@
+// Swin image backbone (reference mmdet3d/models/backbones/swin.py:679-976, the backbone of
+// the shipped config configs/preworld/nuscenes/bevstereo-occ.py:45-67): the three operators
+// that are not a conv/linear.  Tokens stay in ONE layout for the whole backbone -- the
+// channels-last image [B,H,W,C] (== the reference's [B, H*W, C]) -- so the reference's
+// pad / roll / window_partition / window_reverse / crop copies (swin.py:371-440) never
+// exist: the attention kernel resolves them as index arithmetic on its loads and stores.
+//
+//   pw_layernorm         nn.LayerNorm over channels (norm1/norm2/norm{i}/patch_embed.norm)
+//   pw_patch_merge_ln    PatchMerging.forward up to the reduction (swin.py:185-206):
+//                        2x2 gather + zero pad + LayerNorm(4C)
+//   pw_window_attention  ShiftWindowMSA.forward + WindowMSA.forward without the two
+//                        linears (swin.py:262-300, 364-427)
+#include "common.cuh"
+
+#include <math.h>
+
+#include "../../include/preworld_b200.h"
+
+namespace {
+
+#define ST ((cudaStream_t)stream)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- LayerNorm ---------------------------------------------------------------------
+// One warp per row, the row in registers (NV float4 per lane), two-pass moments.
+// A row is `nseg` segments of seg_c channels; MERGE: segment s = ky*2+kx of output token
+// (Y,X) is input token (2Y+ky, 2X+kx) (zeros outside the map, swin.py:198-199).
+struct LnParams {
+  const float* x;
+  float* y;
+  const float* gamma;
+  const float* beta;
+  long long rows;
+  int c, x_ld, y_ld;
+  float eps;
+  int h, w, oh, ow, seg_c;      // MERGE only
+};
+
+template <int NV, bool MERGE>
+__global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int nvec = p.c >> 2;
+  for (long long row = warp0; row < p.rows; row += nwarps) {
+    const float* seg[4];
+    if (MERGE) {
+      const int X = (int)(row % p.ow);
+      const long long t = row / p.ow;
+      const int Y = (int)(t % p.oh);
+      const long long b = t / p.oh;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int yy = 2 * Y + (s >> 1), xx = 2 * X + (s & 1);
+        seg[s] = (yy < p.h && xx < p.w)
+                     ? p.x + ((b * p.h + yy) * (long long)p.w + xx) * p.x_ld
+                     : nullptr;
+      }
+    } else {
+      seg[0] = p.x + row * (long long)p.x_ld;
+    }
+    float4 v[NV];
+    float s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int e = i * 32 + lane;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < nvec) {
+        const float* src;
+        if (MERGE) {
+          const int ch = e * 4, s = ch / p.seg_c;
+          src = seg[s] ? seg[s] + (ch - s * p.seg_c) : nullptr;
+        } else {
+          src = seg[0] + e * 4;
+        }
+        if (src) v[i] = pw_ldg4(src);
+        s1 += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    const float mean = warp_sum(s1) / (float)p.c;
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i * 32 + lane < nvec) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        s2 += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(s2) / (float)p.c + p.eps);
+    float* yrow = p.y + row * (long long)p.y_ld;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int e = i * 32 + lane;
+      if (e < nvec) {
+        const float4 g = pw_ldg4(p.gamma + e * 4), bt = pw_ldg4(p.beta + e * 4);
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + bt.x;
+        o.y = (v[i].y - mean) * rstd * g.y + bt.y;
+        o.z = (v[i].z - mean) * rstd * g.z + bt.z;
+        o.w = (v[i].w - mean) * rstd * g.w + bt.w;
+        *reinterpret_cast<float4*>(yrow + e * 4) = o;
+      }
+    }
+  }
+}
+
+template <bool MERGE>
+int launch_layernorm(const LnParams& p, cudaStream_t s) {
+  const int nvec = p.c / 4;
+  const int wpb = 8;
+  long long blocks = (p.rows + wpb - 1) / wpb;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const dim3 g((unsigned)blocks), b(wpb * 32);
+  if (nvec <= 32) layernorm_kernel<1, MERGE><<<g, b, 0, s>>>(p);
+  else if (nvec <= 64) layernorm_kernel<2, MERGE><<<g, b, 0, s>>>(p);
+  else if (nvec <= 128) layernorm_kernel<4, MERGE><<<g, b, 0, s>>>(p);
+  else if (nvec <= 256) layernorm_kernel<8, MERGE><<<g, b, 0, s>>>(p);
+  else if (nvec <= 512) layernorm_kernel<16, MERGE><<<g, b, 0, s>>>(p);
+  else return PW_ERR_INVALID_ARGUMENT;
+  return 0;
+}
+
+// ---- shifted-window attention --------------------------------------------------------
+// CTA = one (window, head); thread t = query token t of the window (head dim 32: q and the
+// output row live in registers), K and V of the window in shared memory, read as broadcast
+// 128-bit loads.  One pass over the keys with a running maximum instead of a [N,N] score
+// tile: 41 KB of smem per CTA at N = 144, five CTAs per SM.  Window token (iy,ix) of window (wy,wx) sits at (py,px) = (wy*ws+iy,
+// wx*ws+ix) of the padded, rolled map; torch.roll(-shift) puts padded-map position
+// ((py+shift)%Hp, (px+shift)%Wp) there.  Positions outside [H,W] are the zero padding the
+// reference adds BEFORE the qkv linear (swin.py:371-374): their k / v rows are the qkv bias.
+constexpr int HD = 32;
+
+struct AttnParams {
+  const float* qkv;        // [b,h,w,qkv_ld]: q | k | v, each c = heads*32 channels
+  const float* qkv_bias;   // [3c] or null
+  const float* table;      // [heads][(2ws-1)^2] relative position bias, head-major
+  float* out;              // [b,h,w,out_ld]
+  int b, h, w, c, heads, ws, shift, qkv_ld, out_ld;
+  int hp, wp, nwx, nwin;   // padded map, windows per row / per image
+  float scale;
+};
+
+__device__ __forceinline__ float dot32(const float (&q)[HD], const float* k) {
+  // four independent chains (a single 32-long fmaf chain is latency bound at ~5 warps per
+  // scheduler), combined pairwise
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < HD / 4; ++j) {
+    const float4 kv = *reinterpret_cast<const float4*>(k + j * 4);
+    s0 = fmaf(q[j * 4 + 0], kv.x, s0);
+    s1 = fmaf(q[j * 4 + 1], kv.y, s1);
+    s2 = fmaf(q[j * 4 + 2], kv.z, s2);
+    s3 = fmaf(q[j * 4 + 3], kv.w, s3);
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
+__global__ void __launch_bounds__(256) window_attention_kernel(const AttnParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int n = p.ws * p.ws;
+  const int tw = 2 * p.ws - 1;
+  float* ks = smem;                                   // [n][32]
+  float* vs = ks + n * HD;                            // [n][32]
+  float* tab = vs + n * HD;                           // [tw*tw]
+  int* src = reinterpret_cast<int*>(tab + tw * tw);   // [n] pixel index or -1 (padding)
+  int* koff = src + n;                                // [n] ky*tw + kx
+  int* kid = koff + n;                                // [n] shift-mask region
+
+  const int head = blockIdx.x % p.heads;
+  const int win = (blockIdx.x / p.heads) % p.nwin;
+  const int b = blockIdx.x / (p.heads * p.nwin);
+  const int wy = win / p.nwx, wx = win % p.nwx;
+  const int t = threadIdx.x;
+
+  int my_src = -1, my_id = 0, my_base = 0;
+  if (t < n) {
+    const int iy = t / p.ws, ix = t - iy * p.ws;
+    const int py = wy * p.ws + iy, px = wx * p.ws + ix;
+    int sy = py + p.shift, sx = px + p.shift;
+    sy -= sy >= p.hp ? p.hp : 0;
+    sx -= sx >= p.wp ? p.wp : 0;
+    my_src = (sy < p.h && sx < p.w) ? (b * p.h + sy) * p.w + sx : -1;
+    if (p.shift > 0) {
+      // img_mask regions of swin.py:381-391 (slices 0:-ws, -ws:-shift, -shift:)
+      const int hr = py < p.hp - p.ws ? 0 : (py < p.hp - p.shift ? 1 : 2);
+      const int wr = px < p.wp - p.ws ? 0 : (px < p.wp - p.shift ? 1 : 2);
+      my_id = hr * 3 + wr;
+    }
+    my_base = (iy + p.ws - 1) * tw + ix + p.ws - 1;
+    src[t] = my_src;
+    koff[t] = iy * tw + ix;
+    kid[t] = my_id;
+  }
+  for (int i = t; i < tw * tw; i += blockDim.x) tab[i] = __ldg(p.table + head * tw * tw + i);
+  __syncthreads();
+  const int hc = head * HD;
+  for (int i = t; i < n * (HD / 4); i += blockDim.x) {
+    const int tok = i >> 3, j = (i & 7) * 4;
+    const int s = src[tok];
+    float4 kv, vv;
+    if (s >= 0) {
+      const float* row = p.qkv + (long long)s * p.qkv_ld + hc + j;
+      kv = pw_ldg4(row + p.c);
+      vv = pw_ldg4(row + 2 * p.c);
+    } else if (p.qkv_bias) {
+      kv = pw_ldg4(p.qkv_bias + p.c + hc + j);
+      vv = pw_ldg4(p.qkv_bias + 2 * p.c + hc + j);
+    } else {
+      kv = vv = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    *reinterpret_cast<float4*>(ks + tok * HD + j) = kv;
+    *reinterpret_cast<float4*>(vs + tok * HD + j) = vv;
+  }
+  __syncthreads();
+  if (my_src < 0) return;            // padding rows are cropped (swin.py:421-422); t >= n
+
+  float q[HD];
+  {
+    const float* row = p.qkv + (long long)my_src * p.qkv_ld + hc;
+#pragma unroll
+    for (int j = 0; j < HD / 4; ++j) {
+      const float4 v4 = pw_ldg4(row + j * 4);
+      q[j * 4 + 0] = v4.x * p.scale;                  // q = q * self.scale (swin.py:272)
+      q[j * 4 + 1] = v4.y * p.scale;
+      q[j * 4 + 2] = v4.z * p.scale;
+      q[j * 4 + 3] = v4.w * p.scale;
+    }
+  }
+  // One pass over the keys with a running maximum (online softmax): when a key raises the
+  // maximum the partial sums are rescaled; after the first few keys that is rare, and the
+  // branch is warp-uniform most of the time.
+  const bool masked = p.shift > 0;
+  float o[HD];
+#pragma unroll
+  for (int j = 0; j < HD; ++j) o[j] = 0.f;
+  float m = -INFINITY, l = 0.f;
+#pragma unroll 2
+  for (int k = 0; k < n; ++k) {
+    float s = dot32(q, ks + k * HD) + tab[my_base - koff[k]];
+    if (masked && kid[k] != my_id) s += -100.f;
+    if (s > m) {
+      const float r = expf(m - s);              // first key: exp(-inf) = 0
+      l *= r;
+#pragma unroll
+      for (int j = 0; j < HD; ++j) o[j] *= r;
+      m = s;
+    }
+    const float e = expf(s - m);
+    l += e;
+    const float* vr = vs + k * HD;
+#pragma unroll
+    for (int j = 0; j < HD / 4; ++j) {
+      const float4 vv = *reinterpret_cast<const float4*>(vr + j * 4);
+      o[j * 4 + 0] = fmaf(e, vv.x, o[j * 4 + 0]);
+      o[j * 4 + 1] = fmaf(e, vv.y, o[j * 4 + 1]);
+      o[j * 4 + 2] = fmaf(e, vv.z, o[j * 4 + 2]);
+      o[j * 4 + 3] = fmaf(e, vv.w, o[j * 4 + 3]);
+    }
+  }
+  const float inv = 1.f / l;
+  float* orow = p.out + (long long)my_src * p.out_ld + hc;
+#pragma unroll
+  for (int j = 0; j < HD / 4; ++j)
+    *reinterpret_cast<float4*>(orow + j * 4) =
+        make_float4(o[j * 4] * inv, o[j * 4 + 1] * inv, o[j * 4 + 2] * inv, o[j * 4 + 3] * inv);
+}
+
+}  // namespace
+
+PW_API int pw_layernorm(const float* x, int x_ld, const float* gamma, const float* beta,
+                        float eps, float* y, int y_ld, long long rows, int c, void* stream) {
+  PW_REQUIRE(x && y && gamma && beta && rows > 0 && c > 0 && c % 4 == 0 && c <= 2048);
+  PW_REQUIRE(x_ld >= c && y_ld >= c && x_ld % 4 == 0 && y_ld % 4 == 0);
+  LnParams p{x, y, gamma, beta, rows, c, x_ld, y_ld, eps, 0, 0, 0, 0, c};
+  const int rc = launch_layernorm<false>(p, ST);
+  if (rc) return rc;
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+PW_API int pw_patch_merge_ln(const float* x, int x_ld, int b, int h, int w, int c,
+                             const float* gamma, const float* beta, float eps, float* y,
+                             int y_ld, void* stream) {
+  PW_REQUIRE(x && y && gamma && beta && b > 0 && h > 0 && w > 0 && c > 0 && c % 4 == 0);
+  PW_REQUIRE(4 * c <= 2048 && x_ld >= c && x_ld % 4 == 0 && y_ld >= 4 * c && y_ld % 4 == 0);
+  const int oh = (h + 1) / 2, ow = (w + 1) / 2;
+  LnParams p{x, y, gamma, beta, (long long)b * oh * ow, 4 * c, x_ld, y_ld, eps, h, w, oh, ow, c};
+  const int rc = launch_layernorm<true>(p, ST);
+  if (rc) return rc;
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}
+
+PW_API int pw_window_attention(const float* qkv, int qkv_ld, const float* qkv_bias,
+                               const float* table, float* out, int out_ld, int b, int h, int w,
+                               int c, int heads, int ws, int shift, float scale, void* stream) {
+  PW_REQUIRE(qkv && table && out && b > 0 && h > 0 && w > 0 && heads > 0 && c == heads * HD);
+  PW_REQUIRE(ws >= 1 && ws * ws <= 256 && shift >= 0 && shift < ws);
+  PW_REQUIRE(qkv_ld >= 3 * c && qkv_ld % 4 == 0 && out_ld >= c && out_ld % 4 == 0);
+  PW_REQUIRE((long long)b * h * w < (1ll << 31));
+  AttnParams p;
+  p.qkv = qkv; p.qkv_bias = qkv_bias; p.table = table; p.out = out;
+  p.b = b; p.h = h; p.w = w; p.c = c; p.heads = heads; p.ws = ws; p.shift = shift;
+  p.qkv_ld = qkv_ld; p.out_ld = out_ld;
+  p.hp = (h + ws - 1) / ws * ws; p.wp = (w + ws - 1) / ws * ws;
+  p.nwx = p.wp / ws; p.nwin = (p.hp / ws) * p.nwx;
+  p.scale = scale;
+  const int n = ws * ws, tw = 2 * ws - 1;
+  const size_t smem = (size_t)(2 * n * HD + tw * tw) * 4 + (size_t)3 * n * 4;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(window_attention_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const long long blocks = (long long)b * p.nwin * heads;
+  PW_REQUIRE(blocks < (1ll << 31));
+  window_attention_kernel<<<(unsigned)blocks, (n + 31) / 32 * 32, smem, ST>>>(p);
+  PW_LAUNCH_CHECK(); pw_count_launch(1);
+  return 0;
+}

@@ -19,7 +19,7 @@ import torch
 from . import _lib
 from ._lib import ConvDesc, RenderDesc, check
 
-ACT = {None: 0, 'none': 0, 'relu': 1, 'softplus': 2, 'sigmoid': 3}
+ACT = {None: 0, 'none': 0, 'relu': 1, 'softplus': 2, 'sigmoid': 3, 'gelu': 4}
 
 
 def _stream():
@@ -662,6 +662,51 @@ def lift_pool(depth, feat_cl, ws, b, n, grid, out=None):
     check(_lib.lib().pw_lift_pool(
         _ptr(depth), _ptr(feat_cl), cl_ld(feat_cl), b, n, d, h, w, c, gx, gy,
         gz, _ptr(out), _ptr(ws), _stream()), 'pw_lift_pool')
+    return out
+
+
+# ---------------------------------------------------------------- Swin backbone
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    """nn.LayerNorm over the channels of a cl array [..., C] (x / out may be channel
+    slices of wider arrays)."""
+    _require_cuda(x, gamma, beta, out)
+    c = x.shape[-1]
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    assert out.shape == x.shape and gamma.numel() == c and beta.numel() == c
+    rows = x[..., 0].numel()
+    check(_lib.lib().pw_layernorm(_ptr(x), cl_ld(x), _ptr(gamma), _ptr(beta), float(eps),
+                                  _ptr(out), cl_ld(out), rows, c, _stream()), 'pw_layernorm')
+    return out
+
+
+def patch_merge_ln(x, gamma_kkc, beta_kkc, eps=1e-5):
+    """x [B,H,W,C] -> LayerNorm of the 2x2-gathered tokens [B,ceil(H/2),ceil(W/2),4C],
+    channels ordered (ky, kx, c) (gamma / beta given in that order)."""
+    _require_cuda(x, gamma_kkc, beta_kkc)
+    b, h, w, c = x.shape
+    assert gamma_kkc.numel() == 4 * c and beta_kkc.numel() == 4 * c
+    out = torch.empty((b, (h + 1) // 2, (w + 1) // 2, 4 * c), device=x.device,
+                      dtype=torch.float32)
+    check(_lib.lib().pw_patch_merge_ln(_ptr(x), cl_ld(x), b, h, w, c, _ptr(gamma_kkc),
+                                       _ptr(beta_kkc), float(eps), _ptr(out), 4 * c,
+                                       _stream()), 'pw_patch_merge_ln')
+    return out
+
+
+def window_attention(qkv, qkv_bias, table_t, heads, ws, shift, scale, out=None):
+    """qkv [B,H,W,3C] (q|k|v, head-major, head dim 32) -> shifted-window attention output
+    [B,H,W,C]; table_t [heads,(2ws-1)^2]."""
+    _require_cuda(qkv, qkv_bias, table_t, out)
+    b, h, w, c3 = qkv.shape
+    c = c3 // 3
+    assert c * 3 == c3 and c == heads * 32, 'head dim 32 (every Swin variant)'
+    assert table_t.shape == (heads, (2 * ws - 1) ** 2) and table_t.is_contiguous()
+    if out is None:
+        out = torch.empty((b, h, w, c), device=qkv.device, dtype=torch.float32)
+    check(_lib.lib().pw_window_attention(_ptr(qkv), cl_ld(qkv), _ptr(qkv_bias), _ptr(table_t),
+                                         _ptr(out), cl_ld(out), b, h, w, c, heads, ws, shift,
+                                         float(scale), _stream()), 'pw_window_attention')
     return out
 
 

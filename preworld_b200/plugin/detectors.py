@@ -199,7 +199,7 @@ class BEVStereo4DOCC(BaseModule):
         B, N, C, imH, imW = imgs[0].shape
         bn = B * N
         bb = self.img_backbone
-        if not (hasattr(bb, 'run_stem_cl') and 0 in bb.out_indices):
+        if not getattr(bb, 'stage0_is_stereo', False):
             return None
         l1 = getattr(self, '_stereo_batch', None)             # see stem_frame()
         if l1 is None:
@@ -411,7 +411,7 @@ class BEVStereo4DOCC(BaseModule):
             if enc is None:
                 raise NotImplementedError(
                     'camera sharding needs a backbone with the batched stem + '
-                    'layer1 path (run_stem_cl, out_indices containing 0)')
+                    'layer1 path (stage0_is_stereo)')
             # frames of the pose lists beyond the lifted ones are never indexed
             depth, tran = self._depth_frames_batched(
                 cn, [t[:, sl] for t in sensor2keyegos],

@@ -8,6 +8,8 @@ also torchvision's.  ``CustomFPN`` mirrors reference necks/fpn.py:10-203.
 All arithmetic runs in the C-ABI conv kernel with BatchNorm, residual add and
 ReLU fused into its epilogue.
 """
+import math
+
 import torch
 import torch.nn as nn
 
@@ -125,6 +127,12 @@ class ResNet(BaseModule):
     @property
     def norm1(self):
         return self.bn1
+
+    @property
+    def stage0_is_stereo(self):
+        """layer1's output is the stereo feature AND the input of layer2
+        (what detectors.encode_frames batches over all frames)."""
+        return 0 in self.out_indices
 
     def _build_packs(self):
         return dict(stem=pack_conv(self.conv1, self.bn1),
@@ -275,3 +283,97 @@ class CustomFPN(BaseModule):
         outs = [ops.to_logical(ops.conv(lat[i], p['fpn'][k]))
                 for k, i in enumerate(self.out_ids)]
         return outs[0]
+
+
+@NECKS.register_module()
+class FPN_LSS(BaseModule):
+    """necks/lss_fpn.py:13-99 -- the image neck of the shipped Swin config
+    (bevstereo-occ.py:68-74): bilinear (align_corners) upsampling of the
+    coarser map, concatenation with the finer one, two 3x3 conv + BN + ReLU
+    (optionally ``up2``: one more upsampling + 3x3 conv + BN + ReLU + 1x1 conv).
+    The upsampled map and the finer map are written straight into the two
+    channel slices of the concatenation buffer."""
+
+    def __init__(self, in_channels, out_channels, scale_factor=4,
+                 input_feature_index=(0, 2), norm_cfg=dict(type='BN'),
+                 extra_upsample=2, lateral=None, use_input_conv=False):
+        super().__init__()
+        from .base import build_norm_layer
+        self.input_feature_index = input_feature_index
+        self.extra_upsample = extra_upsample is not None
+        self.scale_factor = scale_factor
+        self.up = nn.Upsample(scale_factor=scale_factor, mode='bilinear',
+                              align_corners=True)
+        cf = 2 if self.extra_upsample else 1
+        bn = lambda ch: build_norm_layer(norm_cfg, ch, postfix=0)[1]
+        self.input_conv = nn.Sequential(
+            nn.Conv2d(in_channels, out_channels * cf, 1, padding=0, bias=False),
+            bn(out_channels * cf), nn.ReLU(inplace=True)) \
+            if use_input_conv else None
+        if use_input_conv:
+            in_channels = out_channels * cf
+        self.conv = nn.Sequential(
+            nn.Conv2d(in_channels, out_channels * cf, 3, padding=1, bias=False),
+            bn(out_channels * cf), nn.ReLU(inplace=True),
+            nn.Conv2d(out_channels * cf, out_channels * cf, 3, padding=1,
+                      bias=False),
+            bn(out_channels * cf), nn.ReLU(inplace=True))
+        if self.extra_upsample:
+            self.extra_scale = extra_upsample
+            self.up2 = nn.Sequential(
+                nn.Upsample(scale_factor=extra_upsample, mode='bilinear',
+                            align_corners=True),
+                nn.Conv2d(out_channels * cf, out_channels, 3, padding=1,
+                          bias=False),
+                bn(out_channels), nn.ReLU(inplace=True),
+                nn.Conv2d(out_channels, out_channels, 1, padding=0))
+        self.lateral = lateral is not None
+        if self.lateral:
+            self.lateral_conv = nn.Sequential(
+                nn.Conv2d(lateral, lateral, 1, padding=0, bias=False),
+                bn(lateral), nn.ReLU(inplace=True))
+
+    def _build_packs(self):
+        p = dict(conv=[pack_conv(self.conv[0], self.conv[1]),
+                       pack_conv(self.conv[3], self.conv[4])])
+        if self.input_conv is not None:
+            p['input'] = pack_conv(self.input_conv[0], self.input_conv[1])
+        if self.extra_upsample:
+            p['up2'] = [pack_conv(self.up2[1], self.up2[2]),
+                        pack_conv(self.up2[4])]
+        if self.lateral:
+            p['lateral'] = pack_conv(self.lateral_conv[0], self.lateral_conv[1])
+        return p
+
+    @staticmethod
+    def _upsample_into(out_slice, x):
+        """bilinear, align_corners=True: the trilinear kernel on a depth-1 volume."""
+        ops.upsample_trilinear_(out_slice[:, None], x[:, None])
+
+    def forward(self, feats):
+        p = self.packs()
+        x2 = ops.from_logical(feats[self.input_feature_index[0]])
+        x1 = ops.from_logical(feats[self.input_feature_index[1]])
+        if self.lateral:
+            x2 = ops.conv(x2, p['lateral'], 'relu')
+        n, h1, w1, c1 = x1.shape
+        oh, ow = int(math.floor(h1 * self.scale_factor)), \
+            int(math.floor(w1 * self.scale_factor))
+        c2 = x2.shape[-1]
+        assert tuple(x2.shape[1:3]) == (oh, ow), (x2.shape, oh, ow)
+        cat = torch.empty((n, oh, ow, c2 + c1), device=x1.device,
+                          dtype=torch.float32)
+        ops.copy_channels_(cat[..., :c2], x2)
+        self._upsample_into(cat[..., c2:], x1)
+        x = cat
+        if self.input_conv is not None:
+            x = ops.conv(x, p['input'], 'relu')
+        x = ops.conv(ops.conv(x, p['conv'][0], 'relu'), p['conv'][1], 'relu')
+        if self.extra_upsample:
+            n, h, w, c = x.shape
+            up = torch.empty((n, int(math.floor(h * self.extra_scale)),
+                              int(math.floor(w * self.extra_scale)), c),
+                             device=x.device, dtype=torch.float32)
+            self._upsample_into(up, x)
+            x = ops.conv(ops.conv(up, p['up2'][0], 'relu'), p['up2'][1])
+        return ops.to_logical(x)

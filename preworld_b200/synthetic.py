@@ -167,4 +167,13 @@ def lively_init_(module, seed=0, residual_gain=0.25):
             m.bias.copy_(torch.randn(n, generator=g) * 0.1)
             if name.endswith(_RESIDUAL_TAIL):
                 m.weight.mul_(residual_gain)
+        elif isinstance(m, torch.nn.LayerNorm):                 # Swin image side
+            n = m.normalized_shape[0]
+            g = _key_generator(name + '.ln', seed)
+            m.weight.copy_(torch.rand(n, generator=g) + 0.5)
+            m.bias.copy_(torch.randn(n, generator=g) * 0.1)
+    for name, p in module.named_parameters():
+        if name.endswith('relative_position_bias_table'):
+            g = _key_generator(name, seed)
+            p.copy_(torch.randn(p.shape, generator=g) * 0.5)
     return module

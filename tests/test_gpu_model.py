@@ -87,7 +87,8 @@ def _margin_ok(occ, want, logits_ref, tol=REL_TOL, verbose=False):
     return len(bad)
 
 
-@pytest.mark.parametrize('name', ['tiny_finetune', 'tiny_pretrain'])
+# tiny_swin_finetune: the SHIPPED image side (SwinTransformer + FPN_LSS) under the same detector
+@pytest.mark.parametrize('name', ['tiny_finetune', 'tiny_pretrain', 'tiny_swin_finetune'])
 def test_preworld_matches_reference_and_oracle(name, golden_dir):
     case = CASES[name]
     fx = np.load(os.path.join(golden_dir, name + '.npz'))

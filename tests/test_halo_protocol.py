@@ -14,7 +14,8 @@ def _shipped_sets():
     """Split sets per CTA of the compiled kernel variants:
     conv_halo_kernel<SETS, MIN_CTAS> instantiations in conv_halo.cu."""
     src = open(os.path.join(ROOT, 'preworld_b200', 'csrc', 'conv_halo.cu')).read()
-    sets = {int(m) for m in re.findall(r'conv_halo_kernel<(\d+), \d+><<<', src)}
+    sets = {int(m) for m in re.findall(
+        r'cudaLaunchKernelEx\(&cfg, conv_halo_kernel<(\d+), \d+>', src)}
     assert sets, 'no kernel launches found'
     return tuple(sorted(sets))
 

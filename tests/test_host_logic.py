@@ -21,10 +21,11 @@ def test_registry_surface():
     for name in ('ResNet', 'CustomFPN', 'LSSViewTransformerBEVStereo',
                  'CustomResNet3D', 'LSSFPN3D', 'OccHead', 'NerfHead',
                  'BEVStereo4DOCC', 'PreWorld', 'PreWorld4DTraj',
-                 'CrossEntropyLoss', 'CustomFocalLoss'):
+                 'CrossEntropyLoss', 'CustomFocalLoss', 'SwinTransformer',
+                 'FPN_LSS'):
         assert name in plugin.MODELS, name
     with pytest.raises(KeyError):
-        plugin.build_backbone(dict(type='SwinTransformer'))
+        plugin.build_backbone(dict(type='VoVNet'))
     with pytest.raises(TypeError):
         plugin.build_neck(dict(out_channels=3))
     m = plugin.build_neck(dict(type='LSSFPN3D', in_channels=224,
