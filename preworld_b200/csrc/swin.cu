@@ -145,22 +145,47 @@ struct AttnParams {
   float scale;
 };
 
-__device__ __forceinline__ float dot32(const float (&q)[HD], const float* k) {
-  // four independent chains (a single 32-long fmaf chain is latency bound at ~5 warps per
-  // scheduler), combined pairwise
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+// Packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2: two IEEE fp32 operations per lane and
+// instruction -- the plain 3-register FFMA issues at half rate).  A 128-bit shared-memory
+// load IS two packed pairs, so K / V rows need no packing moves.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pack2(float x, float y) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f2 v, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// q . k over the 32 channels of a head: four independent fmaf chains (two packed
+// accumulators; a single 32-long chain is latency bound at ~5 warps per scheduler)
+__device__ __forceinline__ float dot32(const f2 (&q)[HD / 2], const float* k) {
+  f2 a0 = 0ull, a1 = 0ull;                                   // (+0.f, +0.f)
 #pragma unroll
   for (int j = 0; j < HD / 4; ++j) {
-    const float4 kv = *reinterpret_cast<const float4*>(k + j * 4);
-    s0 = fmaf(q[j * 4 + 0], kv.x, s0);
-    s1 = fmaf(q[j * 4 + 1], kv.y, s1);
-    s2 = fmaf(q[j * 4 + 2], kv.z, s2);
-    s3 = fmaf(q[j * 4 + 3], kv.w, s3);
+    const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(k + j * 4);
+    a0 = fma2(q[2 * j], kv.x, a0);
+    a1 = fma2(q[2 * j + 1], kv.y, a1);
   }
+  float s0, s1, s2, s3;
+  unpack2(a0, s0, s1);
+  unpack2(a1, s2, s3);
   return (s0 + s1) + (s2 + s3);
 }
 
-__global__ void __launch_bounds__(256) window_attention_kernel(const AttnParams p) {
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) window_attention_kernel(const AttnParams p) {
   extern __shared__ __align__(16) float smem[];
   const int n = p.ws * p.ws;
   const int tw = 2 * p.ws - 1;
@@ -219,25 +244,23 @@ __global__ void __launch_bounds__(256) window_attention_kernel(const AttnParams 
   __syncthreads();
   if (my_src < 0) return;            // padding rows are cropped (swin.py:421-422); t >= n
 
-  float q[HD];
+  f2 q[HD / 2];
   {
     const float* row = p.qkv + (long long)my_src * p.qkv_ld + hc;
 #pragma unroll
     for (int j = 0; j < HD / 4; ++j) {
       const float4 v4 = pw_ldg4(row + j * 4);
-      q[j * 4 + 0] = v4.x * p.scale;                  // q = q * self.scale (swin.py:272)
-      q[j * 4 + 1] = v4.y * p.scale;
-      q[j * 4 + 2] = v4.z * p.scale;
-      q[j * 4 + 3] = v4.w * p.scale;
+      q[2 * j] = pack2(v4.x * p.scale, v4.y * p.scale);     // q = q * self.scale (swin.py:272)
+      q[2 * j + 1] = pack2(v4.z * p.scale, v4.w * p.scale);
     }
   }
   // One pass over the keys with a running maximum (online softmax): when a key raises the
   // maximum the partial sums are rescaled; after the first few keys that is rare, and the
   // branch is warp-uniform most of the time.
   const bool masked = p.shift > 0;
-  float o[HD];
+  f2 o[HD / 2];
 #pragma unroll
-  for (int j = 0; j < HD; ++j) o[j] = 0.f;
+  for (int j = 0; j < HD / 2; ++j) o[j] = 0ull;
   float m = -INFINITY, l = 0.f;
 #pragma unroll 2
   for (int k = 0; k < n; ++k) {
@@ -246,28 +269,32 @@ __global__ void __launch_bounds__(256) window_attention_kernel(const AttnParams 
     if (s > m) {
       const float r = expf(m - s);              // first key: exp(-inf) = 0
       l *= r;
+      const f2 r2 = pack2(r, r);
 #pragma unroll
-      for (int j = 0; j < HD; ++j) o[j] *= r;
+      for (int j = 0; j < HD / 2; ++j) o[j] = mul2(o[j], r2);
       m = s;
     }
     const float e = expf(s - m);
     l += e;
+    const f2 e2 = pack2(e, e);
     const float* vr = vs + k * HD;
 #pragma unroll
     for (int j = 0; j < HD / 4; ++j) {
-      const float4 vv = *reinterpret_cast<const float4*>(vr + j * 4);
-      o[j * 4 + 0] = fmaf(e, vv.x, o[j * 4 + 0]);
-      o[j * 4 + 1] = fmaf(e, vv.y, o[j * 4 + 1]);
-      o[j * 4 + 2] = fmaf(e, vv.z, o[j * 4 + 2]);
-      o[j * 4 + 3] = fmaf(e, vv.w, o[j * 4 + 3]);
+      const ulonglong2 vv = *reinterpret_cast<const ulonglong2*>(vr + j * 4);
+      o[2 * j] = fma2(e2, vv.x, o[2 * j]);
+      o[2 * j + 1] = fma2(e2, vv.y, o[2 * j + 1]);
     }
   }
   const float inv = 1.f / l;
   float* orow = p.out + (long long)my_src * p.out_ld + hc;
 #pragma unroll
-  for (int j = 0; j < HD / 4; ++j)
-    *reinterpret_cast<float4*>(orow + j * 4) =
-        make_float4(o[j * 4] * inv, o[j * 4 + 1] * inv, o[j * 4 + 2] * inv, o[j * 4 + 3] * inv);
+  for (int j = 0; j < HD / 4; ++j) {
+    float4 r4;
+    unpack2(o[2 * j], r4.x, r4.y);
+    unpack2(o[2 * j + 1], r4.z, r4.w);
+    r4.x *= inv; r4.y *= inv; r4.z *= inv; r4.w *= inv;
+    *reinterpret_cast<float4*>(orow + j * 4) = r4;
+  }
 }
 
 }  // namespace
@@ -312,14 +339,18 @@ PW_API int pw_window_attention(const float* qkv, int qkv_ld, const float* qkv_bi
   p.scale = scale;
   const int n = ws * ws, tw = 2 * ws - 1;
   const size_t smem = (size_t)(2 * n * HD + tw * tw) * 4 + (size_t)3 * n * 4;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(window_attention_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-  }
   const long long blocks = (long long)b * p.nwin * heads;
   PW_REQUIRE(blocks < (1ll << 31));
-  window_attention_kernel<<<(unsigned)blocks, (n + 31) / 32 * 32, smem, ST>>>(p);
+  const int threads = (n + 31) / 32 * 32;
+  // <= 160 threads (windows up to 12 x 12): four CTAs per SM (96 registers per thread, the
+  // shared-memory carve-out at its maximum); larger windows: 256 threads, two CTAs
+  auto kern = threads <= 160 ? window_attention_kernel<160, 4> : window_attention_kernel<256, 2>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess && smem > 48 * 1024)
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<(unsigned)blocks, threads, smem, ST>>>(p);
   PW_LAUNCH_CHECK(); pw_count_launch(1);
   return 0;
 }
