@@ -582,6 +582,35 @@ int pw_window_attention(const float* qkv, int qkv_ld, const float* qkv_bias,
                         const float* table, float* out, int out_ld, int b, int h, int w,
                         int c, int heads, int ws, int shift, float scale, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Device-side pixel pipeline of PrepareImageInputs
+ * (mmdet3d/datasets/pipelines/loading.py:954-961 img_transform_core: PIL resize,
+ * crop, FLIP_LEFT_RIGHT, rotate; :847-854 mmlabNormalize).  Bit-exact with PIL's
+ * 8-bit fixed-point resampling; the integer tap tables come from
+ * preworld_b200/pixels.py:resample_tables.
+ * ---------------------------------------------------------------------- */
+/* Horizontal pass of Image.resize: tmp[r, x, c] = clip8((2^21 + sum_k src[row0 + r,
+ * first[x] + k, c] * taps[x, k]) >> 22) for r < rows; src uint8 HWC (RGB) with a
+ * row pitch in bytes, tmp uint8 [rows, nw, 3].  identity != 0: nw == w, plain copy
+ * (PIL skips the pass when the width does not change). */
+int pw_resample_rows_u8(const unsigned char* src, long long src_pitch, int h, int w,
+                        int row0, int rows, const int* first, const int* count,
+                        const int* taps, int ksize, int identity, unsigned char* tmp,
+                        int nw, void* stream);
+/* Vertical pass + crop + flip + nearest rotation + imnormalize, evaluated at the
+ * pixels of the final [fh, fw] view: out[c, y, x] = lut[c][v[2 - c]] (lut [3][256] fp32 =
+ * fp32((double(value) - mean[c]) / std[c]-style table of mmcv's imnormalize with to_rgb),
+ * v = pixel (crop_x + gx', crop_y + gy) of the resized [nh, nw] image (0 outside: the
+ * zero fill of Image.crop / Image.rotate), gx' = flip ? fw - 1 - gx : gx, (gx, gy) =
+ * (x, y) or, with affine_fixed (HOST pointer to 6 ints, 16.16 fixed point, as PIL's
+ * nearest-neighbour affine transform walks them; NULL = no rotation),
+ * ((a2 + y a1 + x a0) >> 16, (a5 + y a4 + x a3) >> 16).  out fp32 [3, fh, fw]. */
+int pw_resample_view_norm(const unsigned char* tmp, int row0, int rows, int nw, int nh,
+                          const int* first, const int* count, const int* taps, int ksize,
+                          int identity, int crop_x, int crop_y, int flip,
+                          const int* affine_fixed, const float* lut, float* out, int fh,
+                          int fw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -120,6 +120,10 @@ SIGNATURES = {
     'pw_argmax_geo_zyx_to_xyz': [c_p, c_int, c_int, c_int, c_int, c_p, c_p,
                                  c_int, c_int, c_int, c_p],
     'pw_copy_rows': [c_p, c_ll, c_p, c_ll, c_ll, c_ll, c_p],
+    'pw_resample_rows_u8': [c_p, c_ll, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_int,
+                            c_int, c_p, c_int, c_p],
+    'pw_resample_view_norm': [c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_int, c_int,
+                              c_int, c_int, c_int, c_p, c_p, c_p, c_int, c_int, c_p],
     'pw_layernorm': [c_p, c_int, c_p, c_p, c_f, c_p, c_int, c_ll, c_int, c_p],
     'pw_patch_merge_ln': [c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_f,
                           c_p, c_int, c_p],

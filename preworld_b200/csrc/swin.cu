@@ -342,9 +342,10 @@ PW_API int pw_window_attention(const float* qkv, int qkv_ld, const float* qkv_bi
   const long long blocks = (long long)b * p.nwin * heads;
   PW_REQUIRE(blocks < (1ll << 31));
   const int threads = (n + 31) / 32 * 32;
-  // <= 160 threads (windows up to 12 x 12): four CTAs per SM (96 registers per thread, the
-  // shared-memory carve-out at its maximum); larger windows: 256 threads, two CTAs
-  auto kern = threads <= 160 ? window_attention_kernel<160, 4> : window_attention_kernel<256, 2>;
+  // <= 160 threads (windows up to 12 x 12): three CTAs per SM at 126 registers per thread
+  // (four at 96 registers spill and measured 3 % slower: the kernel is bound by the issue
+  // rate of its FFMA2 / LDS.128 stream, not by occupancy); larger windows: 256 threads
+  auto kern = threads <= 160 ? window_attention_kernel<160, 3> : window_attention_kernel<256, 2>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        (int)cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess && smem > 48 * 1024)
