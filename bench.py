@@ -564,7 +564,8 @@ def main():
     if not args.no_extras and args.config == 'finetune' and args.shard == 'sample':
         k = max(3, min(10, steps))
         if world == 1:
-            for name in ('traj', 'pretrain'):
+            for name in ('traj', 'pretrain', 'shipped'):
+                k = max(3, min(10, steps)) if name != 'shipped' else max(3, min(5, steps))
                 w2 = Workload(name, dev, 2).to_device()
                 r2 = measure(w2, k, 3, barrier, dev, world, dist)
                 _, m2, u2 = CONFIGS[name]
@@ -579,7 +580,7 @@ def main():
                     'config': bench_config(name, 'sample')}
                 if name == 'traj':
                     extras[name]['grids_per_s'] = 7 * extras[name]['value']
-                else:
+                elif name == 'pretrain':
                     extras[name]['samples_per_s'] = extras[name]['value'] / N_RAYS
                 del w2
                 torch.cuda.empty_cache()

@@ -684,6 +684,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
             if (pixi >= 0 && !PW_DBG(128))                     // (128: no output stores)
               *reinterpret_cast<float4*>(const_cast<float*>(yb) + (size_t)pixi * ldo) = o;
           }
+        } else if (vec && a_ == PW_ACT_GELU) {
+          // Swin FFN (fc1 + GELU, 4C wide): the fast path's shape, erff inline.  (In the
+          // opt-in <1, 2> variant this branch costs 140 bytes of extra spill traffic.)
+          const int ldo = p.out_ld;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3);
+            const int pixi = m == 0 ? rowpix[0][i] : rowpix[1][i];
+            const float4 v4 = lds128(stage + (uint32_t)((r * 8 + (ch4 ^ (r & 7))) << 4));
+            float4 o;
+            o.x = pw_activate(fmaf(v4.x, sc[0], bi[0]) + rr[i].x, PW_ACT_GELU);
+            o.y = pw_activate(fmaf(v4.y, sc[1], bi[1]) + rr[i].y, PW_ACT_GELU);
+            o.z = pw_activate(fmaf(v4.z, sc[2], bi[2]) + rr[i].z, PW_ACT_GELU);
+            o.w = pw_activate(fmaf(v4.w, sc[3], bi[3]) + rr[i].w, PW_ACT_GELU);
+            if (pixi >= 0)
+              *reinterpret_cast<float4*>(const_cast<float*>(yb) + (size_t)pixi * ldo) = o;
+          }
         } else {
 #pragma unroll 1
           for (int i = 0; i < 8; ++i) {
@@ -701,13 +718,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a,
               if (cbase + 2 < p.cout) vc += __ldg(rrow + 2);
               if (cbase + 3 < p.cout) vd += __ldg(rrow + 3);
             }
-            if (a_ == PW_ACT_GELU) {                   // Swin FFN (fc1, 4C wide): erff inline
-              va = pw_activate(va, PW_ACT_GELU); vb = pw_activate(vb, PW_ACT_GELU);
-              vc = pw_activate(vc, PW_ACT_GELU); vd = pw_activate(vd, PW_ACT_GELU);
-            } else {
-              va = pw_activate_slow(va, a_); vb = pw_activate_slow(vb, a_);
-              vc = pw_activate_slow(vc, a_); vd = pw_activate_slow(vd, a_);
-            }
+            va = pw_activate_slow(va, a_); vb = pw_activate_slow(vb, a_);
+            vc = pw_activate_slow(vc, a_); vd = pw_activate_slow(vd, a_);
             if (vec) {
               *reinterpret_cast<float4*>(yrow) = make_float4(va, vb, vc, vd);
               continue;
