@@ -163,17 +163,30 @@ def backbone_forward(bb, img):
     return outs
 
 
+def _conv_bn_relu(x, conv, bn, padding):
+    x = F.conv2d(x, conv.weight, None, padding=padding)
+    x = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0., bn.eps)
+    return F.relu(x)
+
+
 def neck_forward(neck, feats):
-    """FPN_LSS without lateral / input_conv / extra_upsample (the shipped configuration)."""
+    """FPN_LSS.forward (lss_fpn.py:83-99) incl. its optional lateral / input_conv / up2
+    branches (the shipped configuration uses none of them)."""
     x2, x1 = feats[neck.input_feature_index[0]], feats[neck.input_feature_index[1]]
+    if getattr(neck, 'lateral', False):
+        x2 = _conv_bn_relu(x2, neck.lateral_conv[0], neck.lateral_conv[1], 0)
     x1 = F.interpolate(x1, scale_factor=neck.up.scale_factor, mode='bilinear',
                        align_corners=True)
     x = torch.cat([x2, x1], dim=1)
-    for conv, bn in ((neck.conv[0], neck.conv[1]), (neck.conv[3], neck.conv[4])):
-        x = F.conv2d(x, conv.weight, None, padding=1)
-        x = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.,
-                         bn.eps)
-        x = F.relu(x)
+    if getattr(neck, 'input_conv', None) is not None:
+        x = _conv_bn_relu(x, neck.input_conv[0], neck.input_conv[1], 0)
+    x = _conv_bn_relu(x, neck.conv[0], neck.conv[1], 1)
+    x = _conv_bn_relu(x, neck.conv[3], neck.conv[4], 1)
+    if getattr(neck, 'extra_upsample', False):
+        x = F.interpolate(x, scale_factor=neck.up2[0].scale_factor, mode='bilinear',
+                          align_corners=True)
+        x = _conv_bn_relu(x, neck.up2[1], neck.up2[2], 1)
+        x = F.conv2d(x, neck.up2[4].weight, neck.up2[4].bias)
     return x
 
 

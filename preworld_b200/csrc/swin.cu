@@ -13,6 +13,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/preworld_b200.h"
 
@@ -168,23 +169,11 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b) {
   return r;
 }
 
-// q . k over the 32 channels of a head: four independent fmaf chains (two packed
-// accumulators; a single 32-long chain is latency bound at ~5 warps per scheduler)
-__device__ __forceinline__ float dot32(const f2 (&q)[HD / 2], const float* k) {
-  f2 a0 = 0ull, a1 = 0ull;                                   // (+0.f, +0.f)
-#pragma unroll
-  for (int j = 0; j < HD / 4; ++j) {
-    const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(k + j * 4);
-    a0 = fma2(q[2 * j], kv.x, a0);
-    a1 = fma2(q[2 * j + 1], kv.y, a1);
-  }
-  float s0, s1, s2, s3;
-  unpack2(a0, s0, s1);
-  unpack2(a1, s2, s3);
-  return (s0 + s1) + (s2 + s3);
-}
-
-template <int MAXT, int MINB>
+// NQ = queries per thread.  With two queries a K / V row fetched from shared memory feeds
+// twice the arithmetic (one LDS.128 per four FFMA2 instead of per two) and every thread
+// carries two independent dependency chains: at 126 registers per thread the one-query form
+// ran with half of its issue slots idle (profiles/r02g_attention.md).
+template <int MAXT, int MINB, int NQ>
 __global__ void __launch_bounds__(MAXT, MINB) window_attention_kernel(const AttnParams p) {
   extern __shared__ __align__(16) float smem[];
   const int n = p.ws * p.ws;
@@ -202,24 +191,22 @@ __global__ void __launch_bounds__(MAXT, MINB) window_attention_kernel(const Attn
   const int wy = win / p.nwx, wx = win % p.nwx;
   const int t = threadIdx.x;
 
-  int my_src = -1, my_id = 0, my_base = 0;
-  if (t < n) {
-    const int iy = t / p.ws, ix = t - iy * p.ws;
+  for (int tok = t; tok < n; tok += blockDim.x) {
+    const int iy = tok / p.ws, ix = tok - iy * p.ws;
     const int py = wy * p.ws + iy, px = wx * p.ws + ix;
     int sy = py + p.shift, sx = px + p.shift;
     sy -= sy >= p.hp ? p.hp : 0;
     sx -= sx >= p.wp ? p.wp : 0;
-    my_src = (sy < p.h && sx < p.w) ? (b * p.h + sy) * p.w + sx : -1;
+    int id = 0;
     if (p.shift > 0) {
       // img_mask regions of swin.py:381-391 (slices 0:-ws, -ws:-shift, -shift:)
       const int hr = py < p.hp - p.ws ? 0 : (py < p.hp - p.shift ? 1 : 2);
       const int wr = px < p.wp - p.ws ? 0 : (px < p.wp - p.shift ? 1 : 2);
-      my_id = hr * 3 + wr;
+      id = hr * 3 + wr;
     }
-    my_base = (iy + p.ws - 1) * tw + ix + p.ws - 1;
-    src[t] = my_src;
-    koff[t] = iy * tw + ix;
-    kid[t] = my_id;
+    src[tok] = (sy < p.h && sx < p.w) ? (b * p.h + sy) * p.w + sx : -1;
+    koff[tok] = iy * tw + ix;
+    kid[tok] = id;
   }
   for (int i = t; i < tw * tw; i += blockDim.x) tab[i] = __ldg(p.table + head * tw * tw + i);
   __syncthreads();
@@ -242,16 +229,31 @@ __global__ void __launch_bounds__(MAXT, MINB) window_attention_kernel(const Attn
     *reinterpret_cast<float4*>(vs + tok * HD + j) = vv;
   }
   __syncthreads();
-  if (my_src < 0) return;            // padding rows are cropped (swin.py:421-422); t >= n
 
-  f2 q[HD / 2];
-  {
-    const float* row = p.qkv + (long long)my_src * p.qkv_ld + hc;
+  // this thread's queries: t, t + stride, ... (padding rows are cropped, swin.py:421-422)
+  const int stride = (n + NQ - 1) / NQ;
+  int my_src[NQ], my_id[NQ], my_base[NQ];
+  bool any = false;
+#pragma unroll
+  for (int r = 0; r < NQ; ++r) {
+    const int qi = t + r * stride;
+    const bool ok = t < stride && qi < n;
+    my_src[r] = ok ? src[qi] : -1;
+    my_id[r] = ok ? kid[qi] : 0;
+    my_base[r] = ok ? koff[qi] + (p.ws - 1) * tw + p.ws - 1 : (p.ws - 1) * tw + p.ws - 1;
+    any = any || my_src[r] >= 0;
+  }
+  if (!any) return;
+
+  f2 q[NQ][HD / 2];
+#pragma unroll
+  for (int r = 0; r < NQ; ++r) {
+    const float* row = p.qkv + (long long)max(my_src[r], 0) * p.qkv_ld + hc;
 #pragma unroll
     for (int j = 0; j < HD / 4; ++j) {
       const float4 v4 = pw_ldg4(row + j * 4);
-      q[2 * j] = pack2(v4.x * p.scale, v4.y * p.scale);     // q = q * self.scale (swin.py:272)
-      q[2 * j + 1] = pack2(v4.z * p.scale, v4.w * p.scale);
+      q[r][2 * j] = pack2(v4.x * p.scale, v4.y * p.scale);  // q = q * self.scale (swin.py:272)
+      q[r][2 * j + 1] = pack2(v4.z * p.scale, v4.w * p.scale);
     }
   }
   // One pass over the keys with a running reference m (online softmax).  m is only moved
@@ -262,42 +264,76 @@ __global__ void __launch_bounds__(MAXT, MINB) window_attention_kernel(const Attn
   // 9 % of the kernel's stall samples with a strict running maximum.
   constexpr float RESCALE_SLACK = 8.f;
   const bool masked = p.shift > 0;
-  f2 o[HD / 2];
+  f2 o[NQ][HD / 2];
+  float m[NQ], l[NQ];
 #pragma unroll
-  for (int j = 0; j < HD / 2; ++j) o[j] = 0ull;
-  float m = -INFINITY, l = 0.f;
+  for (int r = 0; r < NQ; ++r) {
+    m[r] = -INFINITY;
+    l[r] = 0.f;
+#pragma unroll
+    for (int j = 0; j < HD / 2; ++j) o[r][j] = 0ull;
+  }
 #pragma unroll 2
   for (int k = 0; k < n; ++k) {
-    float s = dot32(q, ks + k * HD) + tab[my_base - koff[k]];
-    if (masked && kid[k] != my_id) s += -100.f;
-    if (s > m + RESCALE_SLACK) {
-      const float r = expf(m - s);              // first key: exp(-inf) = 0
-      l *= r;
-      const f2 r2 = pack2(r, r);
+    // q . k: four independent chains per query (two packed accumulators each)
+    f2 a0[NQ], a1[NQ];
 #pragma unroll
-      for (int j = 0; j < HD / 2; ++j) o[j] = mul2(o[j], r2);
-      m = s;
+    for (int r = 0; r < NQ; ++r) a0[r] = a1[r] = 0ull;
+    const float* kr = ks + k * HD;
+#pragma unroll
+    for (int j = 0; j < HD / 4; ++j) {
+      const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(kr + j * 4);
+#pragma unroll
+      for (int r = 0; r < NQ; ++r) {
+        a0[r] = fma2(q[r][2 * j], kv.x, a0[r]);
+        a1[r] = fma2(q[r][2 * j + 1], kv.y, a1[r]);
+      }
     }
-    const float e = expf(s - m);
-    l += e;
-    const f2 e2 = pack2(e, e);
+    const int ko = koff[k], ki = kid[k];
+    f2 e2[NQ];
+#pragma unroll
+    for (int r = 0; r < NQ; ++r) {
+      float s0, s1, s2, s3;
+      unpack2(a0[r], s0, s1);
+      unpack2(a1[r], s2, s3);
+      float s = ((s0 + s1) + (s2 + s3)) + tab[my_base[r] - ko];
+      if (masked && ki != my_id[r]) s += -100.f;
+      if (s > m[r] + RESCALE_SLACK) {
+        const float rs = expf(m[r] - s);          // first key: exp(-inf) = 0
+        l[r] *= rs;
+        const f2 r2 = pack2(rs, rs);
+#pragma unroll
+        for (int j = 0; j < HD / 2; ++j) o[r][j] = mul2(o[r][j], r2);
+        m[r] = s;
+      }
+      const float e = expf(s - m[r]);
+      l[r] += e;
+      e2[r] = pack2(e, e);
+    }
     const float* vr = vs + k * HD;
 #pragma unroll
     for (int j = 0; j < HD / 4; ++j) {
       const ulonglong2 vv = *reinterpret_cast<const ulonglong2*>(vr + j * 4);
-      o[2 * j] = fma2(e2, vv.x, o[2 * j]);
-      o[2 * j + 1] = fma2(e2, vv.y, o[2 * j + 1]);
+#pragma unroll
+      for (int r = 0; r < NQ; ++r) {
+        o[r][2 * j] = fma2(e2[r], vv.x, o[r][2 * j]);
+        o[r][2 * j + 1] = fma2(e2[r], vv.y, o[r][2 * j + 1]);
+      }
     }
   }
-  const float inv = 1.f / l;
-  float* orow = p.out + (long long)my_src * p.out_ld + hc;
 #pragma unroll
-  for (int j = 0; j < HD / 4; ++j) {
-    float4 r4;
-    unpack2(o[2 * j], r4.x, r4.y);
-    unpack2(o[2 * j + 1], r4.z, r4.w);
-    r4.x *= inv; r4.y *= inv; r4.z *= inv; r4.w *= inv;
-    *reinterpret_cast<float4*>(orow + j * 4) = r4;
+  for (int r = 0; r < NQ; ++r) {
+    if (my_src[r] < 0) continue;
+    const float inv = 1.f / l[r];
+    float* orow = p.out + (long long)my_src[r] * p.out_ld + hc;
+#pragma unroll
+    for (int j = 0; j < HD / 4; ++j) {
+      float4 r4;
+      unpack2(o[r][2 * j], r4.x, r4.y);
+      unpack2(o[r][2 * j + 1], r4.z, r4.w);
+      r4.x *= inv; r4.y *= inv; r4.z *= inv; r4.w *= inv;
+      *reinterpret_cast<float4*>(orow + j * 4) = r4;
+    }
   }
 }
 
@@ -345,11 +381,14 @@ PW_API int pw_window_attention(const float* qkv, int qkv_ld, const float* qkv_bi
   const size_t smem = (size_t)(2 * n * HD + tw * tw) * 4 + (size_t)3 * n * 4;
   const long long blocks = (long long)b * p.nwin * heads;
   PW_REQUIRE(blocks < (1ll << 31));
-  const int threads = (n + 31) / 32 * 32;
-  // <= 160 threads (windows up to 12 x 12): three CTAs per SM at 126 registers per thread
-  // (four at 96 registers spill and measured 3 % slower: the kernel is bound by the issue
-  // rate of its FFMA2 / LDS.128 stream, not by occupancy); larger windows: 256 threads
-  auto kern = threads <= 160 ? window_attention_kernel<160, 3> : window_attention_kernel<256, 2>;
+  // two queries per thread (windows up to 14 x 14): 96 threads for the 144 tokens of a
+  // 12 x 12 window; PW_ATTN_NQ=1 selects the one-query form (experiments)
+  static const int nq_env = [] { const char* e = getenv("PW_ATTN_NQ"); return e ? atoi(e) : 2; }();
+  const int nq = (nq_env == 1 || n > 192) ? 1 : 2;
+  const int threads = ((n + nq - 1) / nq + 31) / 32 * 32;
+  auto kern = nq == 2 ? window_attention_kernel<96, 3, 2>
+                      : (threads <= 160 ? window_attention_kernel<160, 3, 1>
+                                        : window_attention_kernel<256, 2, 1>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        (int)cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess && smem > 48 * 1024)

@@ -159,3 +159,21 @@ def test_shipped_config_routes_agree():
         assert (a[k][0] == b[k][0]).all(), k
         assert (a[k][0] == c[k][0]).all() and (a[k][0] == c2[k][0]).all(), k
 
+
+
+def test_fpn_lss_optional_branches_match_oracle():
+    """lateral + input_conv + extra upsampling (up2) of FPN_LSS against the restatement
+    (pinned to the reference class by tests/test_oracle.py)."""
+    cfg = dict(in_channels=128 + 256, out_channels=32, scale_factor=2, input_feature_index=(0, 1),
+               extra_upsample=2, lateral=128, use_input_conv=True)
+    neck = plugin.build_neck(dict(type='FPN_LSS', **cfg)).eval()
+    swin_ref.seeded_init_(neck, 4)
+    neck = neck.to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    feats = [torch.randn((2, 6, 10, 128), device=DEV, generator=g).permute(0, 3, 1, 2),
+             torch.randn((2, 3, 5, 256), device=DEV, generator=g).permute(0, 3, 1, 2)]
+    with torch.no_grad():
+        got = neck(feats)
+        want = swin_ref.neck_forward(neck.double(), [f.double() for f in feats])
+    assert got.shape == want.shape == (2, 32, 12, 20)
+    assert _rel(got.double(), want) <= 1e-5
