@@ -169,10 +169,8 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b) {
   return r;
 }
 
-// NQ = queries per thread.  With two queries a K / V row fetched from shared memory feeds
-// twice the arithmetic (one LDS.128 per four FFMA2 instead of per two) and every thread
-// carries two independent dependency chains: at 126 registers per thread the one-query form
-// ran with half of its issue slots idle (profiles/r02g_attention.md).
+// NQ = queries per thread (1 in production; 2 is an experiment kept for the record, see the
+// launcher).
 template <int MAXT, int MINB, int NQ>
 __global__ void __launch_bounds__(MAXT, MINB) window_attention_kernel(const AttnParams p) {
   extern __shared__ __align__(16) float smem[];
@@ -381,10 +379,12 @@ PW_API int pw_window_attention(const float* qkv, int qkv_ld, const float* qkv_bi
   const size_t smem = (size_t)(2 * n * HD + tw * tw) * 4 + (size_t)3 * n * 4;
   const long long blocks = (long long)b * p.nwin * heads;
   PW_REQUIRE(blocks < (1ll << 31));
-  // two queries per thread (windows up to 14 x 14): 96 threads for the 144 tokens of a
-  // 12 x 12 window; PW_ATTN_NQ=1 selects the one-query form (experiments)
-  static const int nq_env = [] { const char* e = getenv("PW_ATTN_NQ"); return e ? atoi(e) : 2; }();
-  const int nq = (nq_env == 1 || n > 192) ? 1 : 2;
+  // One query per thread.  PW_ATTN_NQ=2 selects two queries per thread (96 threads for the
+  // 144 tokens of a 12 x 12 window, one LDS.128 per four FFMA2): bit-identical results,
+  // measured 19 % SLOWER (1071 vs 897 us at stage 0 of Swin-B) -- a quarter of the lanes of
+  // its third warp idle and 168 registers per thread leave 9 warps per SM.
+  static const int nq_env = [] { const char* e = getenv("PW_ATTN_NQ"); return e ? atoi(e) : 1; }();
+  const int nq = (nq_env == 2 && n <= 192) ? 2 : 1;
   const int threads = ((n + nq - 1) / nq + 31) / 32 * 32;
   auto kern = nq == 2 ? window_attention_kernel<96, 3, 2>
                       : (threads <= 160 ? window_attention_kernel<160, 3, 1>
