@@ -103,7 +103,8 @@ class PackedConv:
     """Weights of one conv/linear in the kernel's layout: w [K, w_ld] with
     K = taps*cin_pad (tap-major), plus the folded per-channel affine."""
     __slots__ = ('w', 'scale', 'bias', 'cin', 'cout', 'k', 'stride', 'pad',
-                 'dil', 'w_ld', 'wt_hi', 'wt_lo', 'wf_hi', 'wf_lo')
+                 'dil', 'w_ld', 'wt_hi', 'wt_lo', 'wf_hi', 'wf_lo', 'src',
+                 'collapsed')
 
     def __init__(self, weight, bias=None, bn=None, stride=1, padding=0,
                  dilation=1, in_scale=None, in_shift=None, eps=None,
@@ -123,6 +124,10 @@ class PackedConv:
         elif w.dim() == 4:
             w = w[:, :, None]
         assert w.dim() == 5
+        # what collapse_axes() rebuilds a narrower conv from (references, no copies)
+        self.src = None if (spatial_perm is not None or in_scale is not None) else \
+            (w, bias, bn, len(tuple(weight.shape)), cin_pad, cout_pad)
+        self.collapsed = {}
         if spatial_perm is not None:
             w = w.permute(0, 1, *[2 + p for p in spatial_perm])
         if cin_pad or cout_pad:
@@ -187,6 +192,34 @@ class PackedConv:
             self.dil = tuple(self.dil[p] for p in spatial_perm)
 
 
+    def collapse_axes(self, spatial):
+        """A dilated 'same' conv whose dilation is at least the input extent along an axis
+        only ever sees zero padding through its off-centre taps there (ASPP's dilation-18
+        branch on a 16-row map, view_transformer.py:355-418): the conv with that axis
+        reduced to its centre tap gives the same sums with a third of the taps and a halo
+        that fits the tensor-core kernel's shared memory.  -> the narrower PackedConv for an
+        input of spatial extent ``spatial`` (d, h, w), or self."""
+        if self.src is None:
+            return self
+        axes = tuple(i for i in range(3)
+                     if self.k[i] > 1 and self.k[i] % 2 == 1 and self.stride[i] == 1
+                     and self.pad[i] == self.dil[i] * (self.k[i] // 2)
+                     and self.dil[i] >= spatial[i])
+        if not axes:
+            return self
+        if axes not in self.collapsed:
+            w, bias, bn, wdim, cin_pad, cout_pad = self.src
+            pad, dil = list(self.pad), list(self.dil)
+            for i in axes:
+                c = self.k[i] // 2
+                w = w.narrow(2 + i, c, 1)
+                pad[i], dil[i] = 0, 1
+            pc = PackedConv(w.contiguous(), bias, bn, stride=self.stride, padding=tuple(pad),
+                            dilation=tuple(dil), cin_pad=cin_pad, cout_pad=cout_pad)
+            self.collapsed[axes] = pc
+        return self.collapsed[axes]
+
+
     def set_umma_weights(self, wt):
         """wt [cout, K] (K-major, tap-major then cin): pre-split for the
         3xTF32 tensor-core path (pw_conv_umma_fwd)."""
@@ -233,6 +266,8 @@ def conv(x, pc, act=None, residual=None, out=None, act_channels=0,
     spatial = x.shape[1:-1]
     sp = (1,) * (3 - len(spatial)) + tuple(spatial)
     n = x.shape[0]
+    if out_size is None and max(pc.dil) > 1:
+        pc = pc.collapse_axes(sp)
     assert x.shape[-1] == pc.cin, (x.shape, pc.cin)
     o = tuple((sp[i] + 2 * pc.pad[i] - pc.dil[i] * (pc.k[i] - 1) - 1)
               // pc.stride[i] + 1 for i in range(3))
