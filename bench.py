@@ -414,8 +414,9 @@ def run_reference(args, rank, world):
     idx, metric, unit = CONFIGS[args.config]
     if args.config in ('stress', 'shipped'):
         print(json.dumps({'impl': 'reference', 'unavailable':
-                          'config 5 is not timed on the CPU (4 x R101 400x400x16 forwards '
-                          'take minutes each); see --config finetune'}), flush=True)
+                          f'--config {args.config} is not timed on the CPU (4 x R101 400x400x16 / '
+                          '18 x Swin-B 512x1408 forwards take minutes each); see --config '
+                          'finetune'}), flush=True)
         return
     budget = float(os.environ.get('PW_REF_BUDGET_S', '240'))
     t_begin = time.perf_counter()
