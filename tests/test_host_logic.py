@@ -235,3 +235,72 @@ def test_no_cpu_fallback():
     det = build_model(model_cfg('finetune', 'r50', (64, 176)))
     with pytest.raises(NotImplementedError):
         det(return_loss=True)
+
+
+def test_collapse_axes_drops_taps_that_only_see_padding():
+    """PackedConv.collapse_axes: ASPP's dilation-18 3x3 conv on a 16-row map equals the 1x3
+    conv of its centre kernel row (the other rows only read zero padding); a dilation that
+    still reaches valid rows is left alone."""
+    import torch.nn.functional as F
+    from preworld_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(12, 8, 3, 3, generator=g)
+    x = torch.randn(2, 8, 16, 44, generator=g)
+    pc = ops.PackedConv(w, None, None, stride=1, padding=18, dilation=18)
+    col = pc.collapse_axes((1, 16, 44))
+    assert col is not pc and col.k == (1, 1, 3) and col.pad == (0, 0, 18) and col.dil == (1, 1, 18)
+    assert pc.collapse_axes((1, 16, 44)) is col                      # cached
+    want = F.conv2d(x, w, padding=18, dilation=18)
+    got = F.conv2d(x, w[:, :, 1:2, :], padding=(0, 18), dilation=(1, 18))
+    assert torch.allclose(got, want, atol=1e-5)
+    # packed weights of the collapsed conv are the centre row, tap-major
+    assert torch.equal(col.w.view(3, 8, 12), w[:, :, 1, :].permute(2, 1, 0).contiguous())
+    assert pc.collapse_axes((1, 32, 88)) is pc                       # 18 < 32: rows are reachable
+    both = ops.PackedConv(w, None, None, stride=1, padding=18, dilation=18).collapse_axes((1, 16, 16))
+    assert both.k == (1, 1, 1) and both.pad == (0, 0, 0)
+    strided = ops.PackedConv(w, None, None, stride=2, padding=18, dilation=18)
+    assert strided.collapse_axes((1, 16, 44)) is strided
+
+
+def test_swin_init_weights_loads_an_official_checkpoint(tmp_path):
+    """SwinTransformer(pretrained=<official-style checkpoint>).init_weights(): keys renamed,
+    downsample tensors re-ordered to nn.Unfold's channel order (swin.py:25-73, 861-925), and a
+    relative position table of another window size is resampled."""
+    from oracle import swin_ref
+    from preworld_b200.plugin.swin import swin_convert
+    cfg = dict(swin_ref.TINY_SWIN, with_cp=False)
+    donor = plugin.build_backbone(dict(type='SwinTransformer', **cfg))
+    swin_ref.seeded_init_(donor, 21)
+    # our keys -> official names (the inverse of the key part of swin_convert)
+    official = {}
+    for k, v in donor.state_dict().items():
+        if 'relative_position_index' in k:
+            continue
+        k = k.replace('stages', 'layers', 1).replace('attn.w_msa.', 'attn.') \
+            .replace('ffn.layers.0.0.', 'mlp.fc1.').replace('ffn.layers.1.', 'mlp.fc2.') \
+            .replace('patch_embed.projection', 'patch_embed.proj')
+        official[k] = v.clone()
+    official['head.weight'] = torch.zeros(3, 3)
+    path = str(tmp_path / 'swin_official.pth')
+    torch.save({'model': official}, path)
+    bb = plugin.build_backbone(dict(type='SwinTransformer', pretrained=path, **cfg))
+    bb.init_weights()
+    want = swin_convert(official)
+    got = bb.state_dict()
+    assert set(want) <= set(got) and 'head.weight' not in want
+    for k, v in want.items():
+        assert torch.equal(got[k], v), k
+    # the reduction columns really moved (official order != nn.Unfold order)
+    k = 'stages.0.downsample.reduction.weight'
+    assert not torch.equal(got[k], donor.state_dict()[k])
+    # a checkpoint trained with window 4 (7x7 table) -> window 6 (11x11 table)
+    small = dict(cfg, window_size=4)
+    donor4 = plugin.build_backbone(dict(type='SwinTransformer', **small))
+    swin_ref.seeded_init_(donor4, 22)
+    torch.save({'state_dict': {k: v for k, v in donor4.state_dict().items()
+                               if 'relative_position_index' not in k}}, path)
+    bb = plugin.build_backbone(dict(type='SwinTransformer', pretrained=path,
+                                    **dict(cfg, pretrain_style='mmcls')))
+    bb.init_weights()
+    t = bb.state_dict()['stages.1.blocks.0.attn.w_msa.relative_position_bias_table']
+    assert t.shape == (121, 2) and torch.isfinite(t).all() and t.abs().sum() > 0
