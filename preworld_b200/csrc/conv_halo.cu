@@ -963,8 +963,12 @@ HaloPlan search_plan(const pw_conv_desc& in, const int SPLIT_SETS, const int tme
             return halo + (long long)nb_ * b_stage + SMEM_SLACK;
           };
           while (nb > max(2, (SPLIT_SETS + mt - 1) / mt) && smem_need(nh, nb) > smem_limit) --nb;
-          // a multi-chunk conv needs two halo slots (load of chunk c+1 under the
-          // taps of chunk c); if that does not fit, conv_umma.cu takes the layer
+          // a multi-chunk conv wants two halo slots (load of chunk c+1 under the taps of
+          // chunk c); where they do not fit (stride-2 3x3x3 convs: 180 KB per slot) a
+          // one-tile plan runs with ONE slot -- the next chunk's halo then loads after the
+          // current chunk's last tap (protocol checked by tools/halo_protocol_sim.py); still
+          // ahead of conv_umma.cu's per-tap tiles (64 -> 256 k333 s2: 64 TFLOP/s there)
+          if (smem_need(nh, nb) > smem_limit && !persist && nh == 2) nh = 1;
           if (smem_need(nh, nb) > smem_limit) continue;
           while (nh < min(chunks, MAX_RING) && nh * halo_stride < 64 * 1024 &&
                  smem_need(nh + 1, nb) <= smem_limit)
