@@ -335,6 +335,253 @@ __global__ void __launch_bounds__(MAXT, MINB) window_attention_kernel(const Attn
   }
 }
 
+
+// ---- shifted-window attention on the (legacy) tensor-core path ---------------------------
+// Same contract as window_attention_kernel.  CTA = one (window, head), warp = 16 query rows;
+// S = Q K^T and O = P V are mma.sync m16n8k8 TF32 MMAs with the 3xTF32 split on both operands
+// (hi = rna_tf32(x), lo = rna_tf32(x - hi); hi*hi + hi*lo + lo*hi, fp32 accumulation), K and V
+// of the window pre-split once per CTA into shared memory (rows padded to 36 floats: the
+// B-fragment loads of both GEMMs are bank-conflict free), the softmax on the accumulator
+// fragments in registers.  Keys are walked in blocks of 72 (9 n-tiles) with a running row
+// maximum (two blocks for a 12 x 12 window), which keeps the score fragment at 36 registers.
+// The score fragment IS the A fragment of P V: accumulator element (row g, col 2t / 2t+1) of
+// n-tile j becomes A element (row g, k-slot t / t+4) of k-step j when the 8 keys of the
+// group are taken in the order 0,2,4,6,1,3,5,7 -- the V rows of the B fragment are fetched
+// in the same order, no shuffles.
+constexpr int MMA_KB = 9;                     // n-tiles (of 8 keys) per key block
+constexpr int KV_LD = 36;                     // smem row pitch of the K / V tiles, floats
+
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+      "{%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) window_attention_mma_kernel(const AttnParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int n = p.ws * p.ws;
+  const int np = (n + 7) & ~7;                          // keys padded to whole n-tiles
+  const int tw = 2 * p.ws - 1;
+  uint32_t* khi = reinterpret_cast<uint32_t*>(smem);    // [np][36]
+  uint32_t* klo = khi + np * KV_LD;
+  uint32_t* vhi = klo + np * KV_LD;
+  uint32_t* vlo = vhi + np * KV_LD;
+  float* tab = reinterpret_cast<float*>(vlo + np * KV_LD);   // [tw*tw]
+  int* src = reinterpret_cast<int*>(tab + tw * tw);     // [np] pixel index or -1 (padding)
+  int* koff = src + np;                                 // [np]
+  int* kid = koff + np;                                 // [np]
+
+  const int head = blockIdx.x % p.heads;
+  const int win = (blockIdx.x / p.heads) % p.nwin;
+  const int b = blockIdx.x / (p.heads * p.nwin);
+  const int wy = win / p.nwx, wx = win % p.nwx;
+  const int tid = threadIdx.x;
+
+  for (int tok = tid; tok < np; tok += blockDim.x) {
+    int s_ = -1, ko = 0, id = -1;
+    if (tok < n) {
+      const int iy = tok / p.ws, ix = tok - iy * p.ws;
+      const int py = wy * p.ws + iy, px = wx * p.ws + ix;
+      int sy = py + p.shift, sx = px + p.shift;
+      sy -= sy >= p.hp ? p.hp : 0;
+      sx -= sx >= p.wp ? p.wp : 0;
+      id = 0;
+      if (p.shift > 0) {
+        const int hr = py < p.hp - p.ws ? 0 : (py < p.hp - p.shift ? 1 : 2);
+        const int wr = px < p.wp - p.ws ? 0 : (px < p.wp - p.shift ? 1 : 2);
+        id = hr * 3 + wr;
+      }
+      s_ = (sy < p.h && sx < p.w) ? (b * p.h + sy) * p.w + sx : -1;
+      ko = iy * tw + ix;
+    }
+    src[tok] = s_; koff[tok] = ko; kid[tok] = id;
+  }
+  for (int i = tid; i < tw * tw; i += blockDim.x) tab[i] = __ldg(p.table + head * tw * tw + i);
+  __syncthreads();
+  const int hc = head * HD;
+  for (int i = tid; i < np * (HD / 4); i += blockDim.x) {
+    const int tok = i >> 3, j = (i & 7) * 4;
+    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    if (tok < n) {
+      const int s_ = src[tok];
+      if (s_ >= 0) {
+        const float* row = p.qkv + (long long)s_ * p.qkv_ld + hc + j;
+        kv = pw_ldg4(row + p.c);
+        vv = pw_ldg4(row + 2 * p.c);
+      } else if (p.qkv_bias) {
+        kv = pw_ldg4(p.qkv_bias + p.c + hc + j);
+        vv = pw_ldg4(p.qkv_bias + 2 * p.c + hc + j);
+      }
+    }
+    const float kf[4] = {kv.x, kv.y, kv.z, kv.w}, vf[4] = {vv.x, vv.y, vv.z, vv.w};
+    uint4 kh, kl, vh, vl;
+    uint32_t* khp = &kh.x; uint32_t* klp = &kl.x; uint32_t* vhp = &vh.x; uint32_t* vlp = &vl.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      khp[e] = tf32_rna(kf[e]);
+      klp[e] = tf32_rna(kf[e] - __uint_as_float(khp[e]));
+      vhp[e] = tf32_rna(vf[e]);
+      vlp[e] = tf32_rna(vf[e] - __uint_as_float(vhp[e]));
+    }
+    *reinterpret_cast<uint4*>(khi + tok * KV_LD + j) = kh;
+    *reinterpret_cast<uint4*>(klo + tok * KV_LD + j) = kl;
+    *reinterpret_cast<uint4*>(vhi + tok * KV_LD + j) = vh;
+    *reinterpret_cast<uint4*>(vlo + tok * KV_LD + j) = vl;
+  }
+  __syncthreads();
+
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = warp * 16 + g, q1 = q0 + 8;            // this thread's two query rows
+  const int src0 = q0 < n ? src[q0] : -1, src1 = q1 < n ? src[q1] : -1;
+  // a warp whose 16 rows are all padding (or beyond the window) has nothing to store
+  if (__ballot_sync(0xffffffffu, src0 >= 0 || src1 >= 0) == 0u) return;
+  const int base0 = (q0 < n ? koff[q0] : 0) + (p.ws - 1) * tw + p.ws - 1;
+  const int base1 = (q1 < n ? koff[q1] : 0) + (p.ws - 1) * tw + p.ws - 1;
+  const int id0 = q0 < n ? kid[q0] : -2, id1 = q1 < n ? kid[q1] : -2;
+  const bool masked = p.shift > 0;
+
+  // Q fragments (4 k-steps of 8 channels), scaled, split hi / lo
+  uint32_t qh[4][4], ql[4][4];
+  {
+    const float* r0 = p.qkv + (long long)max(src0, 0) * p.qkv_ld + hc;
+    const float* r1 = p.qkv + (long long)max(src1, 0) * p.qkv_ld + hc;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const float v[4] = {__ldg(r0 + ks * 8 + t) * p.scale, __ldg(r1 + ks * 8 + t) * p.scale,
+                          __ldg(r0 + ks * 8 + t + 4) * p.scale,
+                          __ldg(r1 + ks * 8 + t + 4) * p.scale};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        qh[ks][e] = tf32_rna(v[e]);
+        ql[ks][e] = tf32_rna(v[e] - __uint_as_float(qh[ks][e]));
+      }
+    }
+  }
+  float o[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[nt][e] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  const int ntiles = np >> 3;
+  for (int kb = 0; kb < ntiles; kb += MMA_KB) {
+    const int nb = min(MMA_KB, ntiles - kb);             // n-tiles of this key block
+    float sc[MMA_KB][4];
+#pragma unroll
+    for (int j = 0; j < MMA_KB; ++j) {
+      sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+      if (j < nb) {
+        const int key = (kb + j) * 8 + g;                // B fragment: n = g, k = t / t + 4
+        const uint32_t* kh_ = khi + key * KV_LD + t;
+        const uint32_t* kl_ = klo + key * KV_LD + t;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t bh0 = kh_[ks * 8], bh1 = kh_[ks * 8 + 4];
+          const uint32_t bl0 = kl_[ks * 8], bl1 = kl_[ks * 8 + 4];
+          mma_tf32(sc[j], ql[ks], bh0, bh1);
+          mma_tf32(sc[j], qh[ks], bl0, bl1);
+          mma_tf32(sc[j], qh[ks], bh0, bh1);
+        }
+      }
+    }
+    // relative position bias, shift mask, padded key columns; block row maxima
+    float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MMA_KB; ++j) {
+      if (j < nb) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = (kb + j) * 8 + 2 * t + e;
+          const int ko = koff[key], ki = kid[key];
+          float s0 = sc[j][e] + tab[base0 - ko], s1 = sc[j][2 + e] + tab[base1 - ko];
+          if (masked && ki != id0) s0 += -100.f;
+          if (masked && ki != id1) s1 += -100.f;
+          if (key >= n) { s0 = -INFINITY; s1 = -INFINITY; }
+          sc[j][e] = s0; sc[j][2 + e] = s1;
+          bm0 = fmaxf(bm0, s0); bm1 = fmaxf(bm1, s1);
+        }
+      }
+    }
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
+    const float r0 = expf(m0 - mn0), r1 = expf(m1 - mn1);       // first block: exp(-inf) = 0
+    m0 = mn0; m1 = mn1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < MMA_KB; ++j) {
+      if (j < nb) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float e0 = expf(sc[j][e] - mn0), e1 = expf(sc[j][2 + e] - mn1);
+          sc[j][e] = e0; sc[j][2 + e] = e1;
+          rs0 += e0; rs1 += e1;
+        }
+      }
+    }
+    rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1);
+    rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+    rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1);
+    rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+    l0 = l0 * r0 + rs0;
+    l1 = l1 * r1 + rs1;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      o[nt][0] *= r0; o[nt][1] *= r0; o[nt][2] *= r1; o[nt][3] *= r1;
+    }
+    // O += P V: k-step j = the 8 keys of n-tile j in the order 0,2,4,6,1,3,5,7
+#pragma unroll
+    for (int j = 0; j < MMA_KB; ++j) {
+      if (j < nb) {
+        uint32_t ph[4], pl[4];
+        const float pv[4] = {sc[j][0], sc[j][2], sc[j][1], sc[j][3]};   // a0 a1 a2 a3
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ph[e] = tf32_rna(pv[e]);
+          pl[e] = tf32_rna(pv[e] - __uint_as_float(ph[e]));
+        }
+        const int key0 = (kb + j) * 8 + 2 * t;            // B fragment: k = t -> key 2t, t+4 -> 2t+1
+        const uint32_t* vh_ = vhi + key0 * KV_LD + g;
+        const uint32_t* vl_ = vlo + key0 * KV_LD + g;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const uint32_t bh0 = vh_[nt * 8], bh1 = vh_[KV_LD + nt * 8];
+          const uint32_t bl0 = vl_[nt * 8], bl1 = vl_[KV_LD + nt * 8];
+          mma_tf32(o[nt], pl, bh0, bh1);
+          mma_tf32(o[nt], ph, bl0, bl1);
+          mma_tf32(o[nt], ph, bh0, bh1);
+        }
+      }
+    }
+  }
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  if (src0 >= 0) {
+    float* orow = p.out + (long long)src0 * p.out_ld + hc + 2 * t;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      *reinterpret_cast<float2*>(orow + nt * 8) = make_float2(o[nt][0] * i0, o[nt][1] * i0);
+  }
+  if (src1 >= 0) {
+    float* orow = p.out + (long long)src1 * p.out_ld + hc + 2 * t;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      *reinterpret_cast<float2*>(orow + nt * 8) = make_float2(o[nt][2] * i1, o[nt][3] * i1);
+  }
+}
+
 }  // namespace
 
 PW_API int pw_layernorm(const float* x, int x_ld, const float* gamma, const float* beta,
@@ -379,6 +626,26 @@ PW_API int pw_window_attention(const float* qkv, int qkv_ld, const float* qkv_bi
   const size_t smem = (size_t)(2 * n * HD + tw * tw) * 4 + (size_t)3 * n * 4;
   const long long blocks = (long long)b * p.nwin * heads;
   PW_REQUIRE(blocks < (1ll << 31));
+  // Tensor-core path (mma.sync TF32, 3xTF32 split): PW_ATTN_MMA=0 selects the fp32 SIMT kernel
+  static const int mma_env = [] { const char* e = getenv("PW_ATTN_MMA"); return e ? atoi(e) : 1; }();
+  if (mma_env != 0) {
+    const int np = (n + 7) & ~7;
+    const size_t smem_m = (size_t)(4 * np * KV_LD + tw * tw) * 4 + (size_t)3 * np * 4;
+    const int warps = (n + 15) / 16;
+    // windows up to 12 x 12 (9 warps): two CTAs per SM at 112 registers per thread
+    // (PW_ATTN_MMA=2: one CTA per SM, 128 registers); larger windows: up to 16 warps
+    auto km = warps * 32 <= 288 ? (mma_env == 2 ? window_attention_mma_kernel<288, 1>
+                                                : window_attention_mma_kernel<288, 2>)
+                                : window_attention_mma_kernel<512, 1>;
+    cudaError_t em = cudaFuncSetAttribute(km, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          (int)cudaSharedmemCarveoutMaxShared);
+    if (em == cudaSuccess)
+      em = cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
+    if (em != cudaSuccess) return (int)em;
+    km<<<(unsigned)blocks, warps * 32, smem_m, ST>>>(p);
+    PW_LAUNCH_CHECK(); pw_count_launch(1);
+    return 0;
+  }
   // One query per thread.  PW_ATTN_NQ=2 selects two queries per thread (96 threads for the
   // 144 tokens of a 12 x 12 window, one LDS.128 per four FFMA2): bit-identical results,
   // measured 19 % SLOWER (1071 vs 897 us at stage 0 of Swin-B) -- a quarter of the lanes of
