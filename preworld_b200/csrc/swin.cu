@@ -627,7 +627,9 @@ PW_API int pw_window_attention(const float* qkv, int qkv_ld, const float* qkv_bi
   const long long blocks = (long long)b * p.nwin * heads;
   PW_REQUIRE(blocks < (1ll << 31));
   // Tensor-core path (mma.sync TF32, 3xTF32 split): PW_ATTN_MMA=0 selects the fp32 SIMT kernel
-  static const int mma_env = [] { const char* e = getenv("PW_ATTN_MMA"); return e ? atoi(e) : 1; }();
+  // (read per call, not cached: the tests switch variants inside one process)
+  const char* mma_s = getenv("PW_ATTN_MMA");
+  const int mma_env = mma_s ? atoi(mma_s) : 1;
   if (mma_env != 0) {
     const int np = (n + 7) & ~7;
     const size_t smem_m = (size_t)(4 * np * KV_LD + tw * tw) * 4 + (size_t)3 * np * 4;
@@ -650,7 +652,8 @@ PW_API int pw_window_attention(const float* qkv, int qkv_ld, const float* qkv_bi
   // 144 tokens of a 12 x 12 window, one LDS.128 per four FFMA2): bit-identical results,
   // measured 19 % SLOWER (1071 vs 897 us at stage 0 of Swin-B) -- a quarter of the lanes of
   // its third warp idle and 168 registers per thread leave 9 warps per SM.
-  static const int nq_env = [] { const char* e = getenv("PW_ATTN_NQ"); return e ? atoi(e) : 1; }();
+  const char* nq_s = getenv("PW_ATTN_NQ");
+  const int nq_env = nq_s ? atoi(nq_s) : 1;
   const int nq = (nq_env == 2 && n <= 192) ? 2 : 1;
   const int threads = ((n + nq - 1) / nq + 31) / 32 * 32;
   auto kern = nq == 2 ? window_attention_kernel<96, 3, 2>

@@ -63,8 +63,17 @@ ATTN_CASES = [
 ]
 
 
+# the production kernel (mma.sync TF32, 3xTF32) and the fp32 SIMT kernels it replaced
+ATTN_VARIANTS = {'mma': {'PW_ATTN_MMA': '1'}, 'mma_1cta': {'PW_ATTN_MMA': '2'},
+                 'simt': {'PW_ATTN_MMA': '0', 'PW_ATTN_NQ': '1'},
+                 'simt_2q': {'PW_ATTN_MMA': '0', 'PW_ATTN_NQ': '2'}}
+
+
+@pytest.mark.parametrize('variant', sorted(ATTN_VARIANTS))
 @pytest.mark.parametrize('b,h,w,heads,ws,shift', ATTN_CASES)
-def test_window_attention_matches_oracle(b, h, w, heads, ws, shift):
+def test_window_attention_matches_oracle(b, h, w, heads, ws, shift, variant, monkeypatch):
+    for k, v in ATTN_VARIANTS[variant].items():
+        monkeypatch.setenv(k, v)
     c = heads * 32
     attn = pswin.ShiftWindowMSA(c, heads, ws, shift).to(DEV)
     swin_ref.seeded_init_(attn, 9)
