@@ -254,7 +254,7 @@ class Sim:
             f()
 
 
-def planner_allows(sets, mt, T, chunks, nh, nb):
+def planner_allows(sets, mt, T, chunks, nh, nb, tiles=1):
     """The ring-depth rules make_plan_uncached() enforces (conv_halo.cu)."""
     if T * chunks > 1 and nb < 2:
         return False
@@ -262,11 +262,7 @@ def planner_allows(sets, mt, T, chunks, nh, nb):
         return False
     # one-tile plans may fall back to ONE halo slot when two do not fit (stride-2 3x3x3 convs:
     # the next chunk's halo then loads after the last tap of the current one, not under it)
-    return nh >= 1 if tiles_one(sets) else nh >= min(chunks, 2)
-
-
-def tiles_one(_sets):
-    return True
+    return nh >= 1 if tiles == 1 else nh >= 2
 
 
 def sweep(sets_list=(2, 3, 4), n=10, seed=0, fixed=True, only_allowed=True, tiles=1):
@@ -276,7 +272,7 @@ def sweep(sets_list=(2, 3, 4), n=10, seed=0, fixed=True, only_allowed=True, tile
     for sets, mt, T, chunks, nb in itertools.product(sets_list, (1, 2), (1, 2, 9, 27),
                                                      (1, 2, 3, 5, 8), (2, 3, 4, 6)):
         for nh in ({1, min(chunks, 2), min(chunks, 3)} if tiles == 1 else {2, 3}):
-            if only_allowed and not planner_allows(sets, mt, T, chunks, nh, nb):
+            if only_allowed and not planner_allows(sets, mt, T, chunks, nh, nb, tiles):
                 continue
             for _ in range(n):
                 cases += 1
