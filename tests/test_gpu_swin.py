@@ -60,6 +60,8 @@ ATTN_CASES = [
     (1, 2, 6, 8, 6, 3),            # map smaller than a window (tiny stage 4)
     (3, 7, 9, 2, 7, 3),            # window 7 (Swin-T/S)
     (1, 13, 31, 1, 12, 0),         # padding without shift
+    (1, 20, 33, 2, 16, 8),         # window 16: 256 tokens, 16 warps, four key blocks (9+9+9+5 tiles)
+    (2, 9, 14, 1, 9, 4),           # window 9: 81 tokens -> 88 padded key columns, two key blocks
 ]
 
 
